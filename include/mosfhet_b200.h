@@ -1,0 +1,216 @@
+/*
+ * mosfhet_b200.h -- C ABI of libmosfhet_b200.so
+ *
+ * B200 (sm_100a) implementation of MOSFHET's programmable-bootstrap hot path, exported
+ *   (1) under the reference's own symbol names and signatures, so that the library is a drop-in
+ *       for that path when it is linked / LD_PRELOADed ahead of libmosfhet.so, and
+ *   (2) as new batched entry points over arrays of ciphertext handles, and
+ *   (3) as a flat (plain pointers + sizes) API for device-resident pipelines and other-language
+ *       bindings (ctypes, cgo, JNI).
+ *
+ * There is NO CPU fallback: every compute entry point aborts with a message on stderr if no
+ * CUDA device / kernel image is available (the reference's own error style: assert()/exit(),
+ * mosfhet.h has no return codes -- see /root/reference/src/misc.c:104-128).
+ *
+ * Reference interface citations are "mosfhet.h:<line>" = /root/reference/include/mosfhet.h.
+ */
+#ifndef MOSFHET_B200_H
+#define MOSFHET_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Ciphertext / key handle types.  A caller that already includes the reference's <mosfhet.h>
+ * defines MOSFHET_B200_USE_REFERENCE_TYPES before including this file; otherwise the
+ * ABI-identical definitions below are used (same member order, widths and pointer depth as
+ * mosfhet.h:22-133; 64-bit torus only -- the TORUS32 build switch of mosfhet.h:23-28 is not
+ * supported by the GPU path).
+ * ---------------------------------------------------------------------------------------- */
+#ifndef MOSFHET_B200_USE_REFERENCE_TYPES
+
+typedef uint64_t Torus;                                                      /* mosfhet.h:27  */
+
+typedef struct _TorusPolynomial { Torus  *coeffs; int N; } *TorusPolynomial; /* mosfhet.h:32  */
+typedef struct _DFT_Polynomial  { double *coeffs; int N; } *DFT_Polynomial;  /* mosfhet.h:37  */
+
+typedef struct _TLWE { Torus *a, b; int n; } *TLWE;                          /* mosfhet.h:51  */
+
+typedef struct _TLWE_KS_Key {                                                /* mosfhet.h:62  */
+  TLWE ***s;              /* s[i][j][d-1], i < n (input dim), j < t, d in 1..2^base_bit-1      */
+  int base_bit, t, n;
+} *TLWE_KS_Key;
+
+typedef struct _TRLWE     { TorusPolynomial *a, b; int k; } *TRLWE;          /* mosfhet.h:73  */
+typedef struct _TRLWE_DFT { DFT_Polynomial  *a, b; int k; } *TRLWE_DFT;      /* mosfhet.h:78  */
+
+typedef struct _TRGSW     { TRLWE     *samples; int l, Bg_bit; } *TRGSW;     /* mosfhet.h:106 */
+typedef struct _TRGSW_DFT { TRLWE_DFT *samples; int l, Bg_bit; } *TRGSW_DFT; /* mosfhet.h:111 */
+
+typedef struct _Bootstrap_Key {                                              /* mosfhet.h:129 */
+  TRGSW_DFT *s;           /* s[i], i < n: Fourier-domain TRGSW of LWE key bit i (unfolding==1) */
+  TRGSW     *su;          /* torus-domain keys for unfolding > 1 (not accelerated; rejected)   */
+  int n, k, N, Bg_bit, l, unfolding;
+} *Bootstrap_Key;
+
+#endif /* MOSFHET_B200_USE_REFERENCE_TYPES */
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Drop-in entry points: same names, argument meaning, ownership and error behaviour as
+ *     the reference.  Outputs are caller-allocated; keys are read-only; blind_rotate mutates
+ *     `tv` in place (bootstrap.c:118).  Keys are uploaded to HBM on first use and cached by
+ *     host pointer (see mb200_register_* below to do it eagerly).
+ * ---------------------------------------------------------------------------------------- */
+void functional_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base);            /* mosfhet.h:412, bootstrap.c:200 */
+void functional_bootstrap_wo_extract(TRLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base); /* mosfhet.h:411, bootstrap.c:192 */
+void programmable_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key,
+                            int precision, int kappa, int theta);                                     /* mosfhet.h:425, bootstrap.c:208 */
+void blind_rotate(TRLWE tv, Torus *a, TRGSW_DFT *s, int size);                                        /* mosfhet.h:409, bootstrap.c:107 */
+void trgsw_mul_trlwe_DFT(TRLWE_DFT out, TRLWE in1, TRGSW_DFT in2);                                    /* mosfhet.h:344, trgsw.c:385     */
+void trlwe_from_DFT(TRLWE out, TRLWE_DFT in);                                                         /* mosfhet.h:263, trlwe.c:629     */
+void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx);                                                 /* mosfhet.h:277, trlwe.c:540     */
+void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key);                                           /* mosfhet.h:227, tlwe.c:289      */
+void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key,
+                                 int torus_base, int n_luts);                                         /* mosfhet.h:424, bootstrap.c:222 */
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Batched variants over arrays of handles (new).  `count` independent ciphertexts per call.
+ *     tv_count is 1 (one test vector shared by the whole batch) or `count` (one per input).
+ * ---------------------------------------------------------------------------------------- */
+void functional_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in,
+                                Bootstrap_Key key, int torus_base, int count);
+void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, TLWE *in,
+                                           Bootstrap_Key key, int torus_base, int count);
+void programmable_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
+                                  int precision, int kappa, int theta, int count);
+void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count);
+void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int in2_count, int count);
+void trlwe_from_DFT_batch(TRLWE *out, TRLWE_DFT *in, int count);
+void trlwe_extract_tlwe_batch(TLWE *out, TRLWE *in, const int *idx, int idx_count, int count);
+void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count);
+/* The BASELINE metric's unit of work: functional_bootstrap followed by tlwe_keyswitch
+ * (caller pattern of applications/multi-ciphertext-arith/src/integer.c:94-96); the
+ * intermediate dimension-k*N TLWE never leaves HBM. out[i]->n == ks_key out dimension. */
+void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in,
+                                          Bootstrap_Key key, TLWE_KS_Key ks_key,
+                                          int torus_base, int count);
+void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE *in,
+                                       Bootstrap_Key key, int torus_base, int n_luts, int count);
+
+/* ------------------------------------------------------------------------------------------
+ * Runtime, key residency and the host Fourier slot order.
+ * ---------------------------------------------------------------------------------------- */
+int  mb200_init(int device);            /* select device, create context; <0 only if device==-2 probe and none present */
+void mb200_shutdown(void);              /* free cached keys, staging buffers, streams */
+int  mb200_device_count(void);          /* number of visible CUDA devices (0 without a GPU; no abort) */
+const char *mb200_version(void);
+void mb200_device_synchronize(void);
+
+/* The reference stores Fourier-domain polynomials in the slot order of whichever CPU FFT backend
+ * it was compiled with (polynomial.c:359-375): slot h of a DFT_Polynomial holds p(w^e_h),
+ * w = exp(i*pi/N).  The GPU library needs e_h to import keys and to return TRLWE_DFT results.
+ *   MB200_FFT_AUTO    : probe the host's polynomial_torus_to_DFT (dlsym) with the monomial X
+ *   MB200_FFT_SPQLIOS : e_h = 1 + 4*bitrev(h)   (src/fft/spqlios)
+ *   MB200_FFT_FFNT    : e_h = 1 - 4*bitrev(h)   (src/fft/ffnt)
+ *   MB200_FFT_NATURAL : e_h = 1 + 4*h
+ * Slots hold Re in coeffs[h] and Im in coeffs[h + N/2] (polynomial.c:396-399). */
+enum { MB200_FFT_AUTO = 0, MB200_FFT_SPQLIOS = 1, MB200_FFT_FFNT = 2, MB200_FFT_NATURAL = 3 };
+void mb200_set_host_fft_layout(int layout);
+int  mb200_get_host_fft_layout(void);
+void mb200_host_slot_exponents(int layout, int N, int32_t *e_out /* N/2 */);
+
+void mb200_register_bootstrap_key(Bootstrap_Key key);   /* upload now (otherwise lazily on first use) */
+void mb200_release_bootstrap_key(Bootstrap_Key key);
+void mb200_register_ks_key(TLWE_KS_Key key);
+void mb200_release_ks_key(TLWE_KS_Key key);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Flat API.  Layouts (all little-endian u64 / f64, contiguous):
+ *     TLWE   of dimension n : n+1 words   = a[0..n) then b
+ *     TRLWE  (k, N)         : (k+1)*N     = a[0] .. a[k-1] then b, N coefficients each
+ *     BSK, host form        : [n][(k+1)*l rows][(k+1) polys a[0..k),b][N doubles = Re(0..N/2) | Im(0..N/2)]
+ *                             in the slot order given by `layout`
+ *     KSK, host form        : [N_in][t][2^base_bit - 1][n_out + 1]
+ *     Pointers named h_* are host, d_* are device (cudaMalloc'd / torch CUDA tensors).
+ *     `stream` is a cudaStream_t passed as void* (NULL = the library's per-thread stream).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mb200_params {
+  int n;         /* LWE dimension (blind-rotation length)                       */
+  int N, k;      /* ring degree and TRLWE mask polynomials                      */
+  int l, Bg_bit; /* gadget levels / log2 base of the bootstrapping key          */
+  int t, base_bit; /* key-switch levels / log2 base                             */
+} mb200_params;
+
+typedef struct mb200_bsk *mb200_bsk_t;   /* resident Fourier-domain bootstrapping key */
+typedef struct mb200_ksk *mb200_ksk_t;   /* resident key-switching table              */
+
+size_t      mb200_bsk_device_bytes(const mb200_params *p);
+size_t      mb200_ksk_device_bytes(const mb200_params *p);
+mb200_bsk_t mb200_bsk_from_host(const mb200_params *p, const double *h_bsk, int layout);
+mb200_ksk_t mb200_ksk_from_host(const mb200_params *p, const uint64_t *h_ksk);
+/* Adopt caller-owned device memory already in the resident layout (e.g. the receive buffer of an
+ * NCCL broadcast from rank 0, see mosfhet_b200/sharding.py); the library does not free it. */
+mb200_bsk_t mb200_bsk_adopt_device(const mb200_params *p, void *d_bsk);
+mb200_ksk_t mb200_ksk_adopt_device(const mb200_params *p, void *d_ksk);
+void       *mb200_bsk_device_ptr(mb200_bsk_t bsk);
+void       *mb200_ksk_device_ptr(mb200_ksk_t ksk);
+void        mb200_bsk_free(mb200_bsk_t bsk);
+void        mb200_ksk_free(mb200_ksk_t ksk);
+
+/* Synthetic keys generated on the device from caller-supplied binary secrets (bench / test
+ * support; replaces the host-side key generators bootstrap.c:3-21 and tlwe.c:193-212, which stay
+ * with the reference CPU build).  lwe_key: n words in {0,1}; rlwe_key: k*N words in {0,1}. */
+mb200_bsk_t mb200_bsk_synthesize(const mb200_params *p, const uint64_t *h_lwe_key,
+                                 const uint64_t *h_rlwe_key, double rlwe_sigma, uint64_t seed);
+mb200_ksk_t mb200_ksk_synthesize(const mb200_params *p, const uint64_t *h_rlwe_key /* k*N, input key  */,
+                                 const uint64_t *h_lwe_key  /* n, output key */,
+                                 double lwe_sigma, uint64_t seed);
+
+/* Device-resident batch ops (inputs/outputs already in HBM; asynchronous on `stream`). */
+void mb200_pbs_dev(mb200_bsk_t bsk, uint64_t *d_out_tlwe /* [count][k*N+1] */,
+                   const uint64_t *d_tv /* [tv_count][(k+1)*N] */, int tv_count,
+                   const uint64_t *d_in /* [count][n+1] */, int torus_base, int count, void *stream);
+void mb200_pbs_wo_extract_dev(mb200_bsk_t bsk, uint64_t *d_out_trlwe /* [count][(k+1)*N] */,
+                              const uint64_t *d_tv, int tv_count, const uint64_t *d_in,
+                              int torus_base, int count, void *stream);
+void mb200_blind_rotate_dev(mb200_bsk_t bsk, uint64_t *d_acc /* [count][(k+1)*N], in place */,
+                            const uint64_t *d_a /* [count][a_stride] */, int a_stride, int size,
+                            int count, void *stream);
+void mb200_extract_dev(uint64_t *d_out_tlwe /* [count*idx_count][k*N+1] */, const uint64_t *d_trlwe,
+                       const int *h_idx, int idx_count, int N, int k, int count, void *stream);
+void mb200_ks_dev(mb200_ksk_t ksk, uint64_t *d_out /* [count][n+1] */,
+                  const uint64_t *d_in /* [count][k*N+1] */, int count, void *stream);
+void mb200_pbs_ks_dev(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *d_out /* [count][n+1] */,
+                      const uint64_t *d_tv, int tv_count, const uint64_t *d_in,
+                      uint64_t *d_scratch /* [count][k*N+1] */, int torus_base, int count, void *stream);
+/* One external product + inverse transform per ciphertext: out = TRGSW_i (.) in (trgsw.c:385 + trlwe.c:629) */
+void mb200_extprod_dev(mb200_bsk_t trgsw_set, const int *h_sel /* [count] index into the set */,
+                       uint64_t *d_out_trlwe, const uint64_t *d_in_trlwe, int count, void *stream);
+/* Negacyclic transforms in the library's internal slot order (bit-reversed, e = 1+4*bitrev(s)). */
+void mb200_torus_to_dft_dev(double *d_out /* [count][N] Re|Im */, const uint64_t *d_in, int N, int count, void *stream);
+void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int count, void *stream);
+
+/* Host-buffer batch ops: H2D of inputs, kernels, D2H of results, synchronous on return. */
+void mb200_pbs_ks_host(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *h_out /* [count][n+1] */,
+                       const uint64_t *h_tv, int tv_count, const uint64_t *h_in /* [count][n+1] */,
+                       int torus_base, int count);
+void mb200_pbs_host(mb200_bsk_t bsk, uint64_t *h_out /* [count][k*N+1] */, const uint64_t *h_tv,
+                    int tv_count, const uint64_t *h_in, int torus_base, int count);
+void mb200_ks_host(mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_in, int count);
+
+/* Introspection for tests / bench: kernels launched by this library since the last reset, and
+ * which blind-rotation kernel variant the last PBS call dispatched to. */
+uint64_t    mb200_launch_count(void);
+void        mb200_reset_launch_count(void);
+const char *mb200_last_blind_rotate_kernel(void);
+/* Force the generic (any k, l, N) kernel instead of the specialised k=1 one: 0 = auto, 1 = generic */
+void        mb200_set_kernel_policy(int policy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSFHET_B200_H */

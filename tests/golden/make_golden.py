@@ -1,0 +1,206 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference library.
+
+Run in the build container (needs oracle/_ref built by oracle/build_ref.sh from /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no golden vectors and its RNG cannot be seeded, so the
+fixtures record, for small parameter sets, the keys and inputs the reference drew and every output
+of the hot-path functions on them: polynomial_decompose_i, polynomial_torus_to_DFT,
+polynomial_DFT_to_torus, the rotations, trgsw_mul_trlwe_DFT, trlwe_from_DFT, blind_rotate,
+functional_bootstrap[_wo_extract], programmable_bootstrap, multivalue_bootstrap_CLOT21,
+trlwe_extract_tlwe and tlwe_keyswitch.  Fourier-domain arrays are stored in the slot order of the
+build that produced them (``layout``: 1 = SPQLIOS, 2 = FFNT).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from mosfhet_b200 import abi  # noqa: E402
+from oracle import ref as reflib  # noqa: E402
+
+SETS = {
+    # name: n, N, k, l, Bg_bit, t, base_bit, lwe_sigma, rlwe_sigma, batch
+    "tiny_k1": dict(n=12, N=256, k=1, l=2, Bg_bit=8, t=3, base_bit=2, lwe_sigma=2.0**-30, rlwe_sigma=2.0**-45, batch=6),
+    "tiny_k2": dict(n=8, N=128, k=2, l=3, Bg_bit=6, t=4, base_bit=3, lwe_sigma=2.0**-30, rlwe_sigma=2.0**-45, batch=4),
+    "small_l4": dict(n=10, N=512, k=1, l=4, Bg_bit=9, t=3, base_bit=4, lwe_sigma=2.0**-30, rlwe_sigma=2.0**-44, batch=4),
+}
+
+
+def rand_u64(R, count):
+    buf = abi.aligned_empty(max(count, 64), np.uint64)[:count]   # aes_prng wants aligned, >= 256 B
+    R.generate_random_bytes(max(count, 64) * 8, buf.ctypes.data_as(C.c_void_p))
+    return buf
+
+
+def key_words(ptr, n):
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(np.uint64).copy()
+
+
+def gen(name, P, variant, full=True):
+    R = reflib.load(variant)
+    n, N, k, l, Bg_bit, t, base_bit = (P[x] for x in ("n", "N", "k", "l", "Bg_bit", "t", "base_bit"))
+    B = P["batch"]
+    R.init_fft(N)
+    out = dict(params=np.array([n, N, k, l, Bg_bit, t, base_bit], np.int32), layout=np.int32(R.layout))
+
+    key_lwe = R.tlwe_new_binary_key(n, P["lwe_sigma"])
+    key_rlwe = R.trlwe_new_binary_key(N, k, P["rlwe_sigma"])
+    key_ext = R.tlwe_new_binary_key(k * N, P["rlwe_sigma"])
+    R.trlwe_extract_tlwe_key(key_ext, key_rlwe)
+    trgsw_key = R.trgsw_new_key(key_rlwe, l, Bg_bit)
+    out["lwe_key"] = key_words(key_lwe.contents.s, n)
+    out["rlwe_key"] = np.stack([key_words(key_rlwe.contents.s[i].contents.coeffs, N) for i in range(k)])
+    out["ext_key"] = key_words(key_ext.contents.s, k * N)
+
+    # --- bootstrapping key, built row by row exactly as new_bootstrap_key_wo_unfolding
+    #     (bootstrap.c:3-21) so that the torus-domain TRGSW can be recorded as well
+    rows = (k + 1) * l
+    bsk_host = np.empty((n, rows, k + 1, N), np.float64)
+    bsk_torus = np.empty((n, rows, k + 1, N), np.uint64)
+    dft = R.trgsw_alloc_new_DFT_sample(l, Bg_bit, k, N)
+    for i in range(n):
+        tmp = R.trgsw_new_monomial_sample(int(out["lwe_key"][i]), 0, trgsw_key)
+        R.trgsw_to_DFT(dft, tmp)
+        bsk_torus[i] = abi.trgsw_to_flat(tmp, k)
+        bsk_host[i] = abi.trgsw_dft_to_flat(dft, k)
+        R.free_trgsw(tmp)
+    out["bsk_host"] = bsk_host
+    out["bsk_torus"] = bsk_torus
+    hbsk = abi.HostBootstrapKey(bsk_host, k, l, Bg_bit)
+
+    # --- single-polynomial primitives
+    poly = rand_u64(R, N)
+    hp = abi.HostTRLWE(np.stack([poly] * (k + 1)))         # reuse its polynomial structs
+    p_in = hp.struct.b
+    p_out = R.polynomial_new_torus_polynomial(N)
+    d_out = R.polynomial_new_DFT_polynomial(N)
+    out["poly"] = poly
+    dec = []
+    for j in range(l):
+        R.polynomial_decompose_i(p_out, p_in, Bg_bit, l, j)
+        dec.append(key_words(p_out.contents.coeffs, N))
+    out["poly_decomp"] = np.stack(dec).view(np.int64)
+    # forward transform of a digit polynomial (the only kind of input the path transforms)
+    hd = abi.HostTRLWE(np.stack([dec[0]] * (k + 1)))
+    R.polynomial_torus_to_DFT(d_out, hd.struct.b)
+    out["digit_dft_host"] = np.ctypeslib.as_array(d_out.contents.coeffs, shape=(N,)).copy()
+    # forward transform of the monomial X (pins the slot order)
+    mono = np.zeros(N, np.uint64); mono[1] = 1
+    hm = abi.HostTRLWE(np.stack([mono] * (k + 1)))
+    R.polynomial_torus_to_DFT(d_out, hm.struct.b)
+    out["monomial_dft_host"] = np.ctypeslib.as_array(d_out.contents.coeffs, shape=(N,)).copy()
+    rots = []
+    rot_amounts = np.array([0, 1, N - 1, N, N + 1, 2 * N - 1, N // 3, N + N // 5], np.int32)
+    for a in rot_amounts:
+        R.torus_polynomial_mul_by_xai(p_out, p_in, int(a))
+        r1 = key_words(p_out.contents.coeffs, N)
+        R.torus_polynomial_mul_by_xai_minus_1(p_out, p_in, int(a))
+        rots.append(np.stack([r1, key_words(p_out.contents.coeffs, N)]))
+    out["rot_amounts"] = rot_amounts
+    out["rot_out"] = np.stack(rots)
+
+    # --- one external product + inverse transform (trgsw.c:385, trlwe.c:629)
+    msg = rand_u64(R, N)
+    hmsg = abi.HostTRLWE(np.stack([msg] * (k + 1)))
+    c_in = R.trlwe_new_sample(hmsg.struct.b, key_rlwe)
+    ep_dft = R.trlwe_alloc_new_DFT_sample(k, N)
+    ep_out = R.trlwe_alloc_new_sample(k, N)
+    R.trgsw_mul_trlwe_DFT(ep_dft, c_in, hbsk.trgsw[0].handle)
+    R.trlwe_from_DFT(ep_out, ep_dft)
+    out["ep_in"] = abi.trlwe_to_flat(c_in)
+    out["ep_dft_host"] = abi.trlwe_dft_to_flat(ep_dft)
+    out["ep_out"] = abi.trlwe_to_flat(ep_out)
+
+    if not full:
+        return out
+
+    # --- key-switching key and key switch (tlwe.c:193-212, 289-303)
+    ksk = R.tlwe_new_KS_key(key_lwe, key_ext, t, base_bit)
+    out["ksk"] = abi.ks_key_to_flat(ksk)
+
+    # --- bootstraps
+    torus_base = 4
+    lut_vals = rand_u64(R, torus_base)
+    tv = R.trlwe_alloc_new_sample(k, N)
+    R.trlwe_torus_packing(tv, lut_vals.ctypes.data_as(C.POINTER(C.c_uint64)), torus_base)
+    out["lut_vals"] = lut_vals
+    out["tv"] = abi.trlwe_to_flat(tv)
+    msgs = np.arange(B) % torus_base
+    ins, br_out, fbwo_out, fb_out, ks_out, pb_out, ext_out = [], [], [], [], [], [], []
+    for b in range(B):
+        m = int(msgs[b]) << (64 - 3)                       # int2torus(m, log2(2*torus_base))
+        c = R.tlwe_new_sample(m, key_lwe)
+        ins.append(abi.tlwe_to_flat(c))
+        # blind_rotate in place on a copy of tv (bootstrap.c:107)
+        acc = abi.HostTRLWE(out["tv"])
+        R.blind_rotate(acc.handle, c.contents.a, hbsk.struct.s, n)
+        br_out.append(acc.flat().copy())
+        wo = abi.HostTRLWE.zeros(k, N)
+        R.functional_bootstrap_wo_extract(wo.handle, tv, c, hbsk.handle, torus_base)
+        fbwo_out.append(wo.flat().copy())
+        o = R.tlwe_alloc_sample(k * N)
+        R.functional_bootstrap(o, tv, c, hbsk.handle, torus_base)
+        fb_out.append(abi.tlwe_to_flat(o))
+        ko = R.tlwe_alloc_sample(n)
+        R.tlwe_keyswitch(ko, o, ksk)
+        ks_out.append(abi.tlwe_to_flat(ko))
+        po = R.tlwe_alloc_sample(k * N)
+        R.programmable_bootstrap(po, tv, c, hbsk.handle, 3, 1, 1)
+        pb_out.append(abi.tlwe_to_flat(po))
+        ex = []
+        for idx in (0, 1, N // 2, N - 1):
+            eo = R.tlwe_alloc_sample(k * N)
+            R.trlwe_extract_tlwe(eo, wo.handle, idx)
+            ex.append(abi.tlwe_to_flat(eo))
+        ext_out.append(np.stack(ex))
+    out["msgs"] = msgs.astype(np.int32)
+    out["tlwe_in"] = np.stack(ins)
+    out["blind_rotate_out"] = np.stack(br_out)
+    out["fb_wo_extract_out"] = np.stack(fbwo_out)
+    out["fb_out"] = np.stack(fb_out)
+    out["ks_out"] = np.stack(ks_out)
+    out["pb_out"] = np.stack(pb_out)
+    out["pb_args"] = np.array([3, 1, 1], np.int32)
+    out["extract_idx"] = np.array([0, 1, N // 2, N - 1], np.int32)
+    out["extract_out"] = np.stack(ext_out)
+
+    # --- multivalue_bootstrap_CLOT21 (bootstrap.c:222-230) with n_luts LUTs of torus_base=2
+    n_luts, tb2 = 4, 2
+    lut2 = rand_u64(R, n_luts * tb2)
+    tv2 = R.trlwe_alloc_new_sample(k, N)
+    R.trlwe_torus_packing_many_LUT(tv2, lut2.ctypes.data_as(C.POINTER(C.c_uint64)), tb2, n_luts)
+    outs = (abi.TLWE * n_luts)(*[R.tlwe_alloc_sample(k * N) for _ in range(n_luts)])
+    c = R.tlwe_new_sample(1 << (64 - 2), key_lwe)            # message 1 of torus_base 2
+    R.multivalue_bootstrap_CLOT21(outs, tv2, c, hbsk.handle, tb2, n_luts)
+    out["mv_lut"] = lut2
+    out["mv_tv"] = abi.trlwe_to_flat(tv2)
+    out["mv_in"] = abi.tlwe_to_flat(c)
+    out["mv_out"] = np.stack([abi.tlwe_to_flat(outs[i]) for i in range(n_luts)])
+    out["mv_args"] = np.array([tb2, n_luts], np.int32)
+    return out
+
+
+def main():
+    for name, P in SETS.items():
+        data = gen(name, P, "avx512")
+        path = os.path.join(HERE, f"{name}_spqlios.npz")
+        np.savez_compressed(path, **data)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+    # FFNT slot order: primitives + one external product only
+    data = gen("tiny_k1", SETS["tiny_k1"], "portable", full=False)
+    path = os.path.join(HERE, "tiny_k1_ffnt.npz")
+    np.savez_compressed(path, **data)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
