@@ -209,6 +209,9 @@ void        mb200_reset_launch_count(void);
 const char *mb200_last_blind_rotate_kernel(void);
 /* Force the generic (any k, l, N) kernel instead of the specialised k=1 one: 0 = auto, 1 = generic */
 void        mb200_set_kernel_policy(int policy);
+/* Measured FP64 FMA throughput (TFLOP/s) of the current device: the roofline denominator of the
+ * FP64-bound blind-rotation kernel (MEASURED_PEAKS.json has no FP64 entry). */
+double      mb200_measure_fp64_tflops(int iters);
 
 #ifdef __cplusplus
 }

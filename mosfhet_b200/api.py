@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference operators for the accelerated path.
+
+Three levels, all thin bindings over ``libmosfhet_b200.so`` (no computation happens in Python):
+
+1. **Reference names over reference handles** -- ``functional_bootstrap(out, tv, in_, key, torus_base)``
+   etc. take ``abi.Host*`` objects (or raw ctypes handles produced by any C library with the
+   ``mosfhet.h`` layouts) and have the argument meaning, ownership and error behaviour of
+   ``/root/reference/include/mosfhet.h:227,263,277,344,409-412,425``.
+2. **Batched variants** over lists of handles.
+3. **Flat calls** on numpy arrays (host) and raw device pointers / torch CUDA tensors (device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, abi
+from .params import Params
+
+FFT_AUTO, FFT_SPQLIOS, FFT_FFNT, FFT_NATURAL = 0, 1, 2, 3
+
+
+def lib():
+    return _lib.load()
+
+
+def _h(x):
+    return getattr(x, "handle", x)
+
+
+# ---------------------------------------------------------------------------------------------
+# runtime
+# ---------------------------------------------------------------------------------------------
+def device_count() -> int:
+    return int(lib().mb200_device_count())
+
+
+def init(device: int = 0) -> None:
+    """Select the CUDA device; aborts the process if there is none (no CPU fallback)."""
+    lib().mb200_init(device)
+
+
+def require_gpu() -> None:
+    if device_count() < 1:
+        raise RuntimeError("mosfhet_b200: no CUDA device visible and there is no CPU fallback")
+
+
+def shutdown() -> None:
+    lib().mb200_shutdown()
+
+
+def synchronize() -> None:
+    lib().mb200_device_synchronize()
+
+
+def set_host_fft_layout(layout: int) -> None:
+    lib().mb200_set_host_fft_layout(layout)
+
+
+def host_slot_exponents(layout: int, N: int) -> np.ndarray:
+    e = np.empty(N // 2, np.int32)
+    lib().mb200_host_slot_exponents(layout, N, e.ctypes.data_as(C.POINTER(C.c_int32)))
+    return e
+
+
+def launch_count() -> int:
+    return int(lib().mb200_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().mb200_reset_launch_count()
+
+
+def last_blind_rotate_kernel() -> str:
+    return lib().mb200_last_blind_rotate_kernel().decode()
+
+
+def measure_fp64_tflops(iters: int = 20000) -> float:
+    return float(lib().mb200_measure_fp64_tflops(iters))
+
+
+def set_kernel_policy(policy: int) -> None:
+    lib().mb200_set_kernel_policy(policy)
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) reference names over reference handles
+# ---------------------------------------------------------------------------------------------
+def functional_bootstrap(out, tv, in_, key, torus_base: int) -> None:
+    lib().functional_bootstrap(_h(out), _h(tv), _h(in_), _h(key), torus_base)
+
+
+def functional_bootstrap_wo_extract(out, tv, in_, key, torus_base: int) -> None:
+    lib().functional_bootstrap_wo_extract(_h(out), _h(tv), _h(in_), _h(key), torus_base)
+
+
+def programmable_bootstrap(out, tv, in_, key, precision: int, kappa: int, theta: int) -> None:
+    lib().programmable_bootstrap(_h(out), _h(tv), _h(in_), _h(key), precision, kappa, theta)
+
+
+def blind_rotate(tv, a, s, size: int) -> None:
+    """In place on ``tv`` (bootstrap.c:118).  ``a``: uint64 array / pointer; ``s``: TRGSW_DFT array."""
+    if isinstance(a, np.ndarray):
+        a = a.ctypes.data_as(C.POINTER(C.c_uint64))
+    lib().blind_rotate(_h(tv), a, s, size)
+
+
+def trgsw_mul_trlwe_DFT(out, in1, in2) -> None:
+    lib().trgsw_mul_trlwe_DFT(_h(out), _h(in1), _h(in2))
+
+
+def trlwe_from_DFT(out, in_) -> None:
+    lib().trlwe_from_DFT(_h(out), _h(in_))
+
+
+def trlwe_extract_tlwe(out, in_, idx: int) -> None:
+    lib().trlwe_extract_tlwe(_h(out), _h(in_), idx)
+
+
+def tlwe_keyswitch(out, in_, ks_key) -> None:
+    lib().tlwe_keyswitch(_h(out), _h(in_), _h(ks_key))
+
+
+def multivalue_bootstrap_CLOT21(out_list, tv, in_, key, torus_base: int, n_luts: int) -> None:
+    lib().multivalue_bootstrap_CLOT21(abi.handle_array(out_list, abi.TLWE), _h(tv), _h(in_), _h(key), torus_base, n_luts)
+
+
+def register_bootstrap_key(key) -> None:
+    lib().mb200_register_bootstrap_key(_h(key))
+
+
+def release_bootstrap_key(key) -> None:
+    lib().mb200_release_bootstrap_key(_h(key))
+
+
+def register_ks_key(key) -> None:
+    lib().mb200_register_ks_key(_h(key))
+
+
+def release_ks_key(key) -> None:
+    lib().mb200_release_ks_key(_h(key))
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) batched variants over lists of handles
+# ---------------------------------------------------------------------------------------------
+def _tvs(tv):
+    tvs = tv if isinstance(tv, (list, tuple)) else [tv]
+    return abi.handle_array(tvs, abi.TRLWE), len(tvs)
+
+
+def functional_bootstrap_batch(out, tv, in_, key, torus_base: int) -> None:
+    tva, tvc = _tvs(tv)
+    lib().functional_bootstrap_batch(abi.handle_array(out, abi.TLWE), tva, tvc, abi.handle_array(in_, abi.TLWE),
+                                     _h(key), torus_base, len(in_))
+
+
+def functional_bootstrap_wo_extract_batch(out, tv, in_, key, torus_base: int) -> None:
+    tva, tvc = _tvs(tv)
+    lib().functional_bootstrap_wo_extract_batch(abi.handle_array(out, abi.TRLWE), tva, tvc,
+                                                abi.handle_array(in_, abi.TLWE), _h(key), torus_base, len(in_))
+
+
+def programmable_bootstrap_batch(out, tv, in_, key, precision: int, kappa: int, theta: int) -> None:
+    tva, tvc = _tvs(tv)
+    lib().programmable_bootstrap_batch(abi.handle_array(out, abi.TLWE), tva, tvc, abi.handle_array(in_, abi.TLWE),
+                                       _h(key), precision, kappa, theta, len(in_))
+
+
+def tlwe_keyswitch_batch(out, in_, ks_key) -> None:
+    lib().tlwe_keyswitch_batch(abi.handle_array(out, abi.TLWE), abi.handle_array(in_, abi.TLWE), _h(ks_key), len(in_))
+
+
+def functional_bootstrap_keyswitch_batch(out, tv, in_, key, ks_key, torus_base: int) -> None:
+    tva, tvc = _tvs(tv)
+    lib().functional_bootstrap_keyswitch_batch(abi.handle_array(out, abi.TLWE), tva, tvc,
+                                               abi.handle_array(in_, abi.TLWE), _h(key), _h(ks_key), torus_base, len(in_))
+
+
+def blind_rotate_batch(tv_list, a_list, s, size: int) -> None:
+    ptrs = (C.POINTER(C.c_uint64) * len(a_list))(*[a.ctypes.data_as(C.POINTER(C.c_uint64)) for a in a_list])
+    lib().blind_rotate_batch(abi.handle_array(tv_list, abi.TRLWE), ptrs, s, size, len(tv_list))
+
+
+def trgsw_mul_trlwe_DFT_batch(out, in1, in2) -> None:
+    in2s = in2 if isinstance(in2, (list, tuple)) else [in2]
+    lib().trgsw_mul_trlwe_DFT_batch(abi.handle_array(out, abi.TRLWE_DFT), abi.handle_array(in1, abi.TRLWE),
+                                    abi.handle_array(in2s, abi.TRGSW_DFT), len(in2s), len(in1))
+
+
+def trlwe_from_DFT_batch(out, in_) -> None:
+    lib().trlwe_from_DFT_batch(abi.handle_array(out, abi.TRLWE), abi.handle_array(in_, abi.TRLWE_DFT), len(in_))
+
+
+def trlwe_extract_tlwe_batch(out, in_, idx) -> None:
+    idx = np.ascontiguousarray(idx, np.int32)
+    lib().trlwe_extract_tlwe_batch(abi.handle_array(out, abi.TLWE), abi.handle_array(in_, abi.TRLWE),
+                                   idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx), len(in_))
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) flat calls: resident keys, host-buffer and device-resident batches
+# ---------------------------------------------------------------------------------------------
+def _ptr(x):
+    """Raw address of a numpy array, a torch tensor, or an int."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return int(x)
+
+
+class BootstrapKey:
+    """Fourier-domain bootstrapping key resident in HBM (``mb200_bsk_t``)."""
+
+    def __init__(self, params: Params, handle: int, keepalive=None):
+        self.params, self.handle, self._keep = params, handle, keepalive
+
+    @classmethod
+    def from_host(cls, params: Params, bsk_host: np.ndarray, layout: int) -> "BootstrapKey":
+        """``bsk_host``: float64 [n, (k+1)l, k+1, N] in the slot order ``layout`` of the CPU build."""
+        bsk_host = np.ascontiguousarray(bsk_host, np.float64)
+        assert bsk_host.shape == (params.n, (params.k + 1) * params.l, params.k + 1, params.N), bsk_host.shape
+        p = params.c()
+        h = lib().mb200_bsk_from_host(C.byref(p), bsk_host.ctypes.data_as(C.POINTER(C.c_double)), layout)
+        return cls(params, h)
+
+    @classmethod
+    def synthesize(cls, params: Params, lwe_key: np.ndarray, rlwe_key: np.ndarray, seed: int = 1) -> "BootstrapKey":
+        lwe_key = np.ascontiguousarray(lwe_key, np.uint64)
+        rlwe_key = np.ascontiguousarray(rlwe_key, np.uint64).reshape(-1)
+        assert lwe_key.shape[0] == params.n and rlwe_key.shape[0] == params.k * params.N
+        p = params.c()
+        u = C.POINTER(C.c_uint64)
+        h = lib().mb200_bsk_synthesize(C.byref(p), lwe_key.ctypes.data_as(u), rlwe_key.ctypes.data_as(u),
+                                       params.rlwe_sigma, seed)
+        return cls(params, h)
+
+    @classmethod
+    def adopt(cls, params: Params, device_buffer) -> "BootstrapKey":
+        """Wrap caller-owned device memory already in the resident layout (e.g. an NCCL receive buffer)."""
+        p = params.c()
+        h = lib().mb200_bsk_adopt_device(C.byref(p), _ptr(device_buffer))
+        return cls(params, h, keepalive=device_buffer)
+
+    @property
+    def device_ptr(self) -> int:
+        return int(lib().mb200_bsk_device_ptr(self.handle))
+
+    @property
+    def nbytes(self) -> int:
+        p = self.params.c()
+        return int(lib().mb200_bsk_device_bytes(C.byref(p)))
+
+    def free(self) -> None:
+        if self.handle:
+            lib().mb200_bsk_free(self.handle)
+            self.handle = None
+
+
+class KeySwitchKey:
+    """TLWE key-switching table resident in HBM (``mb200_ksk_t``)."""
+
+    def __init__(self, params: Params, handle: int, keepalive=None):
+        self.params, self.handle, self._keep = params, handle, keepalive
+
+    @classmethod
+    def from_host(cls, params: Params, ksk: np.ndarray) -> "KeySwitchKey":
+        ksk = np.ascontiguousarray(ksk, np.uint64)
+        assert ksk.shape == (params.k * params.N, params.t, (1 << params.base_bit) - 1, params.n + 1), ksk.shape
+        p = params.c()
+        h = lib().mb200_ksk_from_host(C.byref(p), ksk.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return cls(params, h)
+
+    @classmethod
+    def synthesize(cls, params: Params, rlwe_key: np.ndarray, lwe_key: np.ndarray, seed: int = 2) -> "KeySwitchKey":
+        rlwe_key = np.ascontiguousarray(rlwe_key, np.uint64).reshape(-1)
+        lwe_key = np.ascontiguousarray(lwe_key, np.uint64)
+        p = params.c()
+        u = C.POINTER(C.c_uint64)
+        h = lib().mb200_ksk_synthesize(C.byref(p), rlwe_key.ctypes.data_as(u), lwe_key.ctypes.data_as(u),
+                                       params.lwe_sigma, seed)
+        return cls(params, h)
+
+    @classmethod
+    def adopt(cls, params: Params, device_buffer) -> "KeySwitchKey":
+        p = params.c()
+        h = lib().mb200_ksk_adopt_device(C.byref(p), _ptr(device_buffer))
+        return cls(params, h, keepalive=device_buffer)
+
+    @property
+    def device_ptr(self) -> int:
+        return int(lib().mb200_ksk_device_ptr(self.handle))
+
+    @property
+    def nbytes(self) -> int:
+        p = self.params.c()
+        return int(lib().mb200_ksk_device_bytes(C.byref(p)))
+
+    def free(self) -> None:
+        if self.handle:
+            lib().mb200_ksk_free(self.handle)
+            self.handle = None
+
+
+# ---- host-buffer batches (numpy or pinned torch tensors in, numpy out) ------------------------
+def pbs_ks_host(bsk: BootstrapKey, ksk: KeySwitchKey, tv, tlwe_in, torus_base: int, out=None):
+    """functional_bootstrap then tlwe_keyswitch for every row of ``tlwe_in`` [count, n+1]."""
+    P = bsk.params
+    count = tlwe_in.shape[0]
+    tv_count = 1 if tv.ndim == 2 else tv.shape[0]
+    if out is None:
+        out = np.empty((count, P.n + 1), np.uint64)
+    lib().mb200_pbs_ks_host(bsk.handle, ksk.handle, _ptr(out), _ptr(tv), tv_count, _ptr(tlwe_in), torus_base, count)
+    return out
+
+
+def pbs_host(bsk: BootstrapKey, tv, tlwe_in, torus_base: int, out=None):
+    P = bsk.params
+    count = tlwe_in.shape[0]
+    tv_count = 1 if tv.ndim == 2 else tv.shape[0]
+    if out is None:
+        out = np.empty((count, P.k * P.N + 1), np.uint64)
+    lib().mb200_pbs_host(bsk.handle, _ptr(out), _ptr(tv), tv_count, _ptr(tlwe_in), torus_base, count)
+    return out
+
+
+def ks_host(ksk: KeySwitchKey, tlwe_in, out=None):
+    P = ksk.params
+    count = tlwe_in.shape[0]
+    if out is None:
+        out = np.empty((count, P.n + 1), np.uint64)
+    lib().mb200_ks_host(ksk.handle, _ptr(out), _ptr(tlwe_in), count)
+    return out
+
+
+# ---- device-resident batches (raw device pointers / torch CUDA tensors; async on `stream`) ----
+def pbs_dev(bsk, d_out, d_tv, tv_count, d_in, torus_base, count, stream=None):
+    lib().mb200_pbs_dev(bsk.handle, _ptr(d_out), _ptr(d_tv), tv_count, _ptr(d_in), torus_base, count, _ptr(stream))
+
+
+def pbs_wo_extract_dev(bsk, d_out, d_tv, tv_count, d_in, torus_base, count, stream=None):
+    lib().mb200_pbs_wo_extract_dev(bsk.handle, _ptr(d_out), _ptr(d_tv), tv_count, _ptr(d_in), torus_base, count,
+                                   _ptr(stream))
+
+
+def blind_rotate_dev(bsk, d_acc, d_a, a_stride, size, count, stream=None):
+    lib().mb200_blind_rotate_dev(bsk.handle, _ptr(d_acc), _ptr(d_a), a_stride, size, count, _ptr(stream))
+
+
+def extract_dev(d_out, d_trlwe, idx, N, k, count, stream=None):
+    idx = np.ascontiguousarray(idx, np.int32)
+    lib().mb200_extract_dev(_ptr(d_out), _ptr(d_trlwe), idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx), N, k, count,
+                            _ptr(stream))
+
+
+def ks_dev(ksk, d_out, d_in, count, stream=None):
+    lib().mb200_ks_dev(ksk.handle, _ptr(d_out), _ptr(d_in), count, _ptr(stream))
+
+
+def pbs_ks_dev(bsk, ksk, d_out, d_tv, tv_count, d_in, d_scratch, torus_base, count, stream=None):
+    lib().mb200_pbs_ks_dev(bsk.handle, ksk.handle, _ptr(d_out), _ptr(d_tv), tv_count, _ptr(d_in), _ptr(d_scratch),
+                           torus_base, count, _ptr(stream))
+
+
+def extprod_dev(trgsw_set, sel, d_out, d_in, count, stream=None):
+    sel = np.ascontiguousarray(sel, np.int32)
+    lib().mb200_extprod_dev(trgsw_set.handle, sel.ctypes.data_as(C.POINTER(C.c_int)), _ptr(d_out), _ptr(d_in), count,
+                            _ptr(stream))
+
+
+def torus_to_dft_dev(d_out, d_in, N, count, stream=None):
+    lib().mb200_torus_to_dft_dev(_ptr(d_out), _ptr(d_in), N, count, _ptr(stream))
+
+
+def dft_to_torus_dev(d_out, d_in, N, count, stream=None):
+    lib().mb200_dft_to_torus_dev(_ptr(d_out), _ptr(d_in), N, count, _ptr(stream))

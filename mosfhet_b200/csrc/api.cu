@@ -1,0 +1,794 @@
+// api.cu -- the C ABI of libmosfhet_b200.so (include/mosfhet_b200.h): drop-in entry points
+// under the reference's names, batched variants, key residency and the flat API.
+// Host-side logic only: handle-tree gather/scatter, staging, dispatch.  No CPU compute path.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mosfhet_b200.h"
+#include "common.cuh"
+
+namespace mb {
+void init_device(int device);
+int device_count_noabort();
+int current_device();
+unsigned long long launches();
+void reset_launches();
+void drop_tables();
+}  // namespace mb
+
+struct mb200_bsk : mb::BskDev {};
+struct mb200_ksk : mb::KskDev {};
+
+namespace {
+
+
+
+std::mutex g_mu;
+int g_host_layout = MB200_FFT_AUTO;
+int g_policy = 0;
+std::string g_last_kernel = "none";
+std::map<const void *, mb200_bsk *> g_bsk_cache;   // keyed by Bootstrap_Key->s (the TRGSW_DFT array)
+std::map<const void *, mb200_ksk *> g_ksk_cache;   // keyed by TLWE_KS_Key->s
+
+mb::Params to_params(const mb200_params *p) {
+  mb::Params q;
+  q.n = p->n; q.N = p->N; q.k = p->k; q.l = p->l; q.Bg_bit = p->Bg_bit; q.t = p->t; q.base_bit = p->base_bit;
+  return q;
+}
+
+void check_bsk_params(const mb::Params &p) {
+  MB_REQUIRE(p.N >= 16 && (p.N & (p.N - 1)) == 0 && p.N <= 8192, "N=%d must be a power of two in [16, 8192]", p.N);
+  MB_REQUIRE(p.k >= 1 && p.k <= 8, "k=%d out of range", p.k);
+  MB_REQUIRE(p.l >= 1 && p.Bg_bit >= 1 && p.l * p.Bg_bit <= 63, "gadget l=%d Bg_bit=%d invalid", p.l, p.Bg_bit);
+  MB_REQUIRE(p.n >= 1, "n=%d invalid", p.n);
+}
+
+size_t bsk_elems(const mb::Params &p) { return (size_t)p.n * (p.k + 1) * p.l * (p.k + 1) * (p.N / 2); }
+size_t ksk_rows(const mb::Params &p) { return (size_t)p.k * p.N * p.t * ((1u << p.base_bit) - 1); }
+
+// ---- per-thread staging (pinned host + device), grown on demand -----------------------------
+struct Scratch {
+  void *h = nullptr, *d = nullptr;
+  size_t hcap = 0, dcap = 0;
+  void *host(size_t bytes) {
+    if (bytes > hcap) {
+      if (h) MB_CHECK(cudaFreeHost(h));
+      hcap = bytes + bytes / 4 + 4096;
+      MB_CHECK(cudaMallocHost(&h, hcap));
+    }
+    return h;
+  }
+  void *dev(size_t bytes) {
+    if (bytes > dcap) {
+      if (d) MB_CHECK(cudaFree(d));
+      dcap = bytes + bytes / 4 + 4096;
+      MB_CHECK(cudaMalloc(&d, dcap));
+    }
+    return d;
+  }
+  void release() {
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    h = d = nullptr; hcap = dcap = 0;
+  }
+};
+enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_COUNT };
+thread_local Scratch t_scratch[S_COUNT];
+
+// ---- host FFT slot order ----------------------------------------------------------------------
+struct HostPolyU { u64 *coeffs; int N; };
+struct HostPolyD { double *coeffs; int N; };
+
+bool probe_host_exponents(int N, std::vector<int32_t> &e) {
+  typedef void (*fwd_t)(HostPolyD *, HostPolyU *);
+  void *sym = dlsym(RTLD_DEFAULT, "polynomial_torus_to_DFT");
+  if (!sym) return false;
+  fwd_t fwd = (fwd_t)sym;
+  void *pu = nullptr, *pd = nullptr;
+  if (posix_memalign(&pu, 64, sizeof(u64) * N) || posix_memalign(&pd, 64, sizeof(double) * N)) return false;
+  memset(pu, 0, sizeof(u64) * N);
+  ((u64 *)pu)[1] = 1;                                   // the monomial X: slot h then holds w^e_h
+  HostPolyU in{(u64 *)pu, N};
+  HostPolyD out{(double *)pd, N};
+  fwd(&out, &in);
+  const int M = N / 2;
+  e.resize(M);
+  for (int h = 0; h < M; ++h) {
+    const double ang = atan2(out.coeffs[h + M], out.coeffs[h]);
+    long v = lround(ang * N / M_PI);
+    e[h] = (int32_t)(((v % (2 * N)) + 2 * N) % (2 * N));
+  }
+  free(pu); free(pd);
+  return true;
+}
+
+void host_exponents(int N, std::vector<int32_t> &e, int layout_override = -1) {
+  int layout = layout_override >= 0 ? layout_override : g_host_layout;
+  if (layout == MB200_FFT_AUTO) {
+    MB_REQUIRE(probe_host_exponents(N, e),
+               "host FFT slot order unknown: polynomial_torus_to_DFT is not resolvable in this process; "
+               "call mb200_set_host_fft_layout(MB200_FFT_SPQLIOS | MB200_FFT_FFNT | MB200_FFT_NATURAL)");
+    return;
+  }
+  e.resize(N / 2);
+  mb::host_slot_exponents(layout, N, e.data());
+}
+
+// device-side maps for the DFT boundary ops (trgsw_mul_trlwe_DFT out, trlwe_from_DFT in)
+struct DftMaps { int *stored_to_host, *stored_conj, *pos_to_host, *pos_conj; };
+std::map<std::pair<int, int>, DftMaps> g_dft_maps;   // (N, layout)
+
+DftMaps dft_maps_for(int N) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_pair(N, g_host_layout);
+  auto it = g_dft_maps.find(key);
+  if (it != g_dft_maps.end()) return it->second;
+  const int M = N / 2;
+  std::vector<int32_t> e;
+  host_exponents(N, e);
+  std::vector<int> s2h(M), scj(M), p2h(M), pcj(M);
+  mb::slot_maps(N, e.data(), s2h.data(), scj.data());
+  for (int s = 0; s < M; ++s) {
+    const int idx = mb::stored_index_of_position(s, M);
+    p2h[s] = s2h[idx];
+    pcj[s] = scj[idx];
+  }
+  int *d = nullptr;
+  MB_CHECK(cudaMalloc(&d, sizeof(int) * 4 * M));
+  MB_CHECK(cudaMemcpy(d, s2h.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  MB_CHECK(cudaMemcpy(d + M, scj.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  MB_CHECK(cudaMemcpy(d + 2 * M, p2h.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  MB_CHECK(cudaMemcpy(d + 3 * M, pcj.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  DftMaps m{d, d + M, d + 2 * M, d + 3 * M};
+  g_dft_maps[key] = m;
+  return m;
+}
+
+// ---- key residency ------------------------------------------------------------------------------
+mb200_bsk *bsk_alloc(const mb::Params &p) {
+  check_bsk_params(p);
+  mb::ensure_init();
+  mb200_bsk *b = new mb200_bsk();
+  b->p = p;
+  b->owned = true;
+  MB_CHECK(cudaMalloc(&b->d, sizeof(double2) * bsk_elems(p)));
+  return b;
+}
+
+mb200_ksk *ksk_alloc(const mb::Params &p) {
+  mb::ensure_init();
+  MB_REQUIRE(p.t >= 1 && p.base_bit >= 1, "key switch parameters t=%d base_bit=%d invalid", p.t, p.base_bit);
+  mb200_ksk *k = new mb200_ksk();
+  k->p = p;
+  k->owned = true;
+  k->row_stride = mb::ksk_row_stride(p.n);
+  MB_CHECK(cudaMalloc(&k->d, sizeof(u64) * ksk_rows(p) * k->row_stride));
+  return k;
+}
+
+mb200_bsk *bsk_from_host_array(const mb::Params &p, const double *h_bsk, int layout) {
+  mb200_bsk *b = bsk_alloc(p);
+  const size_t doubles = bsk_elems(p) * 2;
+  double *d_tmp = nullptr;
+  MB_CHECK(cudaMalloc(&d_tmp, sizeof(double) * doubles));
+  MB_CHECK(cudaMemcpy(d_tmp, h_bsk, sizeof(double) * doubles, cudaMemcpyHostToDevice));
+  std::vector<int32_t> e;
+  host_exponents(p.N, e, layout);
+  mb::import_bsk(b, d_tmp, e.data(), mb::default_stream());
+  MB_CHECK(cudaFree(d_tmp));
+  return b;
+}
+
+mb200_bsk *lookup_bsk(Bootstrap_Key key) {
+  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
+  MB_REQUIRE(key->unfolding == 1,
+             "Bootstrap_Key with unfolding=%d: only unfolding==1 keys (Fourier-domain ->s) are accelerated",
+             key->unfolding);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bsk_cache.find((const void *)key->s);
+    if (it != g_bsk_cache.end()) return it->second;
+  }
+  mb::Params p{};
+  p.n = key->n; p.N = key->N; p.k = key->k; p.l = key->l; p.Bg_bit = key->Bg_bit; p.t = 0; p.base_bit = 0;
+  check_bsk_params(p);
+  // flatten the 10k+ separately allocated host polynomials (mosfhet.h:111-133) once
+  const size_t per_poly = (size_t)p.N;
+  const size_t polys = (size_t)p.n * (p.k + 1) * p.l * (p.k + 1);
+  std::vector<double> flat(polys * per_poly);
+  size_t o = 0;
+  for (int i = 0; i < p.n; ++i) {
+    TRGSW_DFT g = key->s[i];
+    MB_REQUIRE(g->l == p.l && g->Bg_bit == p.Bg_bit, "Bootstrap_Key: TRGSW %d gadget mismatch", i);
+    for (int r = 0; r < (p.k + 1) * p.l; ++r) {
+      TRLWE_DFT row = g->samples[r];
+      for (int q = 0; q <= p.k; ++q) {
+        DFT_Polynomial poly = q < p.k ? row->a[q] : row->b;
+        memcpy(&flat[o], poly->coeffs, sizeof(double) * per_poly);
+        o += per_poly;
+      }
+    }
+  }
+  mb200_bsk *b = bsk_from_host_array(p, flat.data(), -1);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_bsk_cache[(const void *)key->s] = b;
+  return b;
+}
+
+mb200_ksk *ksk_from_host_array(const mb::Params &p, const u64 *h_ksk) {
+  mb200_ksk *k = ksk_alloc(p);
+  const size_t rows = ksk_rows(p);
+  const int w = p.n + 1;
+  MB_CHECK(cudaMemset(k->d, 0, sizeof(u64) * rows * k->row_stride));
+  MB_CHECK(cudaMemcpy2D(k->d, sizeof(u64) * k->row_stride, h_ksk, sizeof(u64) * w, sizeof(u64) * w, rows,
+                        cudaMemcpyHostToDevice));
+  return k;
+}
+
+mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
+  MB_REQUIRE(key != nullptr, "TLWE_KS_Key is NULL");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ksk_cache.find((const void *)key->s);
+    if (it != g_ksk_cache.end()) return it->second;
+  }
+  mb::Params p{};
+  p.n = key->s[0][0][0]->n;
+  p.k = 1; p.N = key->n;                 // input dimension k*N is all the key switch needs
+  p.t = key->t; p.base_bit = key->base_bit;
+  const int bm1 = (1 << p.base_bit) - 1, w = p.n + 1;
+  std::vector<u64> flat((size_t)key->n * p.t * bm1 * w);
+  size_t o = 0;
+  for (int i = 0; i < key->n; ++i)
+    for (int j = 0; j < p.t; ++j)
+      for (int d = 0; d < bm1; ++d) {
+        TLWE row = key->s[i][j][d];
+        memcpy(&flat[o], row->a, sizeof(u64) * p.n);
+        flat[o + p.n] = row->b;
+        o += w;
+      }
+  mb200_ksk *k = ksk_from_host_array(p, flat.data());
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_ksk_cache[(const void *)key->s] = k;
+  (void)n_in_expected;
+  return k;
+}
+
+// ---- dispatch ----------------------------------------------------------------------------------
+void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
+  if (a.count <= 0) return;
+  const bool can_k1 = g_policy == 0 && !a.direct && mb::k1_supported(a.bsk->p);
+  if (can_k1) {
+    mb::launch_blind_rotate_k1(a, st);
+    g_last_kernel = mb::k1_variant_name(a.bsk->p);
+  } else {
+    mb::launch_blind_rotate_generic(a, st);
+    g_last_kernel = "generic";
+  }
+}
+
+u64 prec_offset_for(int torus_base) {
+  // double2torus(1./(4*torus_base)), misc.c:13-15 / bootstrap.c:194
+  return (u64)((int64_t)(18446744073709551616.0 * (1.0 / (4.0 * torus_base))));
+}
+
+cudaStream_t as_stream(void *s) { return s ? (cudaStream_t)s : mb::default_stream(); }
+
+void pbs_dev_impl(mb200_bsk_t bsk, u64 *d_out, int extract, const u64 *d_tv, int tv_count, const u64 *d_in,
+                  int torus_base, int count, cudaStream_t st, int preprocess = 0, int kappa = 0, int theta = 0) {
+  MB_REQUIRE(bsk && torus_base > 0 && (tv_count == 1 || tv_count == count), "pbs: bad arguments");
+  mb::BlindRotateLaunch a{};
+  a.bsk = bsk; a.tv = d_tv; a.tv_count = tv_count; a.in = d_in; a.in_stride = bsk->p.n + 1; a.size = bsk->p.n;
+  a.out = d_out; a.extract = extract; a.init_rotate = 1; a.prec_offset = prec_offset_for(torus_base);
+  a.preprocess = preprocess; a.kappa = kappa; a.theta = theta; a.count = count;
+  run_blind_rotate(a, st);
+}
+
+// ---- handle-tree gather / scatter -----------------------------------------------------------------
+void gather_tlwe(u64 *dst, TLWE *in, int count, int n) {
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(in[i]->n == n, "TLWE %d has dimension %d, expected %d", i, in[i]->n, n);
+    memcpy(dst + (size_t)i * (n + 1), in[i]->a, sizeof(u64) * n);
+    dst[(size_t)i * (n + 1) + n] = in[i]->b;
+  }
+}
+void scatter_tlwe(TLWE *out, const u64 *src, int count, int n) {
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(out[i]->n == n, "output TLWE %d has dimension %d, expected %d", i, out[i]->n, n);   // trlwe.c:542 / tlwe.c:293
+    memcpy(out[i]->a, src + (size_t)i * (n + 1), sizeof(u64) * n);
+    out[i]->b = src[(size_t)i * (n + 1) + n];
+  }
+}
+void gather_trlwe(u64 *dst, TRLWE *in, int count, int k, int N) {
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(in[i]->k == k && in[i]->b->N == N, "TRLWE %d has (k=%d, N=%d), expected (%d, %d)", i, in[i]->k,
+               in[i]->b->N, k, N);
+    for (int q = 0; q < k; ++q) memcpy(dst + ((size_t)i * (k + 1) + q) * N, in[i]->a[q]->coeffs, sizeof(u64) * N);
+    memcpy(dst + ((size_t)i * (k + 1) + k) * N, in[i]->b->coeffs, sizeof(u64) * N);
+  }
+}
+void scatter_trlwe(TRLWE *out, const u64 *src, int count, int k, int N) {
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(out[i]->k == k && out[i]->b->N == N, "output TRLWE %d has (k=%d, N=%d), expected (%d, %d)", i,
+               out[i]->k, out[i]->b->N, k, N);
+    for (int q = 0; q < k; ++q) memcpy(out[i]->a[q]->coeffs, src + ((size_t)i * (k + 1) + q) * N, sizeof(u64) * N);
+    memcpy(out[i]->b->coeffs, src + ((size_t)i * (k + 1) + k) * N, sizeof(u64) * N);
+  }
+}
+
+struct PbsStaged {
+  u64 *d_in, *d_tv;
+};
+
+PbsStaged stage_pbs_inputs(TRLWE *tv, int tv_count, TLWE *in, const mb::Params &p, int count, cudaStream_t st) {
+  const size_t in_bytes = sizeof(u64) * (size_t)count * (p.n + 1);
+  const size_t tv_bytes = sizeof(u64) * (size_t)tv_count * (p.k + 1) * p.N;
+  u64 *h_in = (u64 *)t_scratch[S_IN].host(in_bytes), *d_in = (u64 *)t_scratch[S_IN].dev(in_bytes);
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_bytes), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_bytes);
+  gather_tlwe(h_in, in, count, p.n);
+  gather_trlwe(h_tv, tv, tv_count, p.k, p.N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_bytes, cudaMemcpyHostToDevice, st));
+  return PbsStaged{d_in, d_tv};
+}
+
+}  // namespace
+
+// ===================================================================================================
+extern "C" {
+
+int mb200_device_count(void) { return mb::device_count_noabort(); }
+const char *mb200_version(void) { return "mosfhet_b200 0.1 (sm_100a)"; }
+
+int mb200_init(int device) {
+  if (device == -2) return mb::device_count_noabort() > 0 ? 0 : -1;
+  mb::init_device(device);
+  return 0;
+}
+
+void mb200_device_synchronize(void) { mb::ensure_init(); MB_CHECK(cudaDeviceSynchronize()); }
+
+void mb200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_bsk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
+  for (auto &kv : g_ksk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
+  g_bsk_cache.clear();
+  g_ksk_cache.clear();
+  for (auto &kv : g_dft_maps) cudaFree(kv.second.stored_to_host);
+  g_dft_maps.clear();
+  for (int i = 0; i < S_COUNT; ++i) t_scratch[i].release();
+  mb::drop_tables();
+}
+
+void mb200_set_host_fft_layout(int layout) {
+  MB_REQUIRE(layout >= MB200_FFT_AUTO && layout <= MB200_FFT_NATURAL, "unknown FFT layout %d", layout);
+  g_host_layout = layout;
+}
+int mb200_get_host_fft_layout(void) { return g_host_layout; }
+void mb200_host_slot_exponents(int layout, int N, int32_t *e_out) {
+  std::vector<int32_t> e;
+  host_exponents(N, e, layout);
+  memcpy(e_out, e.data(), sizeof(int32_t) * (N / 2));
+}
+
+void mb200_register_bootstrap_key(Bootstrap_Key key) { (void)lookup_bsk(key); }
+void mb200_release_bootstrap_key(Bootstrap_Key key) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_bsk_cache.find((const void *)key->s);
+  if (it == g_bsk_cache.end()) return;
+  if (it->second->owned) cudaFree(it->second->d);
+  delete it->second;
+  g_bsk_cache.erase(it);
+}
+void mb200_register_ks_key(TLWE_KS_Key key) { (void)lookup_ksk(key, 0); }
+void mb200_release_ks_key(TLWE_KS_Key key) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_ksk_cache.find((const void *)key->s);
+  if (it == g_ksk_cache.end()) return;
+  if (it->second->owned) cudaFree(it->second->d);
+  delete it->second;
+  g_ksk_cache.erase(it);
+}
+
+// ---- flat API --------------------------------------------------------------------------------------
+size_t mb200_bsk_device_bytes(const mb200_params *p) { return sizeof(double2) * bsk_elems(to_params(p)); }
+size_t mb200_ksk_device_bytes(const mb200_params *p) {
+  return sizeof(u64) * ksk_rows(to_params(p)) * mb::ksk_row_stride(p->n);
+}
+mb200_bsk_t mb200_bsk_from_host(const mb200_params *p, const double *h_bsk, int layout) {
+  return bsk_from_host_array(to_params(p), h_bsk, layout == MB200_FFT_AUTO ? -1 : layout);
+}
+mb200_ksk_t mb200_ksk_from_host(const mb200_params *p, const uint64_t *h_ksk) {
+  return ksk_from_host_array(to_params(p), (const u64 *)h_ksk);
+}
+mb200_bsk_t mb200_bsk_adopt_device(const mb200_params *p, void *d_bsk) {
+  mb::ensure_init();
+  mb200_bsk *b = new mb200_bsk();
+  b->p = to_params(p);
+  check_bsk_params(b->p);
+  b->d = (double2 *)d_bsk;
+  b->owned = false;
+  return b;
+}
+mb200_ksk_t mb200_ksk_adopt_device(const mb200_params *p, void *d_ksk) {
+  mb::ensure_init();
+  mb200_ksk *k = new mb200_ksk();
+  k->p = to_params(p);
+  k->d = (u64 *)d_ksk;
+  k->row_stride = mb::ksk_row_stride(p->n);
+  k->owned = false;
+  return k;
+}
+void *mb200_bsk_device_ptr(mb200_bsk_t bsk) { return bsk->d; }
+void *mb200_ksk_device_ptr(mb200_ksk_t ksk) { return ksk->d; }
+void mb200_bsk_free(mb200_bsk_t bsk) {
+  if (!bsk) return;
+  if (bsk->owned) cudaFree(bsk->d);
+  delete bsk;
+}
+void mb200_ksk_free(mb200_ksk_t ksk) {
+  if (!ksk) return;
+  if (ksk->owned) cudaFree(ksk->d);
+  delete ksk;
+}
+
+mb200_bsk_t mb200_bsk_synthesize(const mb200_params *p, const uint64_t *h_lwe_key, const uint64_t *h_rlwe_key,
+                                 double rlwe_sigma, uint64_t seed) {
+  mb200_bsk *b = bsk_alloc(to_params(p));
+  mb::synth_bsk(b, (const u64 *)h_lwe_key, (const u64 *)h_rlwe_key, rlwe_sigma, seed, mb::default_stream());
+  return b;
+}
+mb200_ksk_t mb200_ksk_synthesize(const mb200_params *p, const uint64_t *h_rlwe_key, const uint64_t *h_lwe_key,
+                                 double lwe_sigma, uint64_t seed) {
+  mb200_ksk *k = ksk_alloc(to_params(p));
+  mb::synth_ksk(k, (const u64 *)h_rlwe_key, (const u64 *)h_lwe_key, lwe_sigma, seed, mb::default_stream());
+  return k;
+}
+
+void mb200_pbs_dev(mb200_bsk_t bsk, uint64_t *d_out, const uint64_t *d_tv, int tv_count, const uint64_t *d_in,
+                   int torus_base, int count, void *stream) {
+  pbs_dev_impl(bsk, (u64 *)d_out, 1, (const u64 *)d_tv, tv_count, (const u64 *)d_in, torus_base, count, as_stream(stream));
+}
+void mb200_pbs_wo_extract_dev(mb200_bsk_t bsk, uint64_t *d_out, const uint64_t *d_tv, int tv_count,
+                              const uint64_t *d_in, int torus_base, int count, void *stream) {
+  pbs_dev_impl(bsk, (u64 *)d_out, 0, (const u64 *)d_tv, tv_count, (const u64 *)d_in, torus_base, count, as_stream(stream));
+}
+void mb200_blind_rotate_dev(mb200_bsk_t bsk, uint64_t *d_acc, const uint64_t *d_a, int a_stride, int size, int count,
+                            void *stream) {
+  MB_REQUIRE(size <= bsk->p.n, "blind_rotate: size %d exceeds the %d resident TRGSW samples", size, bsk->p.n);
+  mb::BlindRotateLaunch a{};
+  a.bsk = bsk; a.tv = (const u64 *)d_acc; a.tv_count = count > 1 ? count : 1; a.in = (const u64 *)d_a;
+  a.in_stride = a_stride; a.size = size; a.out = (u64 *)d_acc; a.extract = 0; a.init_rotate = 0; a.count = count;
+  if (count == 1) a.tv_count = 1;
+  run_blind_rotate(a, as_stream(stream));
+}
+void mb200_extract_dev(uint64_t *d_out, const uint64_t *d_trlwe, const int *h_idx, int idx_count, int N, int k,
+                       int count, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  int *d_idx = (int *)t_scratch[S_MISC2].dev(sizeof(int) * idx_count);
+  MB_CHECK(cudaMemcpyAsync(d_idx, h_idx, sizeof(int) * idx_count, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < idx_count; ++i) MB_REQUIRE(h_idx[i] >= 0 && h_idx[i] < N, "extract index %d out of range", h_idx[i]);
+  mb::launch_extract((u64 *)d_out, (const u64 *)d_trlwe, d_idx, idx_count, N, k, count, st);
+}
+void mb200_ks_dev(mb200_ksk_t ksk, uint64_t *d_out, const uint64_t *d_in, int count, void *stream) {
+  mb::launch_keyswitch(ksk, (u64 *)d_out, (const u64 *)d_in, count, as_stream(stream));
+}
+void mb200_pbs_ks_dev(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *d_out, const uint64_t *d_tv, int tv_count,
+                      const uint64_t *d_in, uint64_t *d_scratch, int torus_base, int count, void *stream) {
+  MB_REQUIRE(ksk->p.k * ksk->p.N == bsk->p.k * bsk->p.N && ksk->p.n == bsk->p.n,
+             "pbs_ks: key switch (%d -> %d) does not chain with the bootstrap (%d -> %d)", ksk->p.k * ksk->p.N,
+             ksk->p.n, bsk->p.n, bsk->p.k * bsk->p.N);
+  cudaStream_t st = as_stream(stream);
+  pbs_dev_impl(bsk, (u64 *)d_scratch, 1, (const u64 *)d_tv, tv_count, (const u64 *)d_in, torus_base, count, st);
+  mb::launch_keyswitch(ksk, (u64 *)d_out, (const u64 *)d_scratch, count, st);
+}
+void mb200_extprod_dev(mb200_bsk_t set, const int *h_sel, uint64_t *d_out, const uint64_t *d_in, int count, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  int *d_sel = (int *)t_scratch[S_MISC2].dev(sizeof(int) * count);
+  for (int i = 0; i < count; ++i) MB_REQUIRE(h_sel[i] >= 0 && h_sel[i] < set->p.n, "extprod: selector %d out of range", h_sel[i]);
+  MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+  mb::BlindRotateLaunch a{};
+  a.bsk = set; a.tv = (const u64 *)d_in; a.tv_count = count; a.size = 1; a.out = (u64 *)d_out; a.count = count;
+  a.direct = 1; a.sel = d_sel;
+  if (count == 1) a.tv_count = 1;
+  mb::launch_blind_rotate_generic(a, st);
+  g_last_kernel = "generic";
+}
+void mb200_torus_to_dft_dev(double *d_out, const uint64_t *d_in, int N, int count, void *stream) {
+  mb::launch_torus_to_dft(d_out, (const u64 *)d_in, N, count, as_stream(stream));
+}
+void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int count, void *stream) {
+  mb::launch_dft_to_torus((u64 *)d_out, d_in, N, count, nullptr, nullptr, as_stream(stream));
+}
+
+// ---- host-buffer batch ops -------------------------------------------------------------------------
+void mb200_pbs_ks_host(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_tv, int tv_count,
+                       const uint64_t *h_in, int torus_base, int count) {
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), tv_b = sizeof(u64) * (size_t)tv_count * (p.k + 1) * p.N;
+  const size_t mid_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1), out_b = in_b;
+  u64 *d_in = (u64 *)t_scratch[S_IN].dev(in_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  u64 *d_mid = (u64 *)t_scratch[S_MID].dev(mid_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  mb200_pbs_ks_dev(bsk, ksk, (uint64_t *)d_out, (const uint64_t *)d_tv, tv_count, (const uint64_t *)d_in,
+                   (uint64_t *)d_mid, torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+}
+void mb200_pbs_host(mb200_bsk_t bsk, uint64_t *h_out, const uint64_t *h_tv, int tv_count, const uint64_t *h_in,
+                    int torus_base, int count) {
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), tv_b = sizeof(u64) * (size_t)tv_count * (p.k + 1) * p.N;
+  const size_t out_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1);
+  u64 *d_in = (u64 *)t_scratch[S_IN].dev(in_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  pbs_dev_impl(bsk, d_out, 1, d_tv, tv_count, d_in, torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+}
+void mb200_ks_host(mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_in, int count) {
+  const mb::Params &p = ksk->p;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1), out_b = sizeof(u64) * (size_t)count * (p.n + 1);
+  u64 *d_in = (u64 *)t_scratch[S_MID].dev(in_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  mb::launch_keyswitch(ksk, d_out, d_in, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+}
+
+uint64_t mb200_launch_count(void) { return mb::launches(); }
+void mb200_reset_launch_count(void) { mb::reset_launches(); }
+const char *mb200_last_blind_rotate_kernel(void) { return g_last_kernel.c_str(); }
+void mb200_set_kernel_policy(int policy) { g_policy = policy; }
+
+// ---- batched handle API ------------------------------------------------------------------------------
+void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
+                                           int torus_base, int count) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
+  const size_t out_b = sizeof(u64) * (size_t)count * (p.k + 1) * p.N;
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  pbs_dev_impl(bsk, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(out, h_out, count, p.k, p.N);
+}
+
+static void fb_batch_impl(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int torus_base, int count,
+                          int preprocess, int kappa, int theta) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
+  const size_t out_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  pbs_dev_impl(bsk, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st, preprocess, kappa, theta);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, p.k * p.N);
+}
+
+void functional_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int torus_base,
+                                int count) {
+  fb_batch_impl(out, tv, tv_count, in, key, torus_base, count, 0, 0, 0);
+}
+
+void programmable_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int precision,
+                                  int kappa, int theta, int count) {
+  // bootstrap.c:208-220: shape the input, then functional_bootstrap with torus_base = 2^(precision-1)
+  fb_batch_impl(out, tv, tv_count, in, key, 1 << (precision - 1), count, 1, kappa, theta);
+}
+
+void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count) {
+  if (count <= 0) return;
+  mb200_ksk *ksk = lookup_ksk(ks_key, in[0]->n);
+  const mb::Params &p = ksk->p;
+  const int n_in = p.k * p.N;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (n_in + 1), out_b = sizeof(u64) * (size_t)count * (p.n + 1);
+  u64 *h_in = (u64 *)t_scratch[S_MID].host(in_b), *d_in = (u64 *)t_scratch[S_MID].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_tlwe(h_in, in, count, n_in);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  mb::launch_keyswitch(ksk, d_out, d_in, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, p.n);
+}
+
+void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
+                                          TLWE_KS_Key ks_key, int torus_base, int count) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  mb200_ksk *ksk = lookup_ksk(ks_key, bsk->p.k * bsk->p.N);
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
+  const size_t mid_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1), out_b = sizeof(u64) * (size_t)count * (p.n + 1);
+  u64 *d_mid = (u64 *)t_scratch[S_MID].dev(mid_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  mb200_pbs_ks_dev(bsk, ksk, (uint64_t *)d_out, (const uint64_t *)s.d_tv, tv_count, (const uint64_t *)s.d_in,
+                   (uint64_t *)d_mid, torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, p.n);
+}
+
+void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count) {
+  if (count <= 0 || size <= 0) return;
+  // `s` is a bare TRGSW_DFT array (mosfhet.h:409): registered keys are found by pointer, anything
+  // else (e.g. fresh encrypted selectors, vertical_packing.c:50) is uploaded for this call only.
+  mb200_bsk *bsk = nullptr;
+  bool temporary = false;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bsk_cache.find((const void *)s);
+    if (it != g_bsk_cache.end()) bsk = it->second;
+  }
+  const int k = tv[0]->k, N = tv[0]->b->N;
+  if (!bsk) {
+    struct _Bootstrap_Key tmp;
+    tmp.s = s; tmp.su = nullptr; tmp.n = size; tmp.k = k; tmp.N = N; tmp.Bg_bit = s[0]->Bg_bit; tmp.l = s[0]->l;
+    tmp.unfolding = 1;
+    bsk = lookup_bsk(&tmp);
+    temporary = true;
+  }
+  MB_REQUIRE(size <= bsk->p.n, "blind_rotate: size %d exceeds key length %d", size, bsk->p.n);
+  cudaStream_t st = mb::default_stream();
+  const size_t a_b = sizeof(u64) * (size_t)count * size, acc_b = sizeof(u64) * (size_t)count * (k + 1) * N;
+  u64 *h_a = (u64 *)t_scratch[S_IN].host(a_b), *d_a = (u64 *)t_scratch[S_IN].dev(a_b);
+  u64 *h_acc = (u64 *)t_scratch[S_TV].host(acc_b), *d_acc = (u64 *)t_scratch[S_TV].dev(acc_b);
+  for (int i = 0; i < count; ++i) memcpy(h_a + (size_t)i * size, a[i], sizeof(u64) * size);
+  gather_trlwe(h_acc, tv, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_a, h_a, a_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_acc, h_acc, acc_b, cudaMemcpyHostToDevice, st));
+  mb200_blind_rotate_dev(bsk, (uint64_t *)d_acc, (const uint64_t *)d_a, size, size, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_acc, d_acc, acc_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(tv, h_acc, count, k, N);
+  if (temporary) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_bsk_cache.erase((const void *)s);
+    if (bsk->owned) cudaFree(bsk->d);
+    delete bsk;
+  }
+}
+
+void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int in2_count, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(in2_count == 1 || in2_count == count, "trgsw_mul_trlwe_DFT_batch: in2_count must be 1 or count");
+  const int k = in1[0]->k, N = in1[0]->b->N;
+  MB_REQUIRE(k == in2[0]->samples[0]->k, "trgsw_mul_trlwe_DFT: k mismatch (trgsw.c:389)");
+  struct _Bootstrap_Key tmp;
+  tmp.s = in2; tmp.su = nullptr; tmp.n = in2_count; tmp.k = k; tmp.N = N; tmp.Bg_bit = in2[0]->Bg_bit; tmp.l = in2[0]->l;
+  tmp.unfolding = 1;
+  mb200_bsk *set;
+  bool cached;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cached = g_bsk_cache.count((const void *)in2) != 0;
+  }
+  set = lookup_bsk(&tmp);
+  cudaStream_t st = mb::default_stream();
+  DftMaps maps = dft_maps_for(N);
+  const size_t in_b = sizeof(u64) * (size_t)count * (k + 1) * N, out_b = sizeof(double) * (size_t)count * (k + 1) * N;
+  u64 *h_in = (u64 *)t_scratch[S_TV].host(in_b), *d_in = (u64 *)t_scratch[S_TV].dev(in_b);
+  double *h_out = (double *)t_scratch[S_OUT].host(out_b), *d_out = (double *)t_scratch[S_OUT].dev(out_b);
+  int *h_sel = (int *)t_scratch[S_MISC].host(sizeof(int) * count), *d_sel = (int *)t_scratch[S_MISC].dev(sizeof(int) * count);
+  for (int i = 0; i < count; ++i) h_sel[i] = in2_count == 1 ? 0 : i;
+  gather_trlwe(h_in, in1, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+  mb::BlindRotateLaunch a{};
+  a.bsk = set; a.tv = d_in; a.tv_count = count; a.size = 1; a.out = nullptr; a.count = count; a.direct = 1; a.sel = d_sel;
+  a.dft_out = d_out; a.dft_perm = maps.stored_to_host; a.dft_conj = maps.stored_conj;
+  mb::launch_blind_rotate_generic(a, st);
+  g_last_kernel = "generic";
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(out[i]->k == k && out[i]->b->N == N, "output TRLWE_DFT %d shape mismatch", i);
+    for (int q = 0; q < k; ++q) memcpy(out[i]->a[q]->coeffs, h_out + ((size_t)i * (k + 1) + q) * N, sizeof(double) * N);
+    memcpy(out[i]->b->coeffs, h_out + ((size_t)i * (k + 1) + k) * N, sizeof(double) * N);
+  }
+  if (!cached) {   // operand was not a registered key: do not keep it resident
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_bsk_cache.erase((const void *)in2);
+    if (set->owned) cudaFree(set->d);
+    delete set;
+  }
+}
+
+void trlwe_from_DFT_batch(TRLWE *out, TRLWE_DFT *in, int count) {
+  if (count <= 0) return;
+  const int k = in[0]->k, N = in[0]->b->N;
+  cudaStream_t st = mb::default_stream();
+  DftMaps maps = dft_maps_for(N);
+  const size_t in_b = sizeof(double) * (size_t)count * (k + 1) * N, out_b = sizeof(u64) * (size_t)count * (k + 1) * N;
+  double *h_in = (double *)t_scratch[S_TV].host(in_b), *d_in = (double *)t_scratch[S_TV].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(in[i]->k == k && in[i]->b->N == N, "TRLWE_DFT %d shape mismatch", i);
+    for (int q = 0; q < k; ++q) memcpy(h_in + ((size_t)i * (k + 1) + q) * N, in[i]->a[q]->coeffs, sizeof(double) * N);
+    memcpy(h_in + ((size_t)i * (k + 1) + k) * N, in[i]->b->coeffs, sizeof(double) * N);
+  }
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  mb::launch_dft_to_torus(d_out, d_in, N, count * (k + 1), maps.pos_to_host, maps.pos_conj, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(out, h_out, count, k, N);
+}
+
+void trlwe_extract_tlwe_batch(TLWE *out, TRLWE *in, const int *idx, int idx_count, int count) {
+  if (count <= 0 || idx_count <= 0) return;
+  const int k = in[0]->k, N = in[0]->b->N;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (k + 1) * N;
+  const size_t out_b = sizeof(u64) * (size_t)count * idx_count * (k * N + 1);
+  u64 *h_in = (u64 *)t_scratch[S_TV].host(in_b), *d_in = (u64 *)t_scratch[S_TV].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_trlwe(h_in, in, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  mb200_extract_dev((uint64_t *)d_out, (const uint64_t *)d_in, idx, idx_count, N, k, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count * idx_count, k * N);
+}
+
+void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
+                                       int torus_base, int n_luts, int count) {
+  // bootstrap.c:222-230: one blind rotation with torus_base*n_luts, then n_luts extractions
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
+  const int slot_size = p.N / (n_luts * torus_base);
+  std::vector<int> idx(n_luts);
+  for (int i = 0; i < n_luts; ++i) idx[i] = i * slot_size;
+  const size_t acc_b = sizeof(u64) * (size_t)count * (p.k + 1) * p.N;
+  const size_t out_b = sizeof(u64) * (size_t)count * n_luts * (p.k * p.N + 1);
+  u64 *d_acc = (u64 *)t_scratch[S_MID].dev(acc_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  pbs_dev_impl(bsk, d_acc, 0, s.d_tv, tv_count, s.d_in, torus_base * n_luts, count, st);
+  mb200_extract_dev((uint64_t *)d_out, (const uint64_t *)d_acc, idx.data(), n_luts, p.N, p.k, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int c = 0; c < count; ++c) scatter_tlwe(out[c], h_out + (size_t)c * n_luts * (p.k * p.N + 1), n_luts, p.k * p.N);
+}
+
+// ---- drop-in single-ciphertext entry points (reference names) ------------------------------------------
+void functional_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base) {
+  functional_bootstrap_batch(&out, &tv, 1, &in, key, torus_base, 1);
+}
+void functional_bootstrap_wo_extract(TRLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base) {
+  functional_bootstrap_wo_extract_batch(&out, &tv, 1, &in, key, torus_base, 1);
+}
+void programmable_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int precision, int kappa, int theta) {
+  programmable_bootstrap_batch(&out, &tv, 1, &in, key, precision, kappa, theta, 1);
+}
+void blind_rotate(TRLWE tv, Torus *a, TRGSW_DFT *s, int size) { blind_rotate_batch(&tv, &a, s, size, 1); }
+void trgsw_mul_trlwe_DFT(TRLWE_DFT out, TRLWE in1, TRGSW_DFT in2) { trgsw_mul_trlwe_DFT_batch(&out, &in1, &in2, 1, 1); }
+void trlwe_from_DFT(TRLWE out, TRLWE_DFT in) { trlwe_from_DFT_batch(&out, &in, 1); }
+void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_batch(&out, &in, &idx, 1, 1); }
+void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key) { tlwe_keyswitch_batch(&out, &in, ks_key, 1); }
+void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base, int n_luts) {
+  multivalue_bootstrap_CLOT21_batch(&out, &tv, 1, &in, key, torus_base, n_luts, 1);
+}
+
+}  // extern "C"

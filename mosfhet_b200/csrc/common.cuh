@@ -1,0 +1,118 @@
+// common.cuh -- shared declarations for libmosfhet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+#define MB_CHECK(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      fprintf(stderr, "mosfhet_b200: CUDA error '%s' at %s:%d (%s) -- no CPU fallback, aborting\n", \
+              cudaGetErrorString(_e), __FILE__, __LINE__, #expr);                              \
+      abort();                                                                                 \
+    }                                                                                          \
+  } while (0)
+
+#define MB_FATAL(...)                                                                          \
+  do {                                                                                         \
+    fprintf(stderr, "mosfhet_b200: " __VA_ARGS__);                                             \
+    fprintf(stderr, "\n");                                                                     \
+    abort();                                                                                   \
+  } while (0)
+
+#define MB_REQUIRE(cond, ...)                                                                  \
+  do { if (!(cond)) MB_FATAL(__VA_ARGS__); } while (0)
+
+namespace mb {
+
+// ---- parameters of one resident key / one launch ------------------------------------------
+struct Params {
+  int n, N, k, l, Bg_bit, t, base_bit;
+};
+
+// Resident bootstrapping key: double2 [n][(k+1)*l][(k+1)][M] in the tiled internal slot order
+// (see keys.cu: stored index m*(M/8)+c  <->  FFT position 8c+m  <->  frequency bitrev(position)).
+struct BskDev {
+  Params p;
+  double2 *d;
+  bool owned;
+};
+
+// Resident key-switching table: u64 [N_in][t][2^base_bit-1][row_stride], row_stride = round_up(n+1, 4)
+struct KskDev {
+  Params p;
+  u64 *d;
+  int row_stride;
+  bool owned;
+};
+
+inline int ilog2i(int x) { int r = 0; while ((1 << r) < x) ++r; return r; }
+inline int ksk_row_stride(int n_out) { return (n_out + 1 + 3) & ~3; }
+
+// ---- twiddle tables (tables.cu) -------------------------------------------------------------
+// tw[j] = exp(i*pi*j/N), j in [0, N): covers the twist (j < N/2) and every FFT twiddle of the
+// N/2-point transform (W_M^t = tw[4t], t < M/2).
+const double2 *twiddles_for(int N);
+// Per-thread pass tables of the specialised k=1 kernel (blind_rotate_k1.cu).
+const double2 *k1_tables_for(int N);
+
+// ---- launch accounting ------------------------------------------------------------------------
+void count_launch(int n = 1);
+
+// ---- context ----------------------------------------------------------------------------------
+void ensure_init();
+cudaStream_t default_stream();
+int sm_count();
+
+// ---- kernels' host-side launchers ---------------------------------------------------------------
+struct BlindRotateLaunch {
+  const BskDev *bsk;
+  const u64 *tv;        // [(tv_count)][(k+1)*N] initial accumulator(s)
+  int tv_count;
+  const u64 *in;        // [count][in_stride]: a[0..size) (and b at index `size` when init_rotate)
+  int in_stride;
+  int size;             // number of blind-rotation steps (= n for a bootstrap)
+  u64 *out;             // mode 0: [count][(k+1)*N] accumulator; mode 1: [count][k*N+1] TLWE (extract idx 0)
+  int extract;          // 0 / 1
+  int init_rotate;      // 1: acc = tv * X^(2N - round((b+prec_offset)*2N)) (bootstrap.c:194-195); 0: acc = tv
+  u64 prec_offset;
+  int preprocess;       // programmable_bootstrap input shaping (bootstrap.c:210-217)
+  int kappa, theta;
+  int count;
+  // single external product mode (trgsw.c:385): out = TRGSW[sel[ct]] (.) in, no rotation, no accumulate
+  int direct;
+  const int *sel;       // device [count] or nullptr (-> step index)
+  double *dft_out;      // when non-null: write the Fourier-domain result [count][(k+1)][N] (Re|Im) in
+  const int *dft_perm;  //   host slot order via dft_perm/dft_conj (device [M]) instead of inverting
+  const int *dft_conj;
+};
+
+void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);
+bool k1_supported(const Params &p);
+void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
+const char *k1_variant_name(const Params &p);
+
+void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st);
+void launch_extract(u64 *out, const u64 *trlwe, const int *d_idx, int idx_count, int N, int k, int count,
+                    cudaStream_t st);
+void launch_torus_to_dft(double *out, const u64 *in, int N, int count, cudaStream_t st);
+void launch_dft_to_torus(u64 *out, const double *in, int N, int count, const int *perm, const int *conj,
+                         cudaStream_t st);
+
+// keys.cu
+void import_bsk(BskDev *dst, const double *d_host_layout /* device copy of the host-form key */, const int32_t *h_exponents,
+                cudaStream_t st);
+void synth_bsk(BskDev *dst, const u64 *h_lwe_key, const u64 *h_rlwe_key, double sigma, u64 seed, cudaStream_t st);
+void synth_ksk(KskDev *dst, const u64 *h_in_key, const u64 *h_out_key, double sigma, u64 seed, cudaStream_t st);
+void host_slot_exponents(int layout, int N, int32_t *e);
+// host slot h -> (internal stored index, conj flag); used by import and by the DFT-boundary ops
+void slot_maps(int N, const int32_t *e, int *stored_to_host /* M */, int *stored_conj /* M */);
+int stored_index_of_position(int s, int M);
+int position_of_stored_index(int idx, int M);
+
+}  // namespace mb
