@@ -50,6 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                "-Xcompiler", "-fPIC", "-I", INCLUDE, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("MB200_K1_EXPERIMENTS"):
+            cmd.insert(1, "-DMB200_K1_EXPERIMENTS")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

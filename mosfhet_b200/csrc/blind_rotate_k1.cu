@@ -107,17 +107,37 @@ struct K1Args {
   int Bg_bit;
 };
 
-template <int LOGM, int L, int LB>
-__global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args A) {
+// f64 -> u64 mod 2^64, round to nearest (AVX-512 path of the reference, fft_processor_spqlios.c:158-164)
+// done on the FP64 pipe + one F2I instead of ~25 integer instructions: r = rint(x / 2^64) by the
+// 1.5*2^52 trick (|x| < 2^115), y = x - r*2^64 is exact and |y| <= 2^63, then a rounding convert.
+__device__ __forceinline__ u64 f64_to_torus_fast(double x) {
+  const double C = 6755399441055744.0;
+  const double t = x * 5.42101086242752217e-20;       // 2^-64
+  const double r = (t + C) - C;
+  const double y = fma(r, -18446744073709551616.0, x);
+  return (u64)__double2ll_rn(y);
+}
+
+__device__ __forceinline__ double2 ldg_key(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+template <int LOGM, int L, int LB, int MINB>
+__global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
   constexpr int LOGR2 = clog2(R2);
   constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;
+  constexpr int PB_UNROLL = R2 <= 4 ? 4 : 2;          // independent pass-B butterflies in flight per thread
+  constexpr int PC_UNROLL = 2;                        // rows of pass C whose key loads overlap
   static_assert(L % LB == 0, "levels per batch must divide l");
   static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *acc = reinterpret_cast<u64 *>(smem_raw);                       // [2][N]
   double2 *buf = reinterpret_cast<double2 *>(acc + 2 * N);           // [ROWS_B][M]
+  unsigned short *rot = reinterpret_cast<unsigned short *>(buf + ROWS_B * M);   // [size] rotation amounts
 
   const int tid = threadIdx.x, ct = blockIdx.x;
   const int log_N2 = LOGM + 2;
@@ -138,19 +158,24 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
     const int p = c / N, i = c - p * N;
     acc[c] = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
   }
+  // all rotation amounts up front: round(a_i * 2N / 2^64) (bootstrap.c:113), one 16-bit word per step
+  for (int i = tid; i < A.size; i += T) {
+    u64 av = in[i];
+    if (A.preprocess) av = pb_preprocess(av, A.kappa, A.theta, log_N2);
+    rot[i] = (unsigned short)(torus2int(av, log_N2) & (2 * N - 1));
+  }
   __syncthreads();
 
   const u64 off = decomp_offset(Bg_bit, L);
-  const u64 dmask = (1ull << Bg_bit) - 1ull;
-  const int half_bg = 1 << (Bg_bit - 1);
+  const unsigned dmask = (1u << Bg_bit) - 1u;
+  // digit u in [0, Bg) -> double(u - Bg/2) = hiloint2double(0x43300000, u) - (2^52 + Bg/2), exact
+  const double dbias = 4503599627370496.0 + (double)(1 << (Bg_bit - 1));
   const double inv_M = 1.0 / (double)M;
   const int pA = tid / S, qA = tid - pA * S;          // pass A / A' ownership
   const int qpB = tid & 7;                            // pass B twiddle column (T is a multiple of 8)
 
   for (int step = 0; step < A.size; ++step) {
-    u64 av = in[step];
-    if (A.preprocess) av = pb_preprocess(av, A.kappa, A.theta, log_N2);
-    const int a_i = (int)torus2int(av, log_N2) & (2 * N - 1);
+    const int a_i = rot[step];
     if (a_i == 0) continue;                           // bootstrap.c:114
     const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M;
 
@@ -165,23 +190,31 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
       // ------------------------------- pass A -------------------------------------------------
       {
         const u64 *ap = acc + pA * N;
-        u64 v0[16], v1[16];
+        // top LB*Bg_bit bits (this batch's digits) of (X^a - 1)*acc + rounding offset, one word per coefficient
+        const int pk_shift = 64 - (lev0 + LB) * Bg_bit;
+        const int base = (qA - a_i) & (2 * N - 1);     // index of coefficient qA in acc * X^a (sign in bit log2 N)
+        unsigned pk0[16], pk1[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int j = qA + m * S;
-          v0[m] = rotated_coeff(ap, j, a_i, N) - ap[j] + off;          // (X^a - 1) * acc, + rounding offset
-          v1[m] = rotated_coeff(ap, j + M, a_i, N) - ap[j + M] + off;
+          const int s0 = (base + m * S) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
+          const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
+          const u64 t0 = off - ap[j], t1 = off - ap[j + M];
+          const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
+          const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
+          pk0[m] = (unsigned)(v0 >> pk_shift);
+          pk1[m] = (unsigned)(v1 >> pk_shift);
         }
-#pragma unroll
+#pragma unroll 1
         for (int lb = 0; lb < LB; ++lb) {
-          const int sh = 64 - (lev0 + lb + 1) * Bg_bit;
+          const int sh = (LB - 1 - lb) * Bg_bit;
           double2 x[16];
 #pragma unroll
           for (int m = 0; m < 16; ++m) {
-            const int d0 = (int)((v0[m] >> sh) & dmask) - half_bg;
-            const int d1 = (int)((v1[m] >> sh) & dmask) - half_bg;
+            const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
+            const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
             // fold z = d0 + i*d1 and the constant part of the twist, w^(m*M/16) = W_64^m
-            x[m] = mul_w64(make_double2((double)d0, (double)d1), m, false);
+            x[m] = mul_w64(make_double2(d0, d1), m, false);
           }
           reg_dif<16>(x);
           double2 *row = buf + (pA * LB + lb) * M;
@@ -194,8 +227,11 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
       }
       __syncthreads();
       // ------------------------------- pass B -------------------------------------------------
-#pragma unroll 1
-      for (int task = tid; task < ROWS_B * 128; task += T) {
+      constexpr int TASKS_B = ROWS_B * 128 / T;
+      static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
+#pragma unroll(PB_UNROLL)
+      for (int it = 0; it < TASKS_B; ++it) {
+        const int task = tid + it * T;
         double2 *row = buf + (task >> 7) * M;
         const int t = task & 127, b = t >> 3;
         double2 x[R2];
@@ -211,7 +247,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
       }
       __syncthreads();
       // ------------------------------- pass C + MAC ----------------------------------------------
-#pragma unroll
+#pragma unroll(PC_UNROLL)
       for (int rb = 0; rb < ROWS_B; ++rb) {
         const int p = rb / LB, lev = lev0 + (rb - p * LB);
         const int r = p * L + lev;                                      // TRGSW row (trgsw.c:394-419 order)
@@ -219,7 +255,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
         const double2 *__restrict__ k1 = key + (size_t)(r * 2 + 1) * M + tid;
         double2 kv0[8], kv1[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { kv0[i] = __ldg(k0 + i * C8); kv1[i] = __ldg(k1 + i * C8); }
+        for (int i = 0; i < 8; ++i) { kv0[i] = ldg_key(k0 + i * C8); kv1[i] = ldg_key(k1 + i * C8); }
         const double2 *row = buf + rb * M;
         double2 x[8];
 #pragma unroll
@@ -241,8 +277,11 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
     }
     __syncthreads();
     // ---------------------------------- B' ---------------------------------------------------------
-#pragma unroll 1
-    for (int task = tid; task < 2 * 128; task += T) {
+    constexpr int TASKS_BI = 2 * 128 / T > 0 ? 2 * 128 / T : 1;
+#pragma unroll
+    for (int it = 0; it < TASKS_BI; ++it) {
+      const int task = tid + it * T;
+      if (T > 256 / TASKS_BI && task >= 256) break;
       double2 *row = buf + (task >> 7) * M;
       const int t = task & 127, b = t >> 3;
       double2 x[R2];
@@ -272,8 +311,8 @@ __global__ void __launch_bounds__((1 << LOGM) / 8) blind_rotate_k1_kernel(K1Args
       for (int m = 0; m < 16; ++m) {
         const double2 z = mul_w64(x[m], m, true);
         const int j = qA + m * S;
-        ap[j] += f64_to_torus(z.x * inv_M);            // trlwe_from_DFT + trlwe_addto
-        ap[j + M] += f64_to_torus(z.y * inv_M);
+        ap[j] += f64_to_torus_fast(z.x * inv_M);       // trlwe_from_DFT + trlwe_addto
+        ap[j + M] += f64_to_torus_fast(z.y * inv_M);
       }
     }
     __syncthreads();
@@ -321,35 +360,50 @@ const double2 *k1_tables_for(int N) {
 }
 
 // ---- dispatch --------------------------------------------------------------------------------------
-static int levels_per_batch(int logm, int l) {
-  if (logm == 11) return 1;
-  if (logm == 10 && l == 4) return 2;
-  return l;
+// Variant = (levels per batch LB, minimum resident CTAs per SM MINB -> register cap).  The default
+// per (N, l) is the fastest measured on B200 (profiles/); MB200_K1_LB / MB200_K1_MINB override it
+// for experiments.
+struct K1Variant { int lb, minb; };
+
+static K1Variant default_variant(int logm, int l) {
+  if (logm == 11) return {1, 1};
+  if (logm == 10 && l == 4) return {2, 1};
+  return {l, 1};
+}
+
+static K1Variant chosen_variant(int logm, int l) {
+  K1Variant v = default_variant(logm, l);
+  if (const char *e = getenv("MB200_K1_LB")) v.lb = atoi(e);
+  if (const char *e = getenv("MB200_K1_MINB")) v.minb = atoi(e);
+  return v;
 }
 
 bool k1_supported(const Params &p) {
   if (p.k != 1) return false;
   const int logm = ilog2i(p.N) - 1;
-  return logm >= 8 && logm <= 11 && p.l >= 1 && p.l <= 4 && (1 << (logm + 1)) == p.N;
+  if (!(logm >= 8 && logm <= 11 && p.l >= 1 && p.l <= 4 && (1 << (logm + 1)) == p.N)) return false;
+  return default_variant(logm, p.l).lb * p.Bg_bit <= 32;
 }
 
 static char g_name[64];
 const char *k1_variant_name(const Params &p) {
   const int logm = ilog2i(p.N) - 1;
-  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d>", p.N, p.l, levels_per_batch(logm, p.l));
+  const K1Variant v = chosen_variant(logm, p.l);
+  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d>", p.N, p.l, v.lb, v.minb);
   return g_name;
 }
 
-template <int LOGM, int L, int LB>
+template <int LOGM, int L, int LB, int MINB>
 static void launch_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
-  constexpr size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16;
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MB_REQUIRE(smem <= 227 * 1024, "k1 kernel: %zu B of shared memory needed (blind rotation too long)", smem);
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
-  blind_rotate_k1_kernel<LOGM, L, LB><<<count, M / 8, smem, st>>>(a);
+  blind_rotate_k1_kernel<LOGM, L, LB, MINB><<<count, M / 8, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }
@@ -362,13 +416,20 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   const int logm = ilog2i(p.N) - 1;
-#define MB_K1_CASE(LM, LL, LBB) if (logm == LM && p.l == LL) { launch_one<LM, LL, LBB>(a, b.count, st); return; }
-  MB_K1_CASE(8, 1, 1) MB_K1_CASE(8, 2, 2) MB_K1_CASE(8, 3, 3) MB_K1_CASE(8, 4, 4)
-  MB_K1_CASE(9, 1, 1) MB_K1_CASE(9, 2, 2) MB_K1_CASE(9, 3, 3) MB_K1_CASE(9, 4, 4)
-  MB_K1_CASE(10, 1, 1) MB_K1_CASE(10, 2, 2) MB_K1_CASE(10, 3, 3) MB_K1_CASE(10, 4, 2)
-  MB_K1_CASE(11, 1, 1) MB_K1_CASE(11, 2, 1) MB_K1_CASE(11, 3, 1) MB_K1_CASE(11, 4, 1)
+  const K1Variant v = chosen_variant(logm, p.l);
+  MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");
+#define MB_K1_CASE(LM, LL, LBB, MB_) \
+  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_) { launch_one<LM, LL, LBB, MB_>(a, b.count, st); return; }
+  MB_K1_CASE(8, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1) MB_K1_CASE(8, 3, 3, 1) MB_K1_CASE(8, 4, 4, 1)
+  MB_K1_CASE(9, 1, 1, 1) MB_K1_CASE(9, 2, 2, 1) MB_K1_CASE(9, 3, 3, 1) MB_K1_CASE(9, 4, 4, 1)
+  MB_K1_CASE(10, 1, 1, 1) MB_K1_CASE(10, 2, 2, 1) MB_K1_CASE(10, 3, 3, 1) MB_K1_CASE(10, 4, 2, 1)
+  MB_K1_CASE(11, 1, 1, 1) MB_K1_CASE(11, 2, 1, 1) MB_K1_CASE(11, 3, 1, 1) MB_K1_CASE(11, 4, 1, 1)
+#ifdef MB200_K1_EXPERIMENTS
+  MB_K1_CASE(9, 3, 3, 3) MB_K1_CASE(9, 3, 1, 1) MB_K1_CASE(9, 3, 1, 4) MB_K1_CASE(9, 3, 1, 5) MB_K1_CASE(9, 3, 1, 6)
+  MB_K1_CASE(10, 4, 2, 2) MB_K1_CASE(10, 4, 1, 1) MB_K1_CASE(10, 4, 1, 2) MB_K1_CASE(10, 4, 1, 3) MB_K1_CASE(10, 4, 4, 1)
+#endif
 #undef MB_K1_CASE
-  MB_FATAL("k1 kernel: no instantiation for N=%d l=%d", p.N, p.l);
+  MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d", p.N, p.l, v.lb, v.minb);
 }
 
 }  // namespace mb

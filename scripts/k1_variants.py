@@ -1,0 +1,35 @@
+"""Times the blind-rotation kernel variants (MB200_K1_LB / MB200_K1_MINB) on the GPU box."""
+import os, sys, itertools
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mosfhet_b200 import api, synthetic as syn
+from mosfhet_b200.params import NAMED
+
+api.init(0)
+B = int(os.environ.get("BATCH", "4096"))
+for wl, variants in (("level1", [(3, 1), (3, 3), (1, 1), (1, 4), (1, 5), (1, 6)]), ("level2", [(2, 1), (2, 2), (1, 1), (1, 2), (1, 3)])):
+    P = NAMED[wl]
+    lwe_key, rlwe_key = syn.binary_key(P.n, 1), syn.binary_key(P.N, 2)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=3)
+    msgs = np.arange(B) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, P.lwe_sigma, seed=4)
+    lut = syn.encode((3 * np.arange(4) + 1) % 4, 4)
+    d_in = torch.from_numpy(cts.view(np.int64)).cuda()
+    d_tv = torch.from_numpy(syn.test_vector(lut, P.N, 1).view(np.int64)).cuda()
+    d_out = torch.empty((B, P.N + 1), dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    for lb, minb in variants:
+        os.environ["MB200_K1_LB"], os.environ["MB200_K1_MINB"] = str(lb), str(minb)
+        ts = []
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            api.pbs_dev(bsk, d_out, d_tv, 1, d_in, 4, B, st.cuda_stream)
+            e1.record(st)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out = d_out.cpu().numpy().view(np.uint64)
+        ok = syn.torus_distance(syn.tlwe_phase(out, rlwe_key), lut[msgs]).max() <= (1 << 58)
+        ms = min(ts[1:])
+        print(f"{wl} {api.last_blind_rotate_kernel():32s} {ms:8.2f} ms  {B/ms*1e3:9.0f} PBS/s  fp64 {P.flops_per_pbs()*B/ms*1e-9:6.2f} TF  ok={ok}", flush=True)
+    bsk.free()
