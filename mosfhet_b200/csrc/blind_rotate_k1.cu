@@ -124,13 +124,14 @@ __device__ __forceinline__ double2 ldg_key(const double2 *p) {
   return v;
 }
 
-template <int LOGM, int L, int LB, int MINB>
+template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
 __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
   constexpr int LOGR2 = clog2(R2);
   constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;
+  constexpr int PKL = PKALL ? L : LB;                 // gadget levels packed into one 32-bit word per coefficient
   constexpr int PB_UNROLL = R2 <= 4 ? 4 : 2;          // independent pass-B butterflies in flight per thread
-  constexpr int PC_UNROLL = 2;                        // rows of pass C whose key loads overlap
+  constexpr int LEV_UNROLL = (L / LB <= 2) ? 2 : 1;   // two batches: unroll (constant shifts, row indices)
   static_assert(L % LB == 0, "levels per batch must divide l");
   static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
 
@@ -185,47 +186,62 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) fa[pp][i] = make_double2(0.0, 0.0);
 
+    unsigned pk0[16], pk1[16];
+    // (X^a - 1)*acc + rounding offset, top PKL*Bg_bit bits (= PKL signed digits) per coefficient
+    auto pack_digits = [&](int lev_end) {
+      const u64 *ap = acc + pA * N;
+      const int pk_shift = 64 - lev_end * Bg_bit;
+      const int base = (qA - a_i) & (2 * N - 1);       // index of coefficient qA in acc * X^a (sign in bit log2 N)
 #pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int j = qA + m * S;
+        const int s0 = (base + m * S) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
+        const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
+        const u64 t0 = off - ap[j], t1 = off - ap[j + M];
+        const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
+        const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
+        pk0[m] = (unsigned)(v0 >> pk_shift);
+        pk1[m] = (unsigned)(v1 >> pk_shift);
+      }
+    };
+    if (PKALL) pack_digits(L);
+
+#pragma unroll(LEV_UNROLL)
     for (int lev0 = 0; lev0 < L; lev0 += LB) {
       // ------------------------------- pass A -------------------------------------------------
-      {
-        const u64 *ap = acc + pA * N;
-        // top LB*Bg_bit bits (this batch's digits) of (X^a - 1)*acc + rounding offset, one word per coefficient
-        const int pk_shift = 64 - (lev0 + LB) * Bg_bit;
-        const int base = (qA - a_i) & (2 * N - 1);     // index of coefficient qA in acc * X^a (sign in bit log2 N)
-        unsigned pk0[16], pk1[16];
+      if (!PKALL) pack_digits(lev0 + LB);
+#pragma unroll 1
+      for (int lb = 0; lb < LB; ++lb) {
+        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (LB - 1 - lb)) * Bg_bit;
+        double2 x[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
-          const int j = qA + m * S;
-          const int s0 = (base + m * S) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
-          const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
-          const u64 t0 = off - ap[j], t1 = off - ap[j + M];
-          const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
-          const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
-          pk0[m] = (unsigned)(v0 >> pk_shift);
-          pk1[m] = (unsigned)(v1 >> pk_shift);
+          const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
+          const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
+          // fold z = d0 + i*d1 and the constant part of the twist, w^(m*M/16) = W_64^m
+          x[m] = mul_w64(make_double2(d0, d1), m, false);
         }
-#pragma unroll 1
-        for (int lb = 0; lb < LB; ++lb) {
-          const int sh = (LB - 1 - lb) * Bg_bit;
-          double2 x[16];
+        reg_dif<16>(x);
+        double2 *row = buf + (pA * LB + lb) * M;
 #pragma unroll
-          for (int m = 0; m < 16; ++m) {
-            const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
-            const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
-            // fold z = d0 + i*d1 and the constant part of the twist, w^(m*M/16) = W_64^m
-            x[m] = mul_w64(make_double2(d0, d1), m, false);
-          }
-          reg_dif<16>(x);
-          double2 *row = buf + (pA * LB + lb) * M;
-#pragma unroll
-          for (int pos = 0; pos < 16; ++pos) {
-            const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);       // w^q * W_M^(q*k1)
-            row[swz(pos * S + qA)] = cmul(x[pos], t);
-          }
+        for (int pos = 0; pos < 16; ++pos) {
+          const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);         // w^q * W_M^(q*k1)
+          row[swz(pos * S + qA)] = cmul(x[pos], t);
         }
       }
       __syncthreads();
+      // key rows of this batch: row index of buffer rb
+      auto key_row = [&](int rb) {
+        const int p = rb / LB, lev = lev0 + (rb - p * LB);
+        return key + (size_t)((p * L + lev) * 2) * M + tid;            // TRGSW row order of trgsw.c:394-419
+      };
+      double2 kv[PF ? 2 : 1][16];
+      auto load_keys = [&](double2 (&dst)[16], int rb) {
+        const double2 *__restrict__ k0 = key_row(rb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
+      };
+      if (PF) load_keys(kv[0], 0);                                      // in flight across pass B
       // ------------------------------- pass B -------------------------------------------------
       constexpr int TASKS_B = ROWS_B * 128 / T;
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
@@ -247,22 +263,30 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
       }
       __syncthreads();
       // ------------------------------- pass C + MAC ----------------------------------------------
-#pragma unroll(PC_UNROLL)
-      for (int rb = 0; rb < ROWS_B; ++rb) {
-        const int p = rb / LB, lev = lev0 + (rb - p * LB);
-        const int r = p * L + lev;                                      // TRGSW row (trgsw.c:394-419 order)
-        const double2 *__restrict__ k0 = key + (size_t)(r * 2 + 0) * M + tid;
-        const double2 *__restrict__ k1 = key + (size_t)(r * 2 + 1) * M + tid;
-        double2 kv0[8], kv1[8];
+      if (PF) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { kv0[i] = ldg_key(k0 + i * C8); kv1[i] = ldg_key(k1 + i * C8); }
-        const double2 *row = buf + rb * M;
-        double2 x[8];
+        for (int rb = 0; rb < ROWS_B; ++rb) {
+          if (rb + 1 < ROWS_B) load_keys(kv[(rb + 1) & 1], rb + 1);     // next row's keys while this row computes
+          const double2 *row = buf + rb * M;
+          double2 x[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
-        reg_dif<8>(x);
+          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
+          reg_dif<8>(x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv0[i]); cfma(fa[1][i], x[i], kv1[i]); }
+          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[rb & 1][i]); cfma(fa[1][i], x[i], kv[rb & 1][8 + i]); }
+        }
+      } else {
+#pragma unroll 2
+        for (int rb = 0; rb < ROWS_B; ++rb) {
+          load_keys(kv[0], rb);
+          const double2 *row = buf + rb * M;
+          double2 x[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
+          reg_dif<8>(x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[0][i]); cfma(fa[1][i], x[i], kv[0][8 + i]); }
+        }
       }
       __syncthreads();
     }
@@ -281,7 +305,6 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
 #pragma unroll
     for (int it = 0; it < TASKS_BI; ++it) {
       const int task = tid + it * T;
-      if (T > 256 / TASKS_BI && task >= 256) break;
       double2 *row = buf + (task >> 7) * M;
       const int t = task & 127, b = t >> 3;
       double2 x[R2];
@@ -360,21 +383,23 @@ const double2 *k1_tables_for(int N) {
 }
 
 // ---- dispatch --------------------------------------------------------------------------------------
-// Variant = (levels per batch LB, minimum resident CTAs per SM MINB -> register cap).  The default
-// per (N, l) is the fastest measured on B200 (profiles/); MB200_K1_LB / MB200_K1_MINB override it
-// for experiments.
-struct K1Variant { int lb, minb; };
+// Variant = (levels per smem batch LB, min resident CTAs per SM MINB -> register cap, PKALL = all
+// levels' digits packed once per step, PF = pass-C key prefetch mode).  The default per (N, l) is the
+// fastest measured on B200 (profiles/); MB200_K1_LB / _MINB / _PF override it for experiments.
+struct K1Variant { int lb, minb, pf; };
 
 static K1Variant default_variant(int logm, int l) {
-  if (logm == 11) return {1, 1};
-  if (logm == 10 && l == 4) return {2, 1};
-  return {l, 1};
+  if (logm == 11) return {1, 1, 0};
+  if (logm == 10 && l == 4) return {2, 1, 0};
+  // double-buffered key rows in pass C pay off while they fit the register file (profiles/r1b_k1_variants.log)
+  return {l, 1, (logm <= 9 && l <= 3) ? 1 : 0};
 }
 
 static K1Variant chosen_variant(int logm, int l) {
   K1Variant v = default_variant(logm, l);
   if (const char *e = getenv("MB200_K1_LB")) v.lb = atoi(e);
   if (const char *e = getenv("MB200_K1_MINB")) v.minb = atoi(e);
+  if (const char *e = getenv("MB200_K1_PF")) v.pf = atoi(e);
   return v;
 }
 
@@ -385,27 +410,36 @@ bool k1_supported(const Params &p) {
   return default_variant(logm, p.l).lb * p.Bg_bit <= 32;
 }
 
-static char g_name[64];
+static char g_name[80];
 const char *k1_variant_name(const Params &p) {
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l);
-  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d>", p.N, p.l, v.lb, v.minb);
+  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d>", p.N, p.l, v.lb, v.minb,
+           (int)(p.l * p.Bg_bit <= 32), v.pf);
   return g_name;
 }
 
-template <int LOGM, int L, int LB, int MINB>
+template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
 static void launch_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
   static size_t configured = 0;
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1 kernel: %zu B of shared memory needed (blind rotation too long)", smem);
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  blind_rotate_k1_kernel<LOGM, L, LB, MINB><<<count, M / 8, smem, st>>>(a);
+  blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF><<<count, M / 8, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
+}
+
+template <int LOGM, int L, int LB, int MINB, int PF>
+static void launch_pk(const K1Args &a, int count, cudaStream_t st) {
+  // all l levels fit one 32-bit word per coefficient -> pack once per step; otherwise once per batch
+  if (L * a.Bg_bit <= 32) launch_one<LOGM, L, LB, MINB, true, PF>(a, count, st);
+  else launch_one<LOGM, L, LB, MINB, LB == L, PF>(a, count, st);
 }
 
 void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
@@ -418,18 +452,18 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");
-#define MB_K1_CASE(LM, LL, LBB, MB_) \
-  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_) { launch_one<LM, LL, LBB, MB_>(a, b.count, st); return; }
-  MB_K1_CASE(8, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1) MB_K1_CASE(8, 3, 3, 1) MB_K1_CASE(8, 4, 4, 1)
-  MB_K1_CASE(9, 1, 1, 1) MB_K1_CASE(9, 2, 2, 1) MB_K1_CASE(9, 3, 3, 1) MB_K1_CASE(9, 4, 4, 1)
-  MB_K1_CASE(10, 1, 1, 1) MB_K1_CASE(10, 2, 2, 1) MB_K1_CASE(10, 3, 3, 1) MB_K1_CASE(10, 4, 2, 1)
-  MB_K1_CASE(11, 1, 1, 1) MB_K1_CASE(11, 2, 1, 1) MB_K1_CASE(11, 3, 1, 1) MB_K1_CASE(11, 4, 1, 1)
+#define MB_K1_CASE(LM, LL, LBB, MB_, PF_) \
+  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_>(a, b.count, st); return; }
+  MB_K1_CASE(8, 1, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1, 1) MB_K1_CASE(8, 3, 3, 1, 1) MB_K1_CASE(8, 4, 4, 1, 0)
+  MB_K1_CASE(9, 1, 1, 1, 1) MB_K1_CASE(9, 2, 2, 1, 1) MB_K1_CASE(9, 3, 3, 1, 1) MB_K1_CASE(9, 4, 4, 1, 0)
+  MB_K1_CASE(10, 1, 1, 1, 0) MB_K1_CASE(10, 2, 2, 1, 0) MB_K1_CASE(10, 3, 3, 1, 0) MB_K1_CASE(10, 4, 2, 1, 0)
+  MB_K1_CASE(11, 1, 1, 1, 0) MB_K1_CASE(11, 2, 1, 1, 0) MB_K1_CASE(11, 3, 1, 1, 0) MB_K1_CASE(11, 4, 1, 1, 0)
 #ifdef MB200_K1_EXPERIMENTS
-  MB_K1_CASE(9, 3, 3, 3) MB_K1_CASE(9, 3, 1, 1) MB_K1_CASE(9, 3, 1, 4) MB_K1_CASE(9, 3, 1, 5) MB_K1_CASE(9, 3, 1, 6)
-  MB_K1_CASE(10, 4, 2, 2) MB_K1_CASE(10, 4, 1, 1) MB_K1_CASE(10, 4, 1, 2) MB_K1_CASE(10, 4, 1, 3) MB_K1_CASE(10, 4, 4, 1)
+  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 1, 4, 0) MB_K1_CASE(9, 3, 1, 5, 0) MB_K1_CASE(9, 3, 1, 4, 1) MB_K1_CASE(9, 3, 1, 5, 1)
+  MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 4, 1, 2, 0) MB_K1_CASE(10, 4, 1, 3, 0) MB_K1_CASE(10, 4, 1, 2, 1)
 #endif
 #undef MB_K1_CASE
-  MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d", p.N, p.l, v.lb, v.minb);
+  MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
 }
 
 }  // namespace mb

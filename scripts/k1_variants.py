@@ -7,7 +7,8 @@ from mosfhet_b200.params import NAMED
 
 api.init(0)
 B = int(os.environ.get("BATCH", "4096"))
-for wl, variants in (("level1", [(3, 1), (3, 3), (1, 1), (1, 4), (1, 5), (1, 6)]), ("level2", [(2, 1), (2, 2), (1, 1), (1, 2), (1, 3)])):
+for wl, variants in (("level1", [(3, 1, 0), (3, 1, 1), (1, 4, 0), (1, 4, 1), (1, 5, 0), (1, 5, 1)]),
+                     ("level2", [(2, 1, 0), (2, 1, 1), (1, 2, 0), (1, 2, 1), (1, 3, 0)])):
     P = NAMED[wl]
     lwe_key, rlwe_key = syn.binary_key(P.n, 1), syn.binary_key(P.N, 2)
     bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=3)
@@ -18,8 +19,8 @@ for wl, variants in (("level1", [(3, 1), (3, 3), (1, 1), (1, 4), (1, 5), (1, 6)]
     d_tv = torch.from_numpy(syn.test_vector(lut, P.N, 1).view(np.int64)).cuda()
     d_out = torch.empty((B, P.N + 1), dtype=torch.int64, device="cuda")
     st = torch.cuda.Stream()
-    for lb, minb in variants:
-        os.environ["MB200_K1_LB"], os.environ["MB200_K1_MINB"] = str(lb), str(minb)
+    for lb, minb, pf in variants:
+        os.environ["MB200_K1_LB"], os.environ["MB200_K1_MINB"], os.environ["MB200_K1_PF"] = str(lb), str(minb), str(pf)
         ts = []
         for it in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,5 +32,5 @@ for wl, variants in (("level1", [(3, 1), (3, 3), (1, 1), (1, 4), (1, 5), (1, 6)]
         out = d_out.cpu().numpy().view(np.uint64)
         ok = syn.torus_distance(syn.tlwe_phase(out, rlwe_key), lut[msgs]).max() <= (1 << 58)
         ms = min(ts[1:])
-        print(f"{wl} {api.last_blind_rotate_kernel():32s} {ms:8.2f} ms  {B/ms*1e3:9.0f} PBS/s  fp64 {P.flops_per_pbs()*B/ms*1e-9:6.2f} TF  ok={ok}", flush=True)
+        print(f"{wl} {api.last_blind_rotate_kernel():46s} {ms:8.2f} ms  {B/ms*1e3:9.0f} PBS/s  fp64 {P.flops_per_pbs()*B/ms*1e-9:6.2f} TF  ok={ok}", flush=True)
     bsk.free()
