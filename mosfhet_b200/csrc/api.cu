@@ -145,6 +145,9 @@ DftMaps dft_maps_for(int N) {
   MB_CHECK(cudaMemcpy(d + M, scj.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
   MB_CHECK(cudaMemcpy(d + 2 * M, p2h.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
   MB_CHECK(cudaMemcpy(d + 3 * M, pcj.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  // pageable H2D copies may return before the DMA lands, and the kernels run on non-blocking
+  // streams that do not order against the legacy stream: fence explicitly
+  MB_CHECK(cudaDeviceSynchronize());
   DftMaps m{d, d + M, d + 2 * M, d + 3 * M};
   g_dft_maps[key] = m;
   return m;
@@ -177,10 +180,13 @@ mb200_bsk *bsk_from_host_array(const mb::Params &p, const double *h_bsk, int lay
   const size_t doubles = bsk_elems(p) * 2;
   double *d_tmp = nullptr;
   MB_CHECK(cudaMalloc(&d_tmp, sizeof(double) * doubles));
-  MB_CHECK(cudaMemcpy(d_tmp, h_bsk, sizeof(double) * doubles, cudaMemcpyHostToDevice));
+  cudaStream_t st = mb::default_stream();
+  // same stream as the import kernel: a plain cudaMemcpy from pageable memory may return before
+  // the DMA has landed and would not order against this (non-blocking) stream
+  MB_CHECK(cudaMemcpyAsync(d_tmp, h_bsk, sizeof(double) * doubles, cudaMemcpyHostToDevice, st));
   std::vector<int32_t> e;
   host_exponents(p.N, e, layout);
-  mb::import_bsk(b, d_tmp, e.data(), mb::default_stream());
+  mb::import_bsk(b, d_tmp, e.data(), st);
   MB_CHECK(cudaFree(d_tmp));
   return b;
 }
@@ -225,9 +231,11 @@ mb200_ksk *ksk_from_host_array(const mb::Params &p, const u64 *h_ksk) {
   mb200_ksk *k = ksk_alloc(p);
   const size_t rows = ksk_rows(p);
   const int w = p.n + 1;
-  MB_CHECK(cudaMemset(k->d, 0, sizeof(u64) * rows * k->row_stride));
-  MB_CHECK(cudaMemcpy2D(k->d, sizeof(u64) * k->row_stride, h_ksk, sizeof(u64) * w, sizeof(u64) * w, rows,
-                        cudaMemcpyHostToDevice));
+  cudaStream_t st = mb::default_stream();
+  MB_CHECK(cudaMemsetAsync(k->d, 0, sizeof(u64) * rows * k->row_stride, st));
+  MB_CHECK(cudaMemcpy2DAsync(k->d, sizeof(u64) * k->row_stride, h_ksk, sizeof(u64) * w, sizeof(u64) * w, rows,
+                             cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaStreamSynchronize(st));     // h_ksk may be freed by the caller; later kernels may use other streams
   return k;
 }
 

@@ -378,6 +378,7 @@ const double2 *k1_tables_for(int N) {
   double2 *d = nullptr;
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * h.size()));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+  MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
   g_k1_tab[N] = d;
   return d;
 }

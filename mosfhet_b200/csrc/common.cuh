@@ -43,7 +43,7 @@ struct BskDev {
   bool owned;
 };
 
-// Resident key-switching table: u64 [N_in][t][2^base_bit-1][row_stride], row_stride = round_up(n+1, 4)
+// Resident key-switching table: u64 [N_in][t][2^base_bit-1][row_stride], row_stride = round_up(n+1, 64)
 struct KskDev {
   Params p;
   u64 *d;
@@ -52,7 +52,7 @@ struct KskDev {
 };
 
 inline int ilog2i(int x) { int r = 0; while ((1 << r) < x) ++r; return r; }
-inline int ksk_row_stride(int n_out) { return (n_out + 1 + 3) & ~3; }
+inline int ksk_row_stride(int n_out) { return (n_out + 1 + 63) & ~63; }  // 512-byte rows: 128-bit lane loads, no tail guards
 
 // ---- twiddle tables (tables.cu) -------------------------------------------------------------
 // tw[j] = exp(i*pi*j/N), j in [0, N): covers the twist (j < N/2) and every FFT twiddle of the

@@ -79,6 +79,7 @@ const double2 *twiddles_for(int N) {
   double2 *d = nullptr;
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * N));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
+  MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
   g_tw[N] = d;
   return d;
 }

@@ -3,117 +3,122 @@
 //     d_ij = digit j (base 2^base_bit, most significant first) of in.a[i] + 2^(63 - t*base_bit)
 // Pure u64 wrap-around arithmetic: bit-exact with the reference whatever the summation order.
 //
-// Mapping: a CTA owns KS_G ciphertexts; thread c owns output columns c, c+T, ... of all of them in
-// registers.  The table is swept in (i, j) order; for each (i, j) the CTA walks the digit values
-// d = 1 .. 2^base_bit-1 that at least one of its ciphertexts selected, loads that row ONCE
-// (coalesced, lanes on consecutive words) and subtracts it from every ciphertext that selected it.
-// Across the grid all CTAs sweep the table in the same order, so the rows stream from HBM once
-// per wave and are otherwise served by L2.
+// Mapping: ONE WARP PER CIPHERTEXT, up to 28 ciphertexts per CTA, one CTA per SM.  A lane keeps the
+// output words 2*(lane+32q), 2*(lane+32q)+1 (q < NV) of its ciphertext in registers for the whole
+// sweep, so the 5 KB accumulator never touches memory.  For every (i, j) the warp computes its
+// digit (warp-uniform, no divergence), and if it is non-zero reads that table row with NV coalesced
+// 128-bit loads per lane (rows are padded to a multiple of 64 words = 512 B) and subtracts it.
+// All warps of a CTA walk (i, j) in the same order and are re-aligned by a block barrier every few
+// input coefficients, so the (at most 2^base_bit - 1) rows of the current (i, j) are fetched from L2
+// once per CTA and then served to the other warps by L1; across the grid every CTA sweeps the table
+// in the same order, so HBM sees each row about once per wave.
+//
+// Algorithmic work per ciphertext: N_in * t * (1 - 2^-base_bit) row subtractions of (n+1) words.
 #include "common.cuh"
 #include "device_math.cuh"
 
 namespace mb {
 
-constexpr int KS_THREADS = 256;
-constexpr int KS_MAXCOLS = 4;      // columns per thread: supports n+1 <= 1024
-constexpr int KS_CHUNK = 64;       // input coefficients staged per round
+constexpr int KS_MAX_WARPS = 28;     // 28 warps x 72 registers x 32 lanes = the whole register file
+constexpr int KS_SYNC_EVERY = 4;     // input coefficients between block barriers (L1 window: 4*t*(2^b-1) rows)
 
-template <int G>
-__global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(u64 *__restrict__ out, const u64 *__restrict__ in,
-                                                               const u64 *__restrict__ ksk, int count, int n_in,
-                                                               int n_out, int t, int base_bit, int row_stride) {
-  // digit table for the current chunk: dig[g][e], e = (i_local * t + j)
-  extern __shared__ unsigned char ks_smem[];
-  unsigned char *dig = ks_smem;                                   // [G][KS_CHUNK * t]
-  unsigned int *used = reinterpret_cast<unsigned int *>(ks_smem + ((G * KS_CHUNK * t + 15) & ~15));  // [KS_CHUNK * t] bitmask of digits in use
-  const int ct0 = blockIdx.x * G;
-  const int width = n_out + 1;
+__device__ __forceinline__ ulonglong2 ldg_u128(const u64 *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(KS_MAX_WARPS * 32, 1)
+keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u64 *__restrict__ ksk, int count,
+                      int n_in, int n_out, int t, int base_bit, int row_stride, int cts_per_cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ct = blockIdx.x * cts_per_cta + warp;
+  const bool live = warp < cts_per_cta && ct < count;
   const int bm1 = (1 << base_bit) - 1;
   const u64 prec_offset = 1ull << (64 - (1 + base_bit * t));
+  const u64 *a = in + (size_t)(live ? ct : 0) * (n_in + 1);
 
-  u64 acc[G][KS_MAXCOLS];
+  u64 acc[2 * NV];
 #pragma unroll
-  for (int g = 0; g < G; ++g)
-#pragma unroll
-    for (int q = 0; q < KS_MAXCOLS; ++q) {
-      const int c = threadIdx.x + q * KS_THREADS;
-      acc[g][q] = (c == n_out && ct0 + g < count) ? in[(size_t)(ct0 + g) * (n_in + 1) + n_in] : 0ull;
-    }
+  for (int q = 0; q < 2 * NV; ++q) acc[q] = 0ull;
 
-  for (int i0 = 0; i0 < n_in; i0 += KS_CHUNK) {
-    const int ni = min(KS_CHUNK, n_in - i0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < ni * t; e += KS_THREADS) used[e] = 0u;
-    __syncthreads();
-    for (int w = threadIdx.x; w < G * ni; w += KS_THREADS) {
-      const int g = w / ni, il = w - g * ni;
-      const bool live = ct0 + g < count;
-      const u64 ai = live ? in[(size_t)(ct0 + g) * (n_in + 1) + i0 + il] + prec_offset : 0ull;
+  for (int i0 = 0; i0 < n_in; i0 += 32) {
+    const int i_mine = i0 + lane;
+    const u64 a_mine = (live && i_mine < n_in) ? a[i_mine] + prec_offset : 0ull;   // tlwe.c:297
+    const int ni = min(32, n_in - i0);
+    for (int il = 0; il < ni; ++il) {
+      const u64 ai = __shfl_sync(0xffffffffu, a_mine, il);
+      const u64 *base_row = ksk + (size_t)(i0 + il) * t * bm1 * row_stride + 2 * lane;
       for (int j = 0; j < t; ++j) {
-        const unsigned d = live ? (unsigned)((ai >> (64 - (j + 1) * base_bit)) & (u64)bm1) : 0u;
-        dig[g * KS_CHUNK * t + il * t + j] = (unsigned char)d;
-        if (d) atomicOr(&used[il * t + j], 1u << d);
-      }
-    }
-    __syncthreads();
-    for (int e = 0; e < ni * t; ++e) {
-      unsigned m = used[e];
-      const size_t base_row = ((size_t)(i0 * t + e)) * bm1;
-      while (m) {
-        const int d = __ffs(m) - 1;
-        m &= m - 1;
-        const u64 *row = ksk + (base_row + d - 1) * row_stride;
-        u64 v[KS_MAXCOLS];
+        const unsigned d = (unsigned)(ai >> (64 - (j + 1) * base_bit)) & (unsigned)bm1;
+        if (d != 0 && live) {                       // warp-uniform
+          const u64 *row = base_row + (size_t)(j * bm1 + (int)d - 1) * row_stride;
 #pragma unroll
-        for (int q = 0; q < KS_MAXCOLS; ++q) {
-          const int c = threadIdx.x + q * KS_THREADS;
-          v[q] = (c < width) ? __ldg(row + c) : 0ull;
-        }
+          for (int q0 = 0; q0 < NV; q0 += 5) {      // 5 x 128-bit loads in flight keeps the kernel under 72 registers
+            ulonglong2 v[5];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (dig[g * KS_CHUNK * t + e] == d) {
+            for (int q = 0; q < 5; ++q)
+              if (q0 + q < NV) v[q] = ldg_u128(row + 64 * (q0 + q));
 #pragma unroll
-            for (int q = 0; q < KS_MAXCOLS; ++q) acc[g][q] -= v[q];
+            for (int q = 0; q < 5; ++q)
+              if (q0 + q < NV) { acc[2 * (q0 + q)] -= v[q].x; acc[2 * (q0 + q) + 1] -= v[q].y; }
           }
         }
       }
+      if (((i0 + il + 1) % KS_SYNC_EVERY) == 0) __syncthreads();
     }
   }
+  if (live) {
+    u64 *o = out + (size_t)ct * (n_out + 1);
+    const u64 b = a[n_in];
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    if (ct0 + g >= count) continue;
-#pragma unroll
-    for (int q = 0; q < KS_MAXCOLS; ++q) {
-      const int c = threadIdx.x + q * KS_THREADS;
-      if (c < width) out[(size_t)(ct0 + g) * width + c] = acc[g][q];
+    for (int q = 0; q < NV; ++q) {
+      const int c = 2 * (lane + 32 * q);
+      if (c < n_out) o[c] = acc[2 * q];
+      else if (c == n_out) o[c] = acc[2 * q] + b;
+      if (c + 1 < n_out) o[c + 1] = acc[2 * q + 1];
+      else if (c + 1 == n_out) o[c + 1] = acc[2 * q + 1] + b;
     }
   }
 }
 
-template <int G>
-static void launch_ks_g(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
+template <int NV>
+static void launch_ks_nv(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
   const Params &p = ksk->p;
-  const size_t smem = ((size_t)G * KS_CHUNK * p.t + 15 & ~(size_t)15) + sizeof(unsigned) * KS_CHUNK * p.t;
-  const int grid = (count + G - 1) / G;
-  keyswitch_kernel<G><<<grid, KS_THREADS, smem, st>>>(out, in, ksk->d, count, p.k * p.N, p.n, p.t, p.base_bit,
-                                                     ksk->row_stride);
+  const int sms = sm_count();
+  // one CTA per SM when the batch allows; as few waves as possible otherwise
+  int waves = (count + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
+  int per = (count + sms * waves - 1) / (sms * waves);
+  if (per < 1) per = 1;
+  if (per > KS_MAX_WARPS) per = KS_MAX_WARPS;
+  const int grid = (count + per - 1) / per;
+  static bool configured = false;
+  if (!configured) {
+    // no shared memory needed: give the whole unified array to L1, which is what shares rows between warps
+    MB_CHECK(cudaFuncSetAttribute(keyswitch_warp_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    configured = true;
+  }
+  keyswitch_warp_kernel<NV><<<grid, per * 32, 0, st>>>(out, in, ksk->d, count, p.k * p.N, p.n, p.t, p.base_bit,
+                                                     ksk->row_stride, per);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }
 
 void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
   const Params &p = ksk->p;
-  MB_REQUIRE(p.n + 1 <= KS_THREADS * KS_MAXCOLS, "keyswitch: output dimension n=%d too large (max %d)", p.n,
-             KS_THREADS * KS_MAXCOLS - 1);
-  MB_REQUIRE(p.base_bit >= 1 && p.base_bit <= 5, "keyswitch: base_bit=%d unsupported (1..5)", p.base_bit);
-  MB_REQUIRE(p.t * p.base_bit < 64, "keyswitch: t*base_bit must be < 64");
+  MB_REQUIRE(p.n + 1 <= 1024, "keyswitch: output dimension n=%d too large (max 1023)", p.n);
+  MB_REQUIRE(p.base_bit >= 1 && p.base_bit <= 8, "keyswitch: base_bit=%d unsupported (1..8)", p.base_bit);
+  MB_REQUIRE(p.t >= 1 && p.t * p.base_bit < 64, "keyswitch: t*base_bit must be < 64");
+  MB_REQUIRE(ksk->row_stride % 64 == 0, "keyswitch: resident rows must be padded to 64 words");
   if (count <= 0) return;
-  // enough CTAs to fill the machine first, then amortise row loads over more ciphertexts per CTA
-  const int sms = sm_count();
-  if (count >= sms * 8 * 2) launch_ks_g<8>(ksk, out, in, count, st);
-  else if (count >= sms * 4) launch_ks_g<4>(ksk, out, in, count, st);
-  else if (count >= sms * 2) launch_ks_g<2>(ksk, out, in, count, st);
-  else launch_ks_g<1>(ksk, out, in, count, st);
+  switch (ksk->row_stride / 64) {
+#define MB_KS_CASE(NV_) case NV_: launch_ks_nv<NV_>(ksk, out, in, count, st); break;
+    MB_KS_CASE(1) MB_KS_CASE(2) MB_KS_CASE(3) MB_KS_CASE(4) MB_KS_CASE(5) MB_KS_CASE(6) MB_KS_CASE(7) MB_KS_CASE(8)
+    MB_KS_CASE(9) MB_KS_CASE(10) MB_KS_CASE(11) MB_KS_CASE(12) MB_KS_CASE(13) MB_KS_CASE(14) MB_KS_CASE(15) MB_KS_CASE(16)
+#undef MB_KS_CASE
+    default: MB_FATAL("keyswitch: row stride %d unsupported", ksk->row_stride);
+  }
 }
 
 }  // namespace mb
