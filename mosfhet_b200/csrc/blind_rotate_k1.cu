@@ -25,6 +25,7 @@
 // trlwe.c:437, and the prologue/epilogue bootstrap.c:192-206 + trlwe.c:540-552.
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -32,6 +33,18 @@
 #include "w64_constants.cuh"
 
 namespace mb {
+
+// W_64 powers in constant memory: FP64 instructions take c[bank][offset] operands directly, whereas
+// folded 64-bit immediates cost two UMOV each time they are rematerialised (ncu: 184 UMOV per step).
+__constant__ double CW64C[64], CW64S[64];
+static void upload_w64() {
+  static bool done = false;
+  if (done) return;
+  MB_CHECK(cudaMemcpyToSymbol(CW64C, W64C_HOST, sizeof(double) * 64));
+  MB_CHECK(cudaMemcpyToSymbol(CW64S, W64S_HOST, sizeof(double) * 64));
+  MB_CHECK(cudaDeviceSynchronize());
+  done = true;
+}
 
 // x * W_64^idx (or its conjugate).  idx is a compile-time constant after unrolling, so the trivial
 // cases cost nothing and the 8th roots cost 2 mul + 2 add.
@@ -47,7 +60,7 @@ __device__ __forceinline__ double2 mul_w64(double2 x, int idx, bool conj) {
   if (idx == 24) return make_double2((-x.x - x.y) * h, (x.x - x.y) * h);
   if (idx == 40) return make_double2((x.y - x.x) * h, (-x.x - x.y) * h);
   if (idx == 56) return make_double2((x.x + x.y) * h, (x.y - x.x) * h);
-  const double c = W64C[idx], s = W64S[idx];
+  const double c = CW64C[idx], s = CW64S[idx];
   return make_double2(fma(x.x, c, -x.y * s), fma(x.x, s, x.y * c));
 }
 
@@ -128,11 +141,10 @@ template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
 __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
   constexpr int LOGR2 = clog2(R2);
-  constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;
+  constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;    // ROWS_B: shared-memory row buffers (largest batch)
   constexpr int PKL = PKALL ? L : LB;                 // gadget levels packed into one 32-bit word per coefficient
   constexpr int PB_UNROLL = R2 <= 4 ? 4 : 2;          // independent pass-B butterflies in flight per thread
-  constexpr int LEV_UNROLL = (L / LB <= 2) ? 2 : 1;   // two batches: unroll (constant shifts, row indices)
-  static_assert(L % LB == 0, "levels per batch must divide l");
+  static_assert(LB >= 1 && LB <= L, "levels per batch");
   static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -174,6 +186,18 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
   const double inv_M = 1.0 / (double)M;
   const int pA = tid / S, qA = tid - pA * S;          // pass A / A' ownership
   const int qpB = tid & 7;                            // pass B twiddle column (T is a multiple of 8)
+  // Swizzled addresses spelled out so that they are (thread constant) + (compile-time constant):
+  //   swz(s) = s ^ ((s >> 3) & 7) only permutes the low 3 bits, by a mask that depends on s >> 3.
+  // pass A / A': element pos*S + qA -> mask ((pos*(S/8)) + (qA>>3)) & 7: NVA distinct masks
+  constexpr int S8 = S / 8, NVA = (S8 >= 8) ? 1 : 8 / S8;
+  int qsw[NVA];
+#pragma unroll
+  for (int v = 0; v < NVA; ++v) qsw[v] = qA ^ ((v * S8 + (qA >> 3)) & 7);
+  // pass B / B': element b*S + 8m + qp with b = (tid>>3) + it*(T/8): mask ((tid>>3)*S8 + m) & 7 (it drops out)
+  int qx[R2];
+#pragma unroll
+  for (int m = 0; m < R2; ++m) qx[m] = qpB ^ ((((tid >> 3) * S8) + m) & 7);
+  const int bB0 = (tid >> 3) * S;                     // first element of this thread's pass-B block
 
   for (int step = 0; step < A.size; ++step) {
     const int a_i = rot[step];
@@ -206,13 +230,14 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
     };
     if (PKALL) pack_digits(L);
 
-#pragma unroll(LEV_UNROLL)
-    for (int lev0 = 0; lev0 < L; lev0 += LB) {
+    // One batch = NB gadget levels of both input polynomials (2*NB rows of shared-memory buffers).
+    auto batch = [&](auto nb_tag, const int lev0) {
+      constexpr int NB = decltype(nb_tag)::value, ROWS_B = 2 * NB;
       // ------------------------------- pass A -------------------------------------------------
-      if (!PKALL) pack_digits(lev0 + LB);
+      if (!PKALL) pack_digits(lev0 + NB);
 #pragma unroll 1
-      for (int lb = 0; lb < LB; ++lb) {
-        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (LB - 1 - lb)) * Bg_bit;
+      for (int lb = 0; lb < NB; ++lb) {
+        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (NB - 1 - lb)) * Bg_bit;
         double2 x[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -222,7 +247,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
           x[m] = mul_w64(make_double2(d0, d1), m, false);
         }
         reg_dif<16>(x);
-        double2 *row = buf + (pA * LB + lb) * M;
+        double2 *row = buf + (pA * NB + lb) * M;
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) {
           const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);         // w^q * W_M^(q*k1)
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
       __syncthreads();
       // key rows of this batch: row index of buffer rb
       auto key_row = [&](int rb) {
-        const int p = rb / LB, lev = lev0 + (rb - p * LB);
+        const int p = rb / NB, lev = lev0 + (rb - p * NB);
         return key + (size_t)((p * L + lev) * 2) * M + tid;            // TRGSW row order of trgsw.c:394-419
       };
       double2 kv[PF ? 2 : 1][16];
@@ -247,18 +272,17 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
 #pragma unroll(PB_UNROLL)
       for (int it = 0; it < TASKS_B; ++it) {
-        const int task = tid + it * T;
-        double2 *row = buf + (task >> 7) * M;
-        const int t = task & 127, b = t >> 3;
+        // task = tid + it*T: row = task >> 7, block b = (task & 127) >> 3 = (tid >> 3) + it*(T/8) (mod 16)
+        double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
         double2 x[R2];
 #pragma unroll
-        for (int m = 0; m < R2; ++m) x[m] = row[swz(b * S + qpB + 8 * m)];
+        for (int m = 0; m < R2; ++m) x[m] = blk[8 * m + qx[m]];
         reg_dif<R2>(x);
 #pragma unroll
         for (int pos = 0; pos < R2; ++pos) {
           const int k = brev(pos, LOGR2);
           const double2 y = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
-          row[swz(b * S + pos * 8 + qpB)] = y;
+          blk[8 * pos + qx[pos]] = y;
         }
       }
       __syncthreads();
@@ -289,7 +313,11 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
         }
       }
       __syncthreads();
-    }
+    };
+    // full batches of LB levels, then the ragged remainder (compile-time structure: constant shifts and rows)
+#pragma unroll
+    for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
+    if constexpr (L % LB != 0) batch(std::integral_constant<int, L % LB>{}, L - L % LB);
 
     // ---------------------------------- inverse: C' ------------------------------------------------
 #pragma unroll
@@ -304,19 +332,17 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
     constexpr int TASKS_BI = 2 * 128 / T > 0 ? 2 * 128 / T : 1;
 #pragma unroll
     for (int it = 0; it < TASKS_BI; ++it) {
-      const int task = tid + it * T;
-      double2 *row = buf + (task >> 7) * M;
-      const int t = task & 127, b = t >> 3;
+      double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
       double2 x[R2];
 #pragma unroll
       for (int pos = 0; pos < R2; ++pos) {
         const int k = brev(pos, LOGR2);
-        const double2 y = row[swz(b * S + pos * 8 + qpB)];
+        const double2 y = blk[8 * pos + qx[pos]];
         x[pos] = k == 0 ? y : cmul_conj(y, __ldg(&TB[k * 8 + qpB]));
       }
       reg_dit_inv<R2>(x);
 #pragma unroll
-      for (int m = 0; m < R2; ++m) row[swz(b * S + qpB + 8 * m)] = x[m];
+      for (int m = 0; m < R2; ++m) blk[8 * m + qx[m]] = x[m];
     }
     __syncthreads();
     // ---------------------------------- A' + accumulate --------------------------------------------
@@ -326,7 +352,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
 #pragma unroll
       for (int pos = 0; pos < 16; ++pos) {
         const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);
-        x[pos] = cmul_conj(row[swz(pos * S + qA)], t);
+        x[pos] = cmul_conj(row[pos * S + qsw[pos & (NVA - 1)]], t);
       }
       reg_dit_inv<16>(x);
       u64 *ap = acc + pA * N;
@@ -440,12 +466,13 @@ template <int LOGM, int L, int LB, int MINB, int PF>
 static void launch_pk(const K1Args &a, int count, cudaStream_t st) {
   // all l levels fit one 32-bit word per coefficient -> pack once per step; otherwise once per batch
   if (L * a.Bg_bit <= 32) launch_one<LOGM, L, LB, MINB, true, PF>(a, count, st);
-  else launch_one<LOGM, L, LB, MINB, LB == L, PF>(a, count, st);
+  else launch_one<LOGM, L, LB, MINB, false, PF>(a, count, st);
 }
 
 void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   const Params &p = b.bsk->p;
   MB_REQUIRE(k1_supported(p) && !b.direct, "k1 kernel: unsupported parameters");
+  upload_w64();
   K1Args a;
   a.bsk = b.bsk->d; a.tab = k1_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
   a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
@@ -460,8 +487,8 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   MB_K1_CASE(10, 1, 1, 1, 0) MB_K1_CASE(10, 2, 2, 1, 0) MB_K1_CASE(10, 3, 3, 1, 0) MB_K1_CASE(10, 4, 2, 1, 0)
   MB_K1_CASE(11, 1, 1, 1, 0) MB_K1_CASE(11, 2, 1, 1, 0) MB_K1_CASE(11, 3, 1, 1, 0) MB_K1_CASE(11, 4, 1, 1, 0)
 #ifdef MB200_K1_EXPERIMENTS
-  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 1, 4, 0) MB_K1_CASE(9, 3, 1, 5, 0) MB_K1_CASE(9, 3, 1, 4, 1) MB_K1_CASE(9, 3, 1, 5, 1)
-  MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 4, 1, 2, 0) MB_K1_CASE(10, 4, 1, 3, 0) MB_K1_CASE(10, 4, 1, 2, 1)
+  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(9, 3, 1, 4, 1)
+  MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 4, 3, 1, 0) MB_K1_CASE(10, 4, 1, 2, 0)
 #endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
