@@ -11,7 +11,7 @@ import os
 from . import abi
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmosfhet_b200.so")
+LIB_PATH = os.path.join(PKG, os.environ.get("MB200_LIB_NAME", "libmosfhet_b200.so"))
 
 _P = C.POINTER
 _params_p = _P(abi.ParamsS)

@@ -9,7 +9,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libmosfhet_b200.so")
+LIB = os.path.join(PKG, os.environ.get("MB200_LIB_NAME", "libmosfhet_b200.so"))
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 NVCC_FLAGS = [
@@ -52,6 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
         if os.environ.get("MB200_K1_EXPERIMENTS"):
             cmd.insert(1, "-DMB200_K1_EXPERIMENTS")
+        for extra in os.environ.get("MB200_NVCC_DEFS", "").split():
+            cmd.insert(1, "-D" + extra)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

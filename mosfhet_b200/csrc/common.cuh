@@ -96,6 +96,9 @@ void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);
 bool k1_supported(const Params &p);
 void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1_variant_name(const Params &p);
+bool k1h_supported(const Params &p);
+void launch_blind_rotate_k1h(const BlindRotateLaunch &a, cudaStream_t st);
+const char *k1h_variant_name(const Params &p);
 
 void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st);
 void launch_extract(u64 *out, const u64 *trlwe, const int *d_idx, int idx_count, int N, int k, int count,

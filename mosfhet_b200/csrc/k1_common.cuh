@@ -1,0 +1,113 @@
+// k1_common.cuh -- register-resident FFT building blocks shared by the k = 1 blind-rotation kernels.
+#pragma once
+#include "common.cuh"
+#include "device_math.cuh"
+#include "w64_constants.cuh"
+
+namespace mb {
+
+// W_64 powers in constant memory: FP64 instructions take c[bank][offset] operands directly, whereas
+// folded 64-bit immediates cost two UMOV each time they are rematerialised (ncu: 184 UMOV per step).
+static __constant__ double CW64C[64], CW64S[64];   // one copy per translation unit
+static void upload_w64() {
+  static bool done = false;
+  if (done) return;
+  MB_CHECK(cudaMemcpyToSymbol(CW64C, W64C_HOST, sizeof(double) * 64));
+  MB_CHECK(cudaMemcpyToSymbol(CW64S, W64S_HOST, sizeof(double) * 64));
+  MB_CHECK(cudaDeviceSynchronize());
+  done = true;
+}
+
+// x * W_64^idx (or its conjugate).  idx is a compile-time constant after unrolling, so the trivial
+// cases cost nothing and the 8th roots cost 2 mul + 2 add.
+__device__ __forceinline__ double2 mul_w64(double2 x, int idx, bool conj) {
+  idx &= 63;
+  if (conj) idx = (64 - idx) & 63;
+  const double h = 0.70710678118654752440;
+  if (idx == 0) return x;
+  if (idx == 16) return make_double2(-x.y, x.x);
+  if (idx == 32) return make_double2(-x.x, -x.y);
+  if (idx == 48) return make_double2(x.y, -x.x);
+  if (idx == 8) return make_double2((x.x - x.y) * h, (x.x + x.y) * h);
+  if (idx == 24) return make_double2((-x.x - x.y) * h, (x.x - x.y) * h);
+  if (idx == 40) return make_double2((x.y - x.x) * h, (-x.x - x.y) * h);
+  if (idx == 56) return make_double2((x.x + x.y) * h, (x.y - x.x) * h);
+  const double c = CW64C[idx], s = CW64S[idx];
+  return make_double2(fma(x.x, c, -x.y * s), fma(x.x, s, x.y * c));
+}
+
+__host__ __device__ constexpr int brev(int x, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+__host__ __device__ constexpr int clog2(int x) { return x <= 1 ? 0 : 1 + clog2(x >> 1); }
+
+// in-register radix-R DIF: on return x[pos] = X[brev(pos)],  X_k = sum_m x_m W_R^(+mk)
+template <int R>
+__device__ __forceinline__ void reg_dif(double2 (&x)[R]) {
+#pragma unroll
+  for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int b = 0; b < R / 2; ++b) {
+      const int j = b & (h - 1);
+      const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
+      const double2 u = x[i0], v = x[i1];
+      x[i0] = cadd(u, v);
+      x[i1] = mul_w64(csub(u, v), j * (32 / h), false);
+    }
+  }
+}
+
+// in-register radix-R DIT inverse: input x[pos] = X[brev(pos)], output x[m] = sum_k X_k W_R^(-mk)
+template <int R>
+__device__ __forceinline__ void reg_dit_inv(double2 (&x)[R]) {
+#pragma unroll
+  for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+    for (int b = 0; b < R / 2; ++b) {
+      const int j = b & (h - 1);
+      const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
+      const double2 u = x[i0], v = mul_w64(x[i1], j * (32 / h), true);
+      x[i0] = cadd(u, v);
+      x[i1] = csub(u, v);
+    }
+  }
+}
+
+__device__ __forceinline__ int swz(int s) { return s ^ ((s >> 3) & 7); }
+
+struct K1Args {
+  const double2 *bsk;
+  const double2 *tab;     // TA[16][S] then TB[R2][8]
+  const u64 *tv;
+  int tv_count;
+  const u64 *in;
+  int in_stride;
+  int size;
+  u64 *out;
+  int extract, init_rotate;
+  u64 prec_offset;
+  int preprocess, kappa, theta;
+  int Bg_bit;
+};
+
+// f64 -> u64 mod 2^64, round to nearest (AVX-512 path of the reference, fft_processor_spqlios.c:158-164)
+// done on the FP64 pipe + one F2I instead of ~25 integer instructions: r = rint(x / 2^64) by the
+// 1.5*2^52 trick (|x| < 2^115), y = x - r*2^64 is exact and |y| <= 2^63, then a rounding convert.
+__device__ __forceinline__ u64 f64_to_torus_fast(double x) {
+  const double C = 6755399441055744.0;
+  const double t = x * 5.42101086242752217e-20;       // 2^-64
+  const double r = (t + C) - C;
+  const double y = fma(r, -18446744073709551616.0, x);
+  return (u64)__double2ll_rn(y);
+}
+
+__device__ __forceinline__ double2 ldg_key(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+
+}  // namespace mb
