@@ -290,8 +290,18 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved_tf = flops_launch / pbs_avg_s * 1e-12
+        # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+        # workload (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); null if not captured
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(f"{args.workload}:{B}")
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {"bound": "fp64", "kernel": api.last_blind_rotate_kernel(), "achieved": achieved_tf, "peak": fp64_peak,
-                    "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                     "peak_source": "measured live: mb200_measure_fp64_tflops (dependent-FMA microbenchmark, same clocks)",
                     "algorithmic_flops_per_unit": P.flops_per_pbs(), "units_per_launch": B,
                     "kernel_share_of_step": pbs_total / total_ms,

@@ -323,15 +323,21 @@ const double2 *k1_tables_for(int N) {
 // fastest measured on B200 (profiles/); MB200_K1_LB / _MINB / _PF override it for experiments.
 struct K1Variant { int lb, minb, pf; };
 
-static K1Variant default_variant(int logm, int l) {
-  if (logm == 11) return {1, 1, 0};
-  if (logm == 10 && l == 4) return {2, 1, 0};
+// Levels per shared-memory batch: as many as fit (a) the 32-bit packed-digit word, lb*Bg_bit <= 32, and
+// (b) shared memory with >= 2 CTAs per SM at N = 2048 / 1 CTA at N = 4096.
+static K1Variant default_variant(int logm, int l, int Bg_bit) {
+  int lb = l;
+  if (logm == 10 && lb > 2) lb = 2;
+  if (logm == 11) lb = 1;
+  while (lb > 1 && lb * Bg_bit > 32) --lb;
+  if (lb == 3 && l == 4) lb = 2;                        // instantiated batch sizes: l, 2, 1
   // double-buffered key rows in pass C pay off while they fit the register file (profiles/r1b_k1_variants.log)
-  return {l, 1, (logm <= 9 && l <= 3) ? 1 : 0};
+  const int pf = (logm <= 9 && lb == l && l <= 3) ? 1 : 0;
+  return {lb, 1, pf};
 }
 
-static K1Variant chosen_variant(int logm, int l) {
-  K1Variant v = default_variant(logm, l);
+static K1Variant chosen_variant(int logm, int l, int Bg_bit) {
+  K1Variant v = default_variant(logm, l, Bg_bit);
   if (const char *e = getenv("MB200_K1_LB")) v.lb = atoi(e);
   if (const char *e = getenv("MB200_K1_MINB")) v.minb = atoi(e);
   if (const char *e = getenv("MB200_K1_PF")) v.pf = atoi(e);
@@ -342,13 +348,13 @@ bool k1_supported(const Params &p) {
   if (p.k != 1) return false;
   const int logm = ilog2i(p.N) - 1;
   if (!(logm >= 8 && logm <= 11 && p.l >= 1 && p.l <= 4 && (1 << (logm + 1)) == p.N)) return false;
-  return default_variant(logm, p.l).lb * p.Bg_bit <= 32;
+  return p.Bg_bit >= 1 && p.Bg_bit <= 32;
 }
 
 static char g_name[80];
 const char *k1_variant_name(const Params &p) {
   const int logm = ilog2i(p.N) - 1;
-  const K1Variant v = chosen_variant(logm, p.l);
+  const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d>", p.N, p.l, v.lb, v.minb,
            (int)(p.l * p.Bg_bit <= 32), v.pf);
   return g_name;
@@ -386,17 +392,21 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   const int logm = ilog2i(p.N) - 1;
-  const K1Variant v = chosen_variant(logm, p.l);
+  const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");
 #define MB_K1_CASE(LM, LL, LBB, MB_, PF_) \
   if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_>(a, b.count, st); return; }
+  // N = 512, 1024: batch = all levels (double-buffered keys for l <= 3), or 2 / 1 levels when l*Bg_bit > 32
   MB_K1_CASE(8, 1, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1, 1) MB_K1_CASE(8, 3, 3, 1, 1) MB_K1_CASE(8, 4, 4, 1, 0)
+  MB_K1_CASE(8, 2, 1, 1, 0) MB_K1_CASE(8, 3, 2, 1, 0) MB_K1_CASE(8, 3, 1, 1, 0) MB_K1_CASE(8, 4, 2, 1, 0) MB_K1_CASE(8, 4, 1, 1, 0)
   MB_K1_CASE(9, 1, 1, 1, 1) MB_K1_CASE(9, 2, 2, 1, 1) MB_K1_CASE(9, 3, 3, 1, 1) MB_K1_CASE(9, 4, 4, 1, 0)
-  MB_K1_CASE(10, 1, 1, 1, 0) MB_K1_CASE(10, 2, 2, 1, 0) MB_K1_CASE(10, 3, 3, 1, 0) MB_K1_CASE(10, 4, 2, 1, 0)
+  MB_K1_CASE(9, 2, 1, 1, 0) MB_K1_CASE(9, 3, 2, 1, 0) MB_K1_CASE(9, 3, 1, 1, 0) MB_K1_CASE(9, 4, 2, 1, 0) MB_K1_CASE(9, 4, 1, 1, 0)
+  // N = 2048: at most 2 levels per batch (2 CTAs per SM); N = 4096: 1
+  MB_K1_CASE(10, 1, 1, 1, 0) MB_K1_CASE(10, 2, 2, 1, 0) MB_K1_CASE(10, 3, 2, 1, 0) MB_K1_CASE(10, 4, 2, 1, 0)
+  MB_K1_CASE(10, 2, 1, 1, 0) MB_K1_CASE(10, 3, 1, 1, 0) MB_K1_CASE(10, 4, 1, 1, 0)
   MB_K1_CASE(11, 1, 1, 1, 0) MB_K1_CASE(11, 2, 1, 1, 0) MB_K1_CASE(11, 3, 1, 1, 0) MB_K1_CASE(11, 4, 1, 1, 0)
 #ifdef MB200_K1_EXPERIMENTS
-  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(9, 3, 1, 4, 1)
-  MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 4, 3, 1, 0) MB_K1_CASE(10, 4, 1, 2, 0)
+  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 3, 3, 1, 0)
 #endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);

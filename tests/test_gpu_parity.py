@@ -393,3 +393,49 @@ def test_full_size_round_trip(P, count):
     assert np.array_equal(dec2 % (2 * torus_base), (((msgs * 3 + 1) % torus_base) * 3 + 1) % torus_base)
     bsk.free()
     ksk.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# Every instantiation of the specialised kernels against the generic kernel and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("l,Bg_bit", [(1, 23), (2, 8), (3, 6), (4, 9), (2, 15), (3, 10)])
+def test_k1_instantiations_vs_generic(N, l, Bg_bit):
+    """(l, Bg_bit) covers digits packed once per step (l*Bg_bit <= 32) and per batch (> 32)."""
+    n_short, count = 10, 5
+    P = Params(n_short, N, 1, l, Bg_bit, 3, 2, 2.0 ** -30, 2.0 ** -50)
+    lwe_key, rlwe_key = syn.binary_key(P.n, 5), syn.binary_key(P.N, 6)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=N + l)
+    msgs = np.arange(count) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, 2.0 ** -30, seed=7)
+    cts[1, 0] = 0                                   # a skipped step
+    cts[2, :3] = np.uint64(2 ** 64 - 2 ** 40)       # rotations by 2N-1 ... wrap to 0
+    lut = syn.splitmix64_stream(N + 17, 4)
+    tv = syn.test_vector(lut, P.N, 1)
+    outs = {}
+    for name, policy in (("generic", 1), ("k1", 2), ("k1h", 3)):
+        api.set_kernel_policy(policy)
+        outs[name] = api.pbs_host(bsk, tv, cts, 4).copy()
+        outs[name + "_kernel"] = api.last_blind_rotate_kernel()
+    api.set_kernel_policy(0)
+    assert outs["generic_kernel"] == "generic"
+    assert outs["k1_kernel"].startswith("k1<"), outs["k1_kernel"]
+    # 2^44 is the SURVEY 8(c) bound for 36-bit gadgets; with a 23-bit gadget the digits (and with them the
+    # f64 rounding of every product) are 2^14 times larger, so two FFT orders differ by up to ~2^48 there
+    tol = TOL_PHASE if l * Bg_bit >= 27 else (1 << 48)
+    ph_g = syn.tlwe_phase(outs["generic"], rlwe_key)
+    for name in ("k1", "k1h"):
+        ph = syn.tlwe_phase(outs[name], rlwe_key)
+        assert syn.torus_distance(ph, ph_g).max() <= tol, (name, outs[name + "_kernel"])
+    # the oracle on the first ciphertext (keys read back from the resident layout)
+    M = N // 2
+    key_t = _tensor_from_ptr(bsk.device_ptr, P.n * 2 * l * 2 * M * 2)
+    res = key_t.cpu().numpy().reshape(P.n, 2 * l, 2, M, 2)
+    idx = np.arange(M)
+    freq = bitrev_perm(M)[((idx % (M // 8)) << 3) + idx // (M // 8)]
+    nat = np.empty((P.n, 2 * l, 2, N))
+    nat[..., freq] = res[..., 0]
+    nat[..., freq + M] = res[..., 1]
+    want = O.functional_bootstrap(tv, cts[0], nat, l, Bg_bit, 4)
+    assert sdiff(np.uint64(O.tlwe_phase(outs["k1"][0], rlwe_key)), np.uint64(O.tlwe_phase(want, rlwe_key))) <= tol
+    bsk.free()
