@@ -15,7 +15,11 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
         "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sass__inst_executed_local_loads",
-        "sass__inst_executed_local_stores", "sm__cycles_elapsed.max", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sass__inst_executed_local_stores", "sm__cycles_elapsed.max", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed", "sm__icc_requests.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active"]
 k = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
 print("kernel:", vals[k] if k is not None else "?", file=out)
 for h, u, v in zip(hdr, units, vals):
