@@ -76,6 +76,9 @@ void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx);                           
 void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key);                                           /* mosfhet.h:227, tlwe.c:289      */
 void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key,
                                  int torus_base, int n_luts);                                         /* mosfhet.h:424, bootstrap.c:222 */
+void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base);             /* mosfhet.h:413, bootstrap.c:232 */
+void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base,
+                                 int log_torus_base);                                                 /* mosfhet.h:414, bootstrap.c:245 */
 
 /* ------------------------------------------------------------------------------------------
  * (2) Batched variants over arrays of handles (new).  `count` independent ciphertexts per call.
@@ -100,6 +103,11 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
                                           int torus_base, int count);
 void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE *in,
                                        Bootstrap_Key key, int torus_base, int n_luts, int count);
+/* out[c] points to torus_base+1 TRLWEs; lut[c] (lut_count == count) or lut[0] (lut_count == 1) holds
+ * torus_base integers (the cleartext LUT of bootstrap.c:245). */
+void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count);
+void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLWE **rotated_tv,
+                                       int torus_base, int log_torus_base, int count);
 
 /* ------------------------------------------------------------------------------------------
  * Runtime, key residency and the host Fourier slot order.

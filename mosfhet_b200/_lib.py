@@ -30,7 +30,11 @@ PROTOTYPES = {
     "trlwe_extract_tlwe": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
     "tlwe_keyswitch": (None, [abi.TLWE, abi.TLWE, abi.TLWE_KS_Key]),
     "multivalue_bootstrap_CLOT21": (None, [_P(abi.TLWE), abi.TRLWE, abi.TLWE, abi.Bootstrap_Key, C.c_int, C.c_int]),
+    "multivalue_bootstrap_phase1": (None, [_P(abi.TRLWE), abi.TLWE, abi.Bootstrap_Key, C.c_int]),
+    "multivalue_bootstrap_phase2": (None, [abi.TLWE, _P(C.c_int), _P(abi.TRLWE), C.c_int, C.c_int]),
     # (2) batched
+    "multivalue_bootstrap_phase1_batch": (None, [_P(_P(abi.TRLWE)), _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int]),
+    "multivalue_bootstrap_phase2_batch": (None, [_P(abi.TLWE), _P(_P(C.c_int)), C.c_int, _P(_P(abi.TRLWE)), C.c_int, C.c_int, C.c_int]),
     "functional_bootstrap_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int]),
     "functional_bootstrap_wo_extract_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int]),
     "programmable_bootstrap_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int, C.c_int, C.c_int]),

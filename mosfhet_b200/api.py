@@ -126,6 +126,16 @@ def multivalue_bootstrap_CLOT21(out_list, tv, in_, key, torus_base: int, n_luts:
     lib().multivalue_bootstrap_CLOT21(abi.handle_array(out_list, abi.TLWE), _h(tv), _h(in_), _h(key), torus_base, n_luts)
 
 
+def multivalue_bootstrap_phase1(out_list, in_, key, torus_base: int) -> None:
+    """out_list: torus_base + 1 TRLWEs (bootstrap.c:232-243)."""
+    lib().multivalue_bootstrap_phase1(abi.handle_array(out_list, abi.TRLWE), _h(in_), _h(key), torus_base)
+
+
+def multivalue_bootstrap_phase2(out, lut_ints, rotated_tv, torus_base: int, log_torus_base: int) -> None:
+    lut = (C.c_int * len(lut_ints))(*[int(x) for x in lut_ints])
+    lib().multivalue_bootstrap_phase2(_h(out), lut, abi.handle_array(rotated_tv, abi.TRLWE), torus_base, log_torus_base)
+
+
 def register_bootstrap_key(key) -> None:
     lib().mb200_register_bootstrap_key(_h(key))
 

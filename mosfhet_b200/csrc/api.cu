@@ -787,6 +787,54 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
   for (int c = 0; c < count; ++c) scatter_tlwe(out[c], h_out + (size_t)c * n_luts * (p.k * p.N + 1), n_luts, p.k * p.N);
 }
 
+void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  const mb::Params &p = bsk->p;
+  cudaStream_t st = mb::default_stream();
+  const size_t W = (size_t)(p.k + 1) * p.N;
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), tv_b = sizeof(u64) * W;
+  const size_t acc_b = sizeof(u64) * count * W, out_b = acc_b * (torus_base + 1);
+  u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  u64 *d_acc = (u64 *)t_scratch[S_MID].dev(acc_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_tlwe(h_in, in, count, p.n);
+  // constant test vector: a = 0, b[i] = double2torus(1/(4*torus_base))  (bootstrap.c:234-235)
+  memset(h_tv, 0, tv_b);
+  const u64 cst = prec_offset_for(torus_base);
+  for (int i = 0; i < p.N; ++i) h_tv[(size_t)p.k * p.N + i] = cst;
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, torus_base, count, st);
+  mb::launch_mv_phase1_rotations(d_out, d_acc, p.N, p.k, torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int c = 0; c < count; ++c) scatter_trlwe(out[c], h_out + (size_t)c * (torus_base + 1) * W, torus_base + 1, p.k, p.N);
+}
+
+void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLWE **rotated_tv, int torus_base,
+                                       int log_torus_base, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(lut_count == 1 || lut_count == count, "multivalue phase 2: lut_count must be 1 or count");
+  const int k = rotated_tv[0][0]->k, N = rotated_tv[0][0]->b->N;
+  cudaStream_t st = mb::default_stream();
+  const size_t W = (size_t)(k + 1) * N;
+  const size_t rot_b = sizeof(u64) * count * (torus_base + 1) * W, out_b = sizeof(u64) * (size_t)count * (k * N + 1);
+  const size_t lut_b = sizeof(int) * (size_t)lut_count * torus_base;
+  u64 *h_rot = (u64 *)t_scratch[S_TV].host(rot_b), *d_rot = (u64 *)t_scratch[S_TV].dev(rot_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  int *h_lut = (int *)t_scratch[S_MISC].host(lut_b), *d_lut = (int *)t_scratch[S_MISC].dev(lut_b);
+  for (int c = 0; c < count; ++c) gather_trlwe(h_rot + (size_t)c * (torus_base + 1) * W, rotated_tv[c], torus_base + 1, k, N);
+  for (int c = 0; c < lut_count; ++c) memcpy(h_lut + (size_t)c * torus_base, lut[c], sizeof(int) * torus_base);
+  MB_CHECK(cudaMemcpyAsync(d_rot, h_rot, rot_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_lut, h_lut, lut_b, cudaMemcpyHostToDevice, st));
+  mb::launch_mv_phase2(d_out, d_lut, lut_count, d_rot, N, k, torus_base, log_torus_base, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, k * N);
+}
+
 // ---- drop-in single-ciphertext entry points (reference names) ------------------------------------------
 void functional_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base) {
   functional_bootstrap_batch(&out, &tv, 1, &in, key, torus_base, 1);
@@ -804,6 +852,12 @@ void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_batch(
 void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key) { tlwe_keyswitch_batch(&out, &in, ks_key, 1); }
 void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base, int n_luts) {
   multivalue_bootstrap_CLOT21_batch(&out, &tv, 1, &in, key, torus_base, n_luts, 1);
+}
+void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base) {
+  multivalue_bootstrap_phase1_batch(&out, &in, key, torus_base, 1);
+}
+void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base, int log_torus_base) {
+  multivalue_bootstrap_phase2_batch(&out, &in, 1, &rotated_tv, torus_base, log_torus_base, 1);
 }
 
 }  // extern "C"

@@ -107,6 +107,11 @@ void launch_torus_to_dft(double *out, const u64 *in, int N, int count, cudaStrea
 void launch_dft_to_torus(u64 *out, const double *in, int N, int count, const int *perm, const int *conj,
                          cudaStream_t st);
 
+// multivalue.cu
+void launch_mv_phase1_rotations(u64 *out, const u64 *src, int N, int k, int torus_base, int count, cudaStream_t st);
+void launch_mv_phase2(u64 *out, const int *d_lut, int lut_count, const u64 *rot, int N, int k, int torus_base,
+                      int log_torus_base, int count, cudaStream_t st);
+
 // keys.cu
 void import_bsk(BskDev *dst, const double *d_host_layout /* device copy of the host-form key */, const int32_t *h_exponents,
                 cudaStream_t st);

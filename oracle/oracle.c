@@ -406,3 +406,52 @@ void oracle_blind_rotate_exact(Torus *acc, const Torus *a, const Torus *bsk_toru
   }
   free(rot); free(prod);
 }
+
+/* ---------- multi-value bootstrap ------------------------------------- */
+
+/* bootstrap.c:232-243  multivalue_bootstrap_phase1: out[0..torus_base] TRLWEs */
+void oracle_multivalue_phase1(Torus *out, const Torus *in_tlwe, const double *bsk, int n, int N, int k, int l,
+                              int Bg_bit, int torus_base, int mode) {
+  const size_t W = (size_t)(k + 1) * N;
+  Torus *tv = (Torus *)calloc(W, sizeof(Torus));
+  for (int i = 0; i < N; i++) tv[(size_t)k * N + i] = oracle_double2torus(1.0 / (4 * torus_base));
+  oracle_functional_bootstrap_wo_extract(out, tv, in_tlwe, bsk, n, N, k, l, Bg_bit, torus_base, mode);
+  for (int i = 1; i < torus_base; i++)
+    for (int q = 0; q <= k; q++) oracle_mul_by_xai(out + i * W + (size_t)q * N, out + (size_t)q * N, N, i * N / torus_base);
+  for (int q = 0; q <= k; q++) {
+    oracle_mul_by_xai(out + torus_base * W + (size_t)q * N, out + (size_t)q * N, N, torus_base);
+    for (int c = 0; c < N; c++) out[torus_base * W + (size_t)q * N + c] += out[(size_t)q * N + c];   /* trlwe_addto */
+  }
+  free(tv);
+}
+
+/* trlwe.c:554-578  trlwe_extract_tlwe_addto / _subto */
+static void extract_acc(Torus *out, const Torus *in, int N, int k, int idx, int sign) {
+  Torus *e = (Torus *)malloc(sizeof(Torus) * (k * N + 1));
+  oracle_extract_tlwe(e, in, N, k, idx);
+  for (int c = 0; c <= k * N; c++) out[c] = sign > 0 ? out[c] + e[c] : out[c] - e[c];
+  free(e);
+}
+
+/* bootstrap.c:245-265  multivalue_bootstrap_phase2 (+ trlwe_mv_extract_tlwe_scaling_addto, trlwe.c:602-610) */
+void oracle_multivalue_phase2(Torus *out_tlwe, const int *in, const Torus *rot, int N, int k, int torus_base,
+                              int log_torus_base) {
+  const size_t W = (size_t)(k + 1) * N;
+  Torus *tmp = (Torus *)malloc(sizeof(Torus) * W);
+  memset(out_tlwe, 0, sizeof(Torus) * (k * N + 1));
+  for (int j = 0; j < log_torus_base; j++) {
+    const int s0 = ((in[0] >> j) & 1) + ((in[torus_base - 1] >> j) & 1);
+    if (s0 == 2) memcpy(tmp, rot + torus_base * W, sizeof(Torus) * W);
+    else if (s0 == 1) memcpy(tmp, rot, sizeof(Torus) * W);
+    else memset(tmp, 0, sizeof(Torus) * W);
+    for (int i = 1; i < torus_base; i++) {
+      const int d = ((in[i] >> j) & 1) - ((in[i - 1] >> j) & 1);
+      if (d == 1) for (size_t c = 0; c < W; c++) tmp[c] += rot[i * W + c];
+      else if (d == -1) for (size_t c = 0; c < W; c++) tmp[c] -= rot[i * W + c];
+    }
+    const int amount = 1 << j;
+    for (int i = amount / 2; i < amount; i++) extract_acc(out_tlwe, tmp, N, k, N - 1 - (i - amount / 2), -1);
+    for (int i = 0; i < amount / 2; i++) extract_acc(out_tlwe, tmp, N, k, i, +1);
+  }
+  free(tmp);
+}

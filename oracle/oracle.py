@@ -60,6 +60,8 @@ def lib():
             "oracle_programmable_preprocess": (None, [_u64p, _u64p, _int, _int, _int, _int]),
             "oracle_programmable_bootstrap": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 9),
             "oracle_multivalue_bootstrap_CLOT21": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 8),
+            "oracle_multivalue_phase1": (None, [_u64p, _u64p, _f64p] + [_int] * 7),
+            "oracle_multivalue_phase2": (None, [_u64p, _i32p, _u64p, _int, _int, _int, _int]),
             "oracle_tlwe_keyswitch": (None, [_u64p, _u64p, _u64p, _int, _int, _int, _int]),
             "oracle_tlwe_phase": (C.c_uint64, [_u64p, _u64p, _int]),
             "oracle_trlwe_phase": (None, [_u64p, _u64p, _u64p, _int, _int]),
@@ -232,6 +234,23 @@ def multivalue_bootstrap_CLOT21(tv, tlwe_in, bsk, l, Bg_bit, torus_base, n_luts,
     n = tlwe_in.shape[0] - 1
     out = np.empty((n_luts, k * N + 1), np.uint64)
     lib().oracle_multivalue_bootstrap_CLOT21(out, tv, tlwe_in, bsk, n, N, k, l, Bg_bit, torus_base, n_luts, mode)
+    return out
+
+
+def multivalue_phase1(tlwe_in, bsk, N, k, l, Bg_bit, torus_base, mode=0):
+    tlwe_in = _c(tlwe_in, np.uint64)
+    bsk = _c(bsk, np.float64)
+    out = np.empty((torus_base + 1, k + 1, N), np.uint64)
+    lib().oracle_multivalue_phase1(out, tlwe_in, bsk, tlwe_in.shape[0] - 1, N, k, l, Bg_bit, torus_base, mode)
+    return out
+
+
+def multivalue_phase2(lut_ints, rot, torus_base, log_torus_base):
+    rot = _c(rot, np.uint64)
+    lut = _c(lut_ints, np.int32)
+    k, N = rot.shape[1] - 1, rot.shape[2]
+    out = np.empty(k * N + 1, np.uint64)
+    lib().oracle_multivalue_phase2(out, lut, rot, N, k, torus_base, log_torus_base)
     return out
 
 

@@ -31,5 +31,10 @@ def golden(request):
 
 
 @pytest.fixture
+def golden_mv():
+    return load_golden("tiny_k1_mv_spqlios")
+
+
+@pytest.fixture
 def golden_ffnt():
     return load_golden("tiny_k1_ffnt")

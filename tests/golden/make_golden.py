@@ -189,7 +189,55 @@ def gen(name, P, variant, full=True):
     return out
 
 
+def gen_mv(P, variant):
+    """multivalue_bootstrap_phase1 / phase2 (bootstrap.c:232-265), as test_functional_mv_bootstrap (tests.c:1793-1827)."""
+    R = reflib.load(variant)
+    R.multivalue_bootstrap_phase1.restype = None
+    R.multivalue_bootstrap_phase1.argtypes = [C.POINTER(abi.TRLWE), abi.TLWE, abi.Bootstrap_Key, C.c_int]
+    R.multivalue_bootstrap_phase2.restype = None
+    R.multivalue_bootstrap_phase2.argtypes = [abi.TLWE, C.POINTER(C.c_int), C.POINTER(abi.TRLWE), C.c_int, C.c_int]
+    n, N, k, l, Bg_bit = (P[x] for x in ("n", "N", "k", "l", "Bg_bit"))
+    R.init_fft(N)
+    out = dict(params=np.array([n, N, k, l, Bg_bit, P["t"], P["base_bit"]], np.int32), layout=np.int32(R.layout))
+    key_lwe = R.tlwe_new_binary_key(n, P["lwe_sigma"])
+    key_rlwe = R.trlwe_new_binary_key(N, k, P["rlwe_sigma"])
+    key_ext = R.tlwe_new_binary_key(k * N, P["rlwe_sigma"])
+    R.trlwe_extract_tlwe_key(key_ext, key_rlwe)
+    trgsw_key = R.trgsw_new_key(key_rlwe, l, Bg_bit)
+    bk = R.new_bootstrap_key(trgsw_key, key_lwe, 1)
+    out["lwe_key"] = key_words(key_lwe.contents.s, n)
+    out["ext_key"] = key_words(key_ext.contents.s, k * N)
+    out["bsk_host"] = abi.bootstrap_key_to_flat(bk)
+    tb, log_tb = 4, 2
+    luts = np.array([[1, 2, 3, 0], [3, 3, 0, 1], [0, 1, 2, 3]], np.int32)
+    ins, p1, p2 = [], [], []
+    for m in range(tb):
+        c = R.tlwe_new_sample(m << 61, key_lwe)
+        ins.append(abi.tlwe_to_flat(c))
+        rots = [abi.HostTRLWE.zeros(k, N) for _ in range(tb + 1)]
+        arr = abi.handle_array(rots, abi.TRLWE)
+        R.multivalue_bootstrap_phase1(arr, c, bk, tb)
+        p1.append(np.stack([r.polys.copy() for r in rots]))
+        row = []
+        for lut in luts:
+            o = R.tlwe_alloc_sample(k * N)
+            R.multivalue_bootstrap_phase2(o, (C.c_int * tb)(*[int(x) for x in lut]), arr, tb, log_tb)
+            row.append(abi.tlwe_to_flat(o))
+        p2.append(np.stack(row))
+    out["mv_luts"] = luts
+    out["mv_in"] = np.stack(ins)
+    out["mv_phase1"] = np.stack(p1)
+    out["mv_phase2"] = np.stack(p2)
+    return out
+
+
 def main():
+    if "--mv-only" in sys.argv:
+        data = gen_mv(SETS["tiny_k1"], "avx512")
+        path = os.path.join(HERE, "tiny_k1_mv_spqlios.npz")
+        np.savez_compressed(path, **data)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+        return
     for name, P in SETS.items():
         data = gen(name, P, "avx512")
         path = os.path.join(HERE, f"{name}_spqlios.npz")

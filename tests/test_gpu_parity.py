@@ -439,3 +439,31 @@ def test_k1_instantiations_vs_generic(N, l, Bg_bit):
     want = O.functional_bootstrap(tv, cts[0], nat, l, Bg_bit, 4)
     assert sdiff(np.uint64(O.tlwe_phase(outs["k1"][0], rlwe_key)), np.uint64(O.tlwe_phase(want, rlwe_key))) <= tol
     bsk.free()
+
+
+def test_multivalue_phases_dropin(golden_mv, policy):
+    """multivalue_bootstrap_phase1 / phase2 through the reference handle types (tests.c:1793-1827)."""
+    g, P = golden_mv, golden_mv["P"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], P["k"], P["l"], P["Bg_bit"])
+    tb, log_tb = 4, 2
+    for m in range(g["mv_in"].shape[0]):
+        # phase 2 alone on the reference's phase-1 output: integer only -> bit-exact
+        ref_rots = [abi.HostTRLWE(g["mv_phase1"][m][i]) for i in range(tb + 1)]
+        for li, lut in enumerate(g["mv_luts"]):
+            out = abi.HostTLWE.zeros(P["k"] * P["N"])
+            api.multivalue_bootstrap_phase2(out, lut, ref_rots, tb, log_tb)
+            assert np.array_equal(out.flat(), g["mv_phase2"][m][li])
+        # phase 1 on the GPU: every rotated copy within the phase tolerance of the reference's
+        rots = [abi.HostTRLWE.zeros(P["k"], P["N"]) for _ in range(tb + 1)]
+        api.multivalue_bootstrap_phase1(rots, abi.HostTLWE(g["mv_in"][m]), hbsk, tb)
+        for i in range(tb + 1):
+            e_got, e_ref = O.extract_tlwe(rots[i].polys, 0), O.extract_tlwe(g["mv_phase1"][m][i], 0)
+            assert sdiff(np.uint64(O.tlwe_phase(e_got, g["ext_key"])), np.uint64(O.tlwe_phase(e_ref, g["ext_key"]))) <= TOL_PHASE
+        # rotations are exact given out[0]
+        want = O.mul_by_xai(rots[0].polys[P["k"]], 2 * P["N"] // tb)
+        assert np.array_equal(rots[2].polys[P["k"]], want)
+        out = abi.HostTLWE.zeros(P["k"] * P["N"])
+        api.multivalue_bootstrap_phase2(out, g["mv_luts"][0], rots, tb, log_tb)
+        assert sdiff(np.uint64(O.tlwe_phase(out.flat(), g["ext_key"])), np.uint64((int(g["mv_luts"][0][m]) << 61) % 2**64)) <= TOL_TEST
+    api.release_bootstrap_key(hbsk)

@@ -138,3 +138,25 @@ def test_keyswitch_bit_exact(golden):
     for b in range(g["tlwe_in"].shape[0]):
         got = O.tlwe_keyswitch(g["fb_out"][b], g["ksk"], P["base_bit"])
         assert np.array_equal(got, g["ks_out"][b])
+
+
+def test_multivalue_phases(golden_mv):
+    """multivalue_bootstrap_phase1 / phase2 (bootstrap.c:232-265): phase 2 is integer-only, so fed with the
+    reference's own phase-1 output it must be bit-exact; phase 1 is compared in phase."""
+    g, P = golden_mv, golden_mv["P"]
+    nat = O.permute_from_host(g["bsk_host"], g["layout"])
+    tb, log_tb = 4, 2
+    for m in range(g["mv_in"].shape[0]):
+        for li, lut in enumerate(g["mv_luts"]):
+            got = O.multivalue_phase2(lut, g["mv_phase1"][m], tb, log_tb)
+            assert np.array_equal(got, g["mv_phase2"][m][li])
+        p1 = O.multivalue_phase1(g["mv_in"][m], nat, P["N"], P["k"], P["l"], P["Bg_bit"], tb)
+        for i in range(tb + 1):
+            e_got, e_ref = O.extract_tlwe(p1[i], 0), O.extract_tlwe(g["mv_phase1"][m][i], 0)
+            d = (O.tlwe_phase(e_got, g["ext_key"]) - O.tlwe_phase(e_ref, g["ext_key"])) % 2**64
+            assert abs(int(np.int64(np.uint64(d)))) <= TOL_PHASE
+        # end to end: LUT value of the encrypted message (tests.c:1816-1819)
+        out = O.multivalue_phase2(g["mv_luts"][0], p1, tb, log_tb)
+        want = (int(g["mv_luts"][0][m]) << 61) % 2**64
+        d = (O.tlwe_phase(out, g["ext_key"]) - want) % 2**64
+        assert abs(int(np.int64(np.uint64(d)))) <= (1 << 58)
