@@ -32,8 +32,13 @@
 
 namespace mb {
 
-template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
-__global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
+// G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
+// memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
+// are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
+// CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
+// G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
+template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G>
+__global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
   constexpr int LOGR2 = clog2(R2);
   constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;    // ROWS_B: shared-memory row buffers (largest batch)
@@ -51,11 +56,16 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
   static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64 *acc = reinterpret_cast<u64 *>(smem_raw);                       // [2][N]
+  const int grp = (G > 1) ? threadIdx.x / T : 0;
+  const int tid = (G > 1) ? threadIdx.x - grp * T : threadIdx.x;
+  const int ct_raw = blockIdx.x * G + grp;
+  const bool live = ct_raw < A.count;
+  const int ct = live ? ct_raw : A.count - 1;        // surplus groups of the last CTA shadow a real ciphertext
+  const size_t region = (size_t)2 * N * 8 + (size_t)ROWS_B * M * 16 + (((size_t)A.size * 2 + 15) & ~(size_t)15);
+  u64 *acc = reinterpret_cast<u64 *>(smem_raw + grp * region);       // [2][N]
   double2 *buf = reinterpret_cast<double2 *>(acc + 2 * N);           // [ROWS_B][M]
   unsigned short *rot = reinterpret_cast<unsigned short *>(buf + ROWS_B * M);   // [size] rotation amounts
 
-  const int tid = threadIdx.x, ct = blockIdx.x;
   const int log_N2 = LOGM + 2;
   const double2 *__restrict__ TA = A.tab;
   const double2 *__restrict__ TB = A.tab + 16 * S;
@@ -104,7 +114,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
 
   for (int step = 0; step < A.size; ++step) {
     const int a_i = rot[step];
-    if (a_i == 0) continue;                           // bootstrap.c:114
+    // bootstrap.c:114 skips a_i == 0.  With several ciphertexts in lockstep the step is executed
+    // instead: (X^0 - 1)*acc = 0 decomposes into all-zero digits, so the accumulator is unchanged.
+    if (G == 1 && a_i == 0) continue;
     const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M;
 
     double2 fa[2][8];                                 // Fourier accumulators: positions 8*tid .. 8*tid+7
@@ -171,12 +183,23 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
       auto load_keys = [&](double2 (&dst)[16], int rb) {
         const double2 *__restrict__ k0 = key_row(rb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
+#ifdef MB200_ABL_NOKEY
+        for (int i = 0; i < 8; ++i) { dst[i] = make_double2(1.0 + i, 0.5 * rb); dst[8 + i] = make_double2(0.25 * i, 2.0 + rb); }
+        (void)k0;
+#else
+        for (int i = 0; i < 8; ++i) {
+          if (G > 1) { dst[i] = __ldg(k0 + i * C8); dst[8 + i] = __ldg(k0 + M + i * C8); }      // L1-allocating: shared by the groups
+          else { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }          // streaming
+        }
+#endif
       };
       if (PF) load_keys(kv[0], 0);                                      // in flight across pass B
       // ------------------------------- pass B -------------------------------------------------
       constexpr int TASKS_B = ROWS_B * 128 / T;
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
+#ifdef MB200_ABL_NOPASSB
+      if (a_i < 0)
+#endif
 #pragma unroll(PB_UNROLL)
       for (int it = 0; it < TASKS_B; ++it) {
         // task = tid + it*T: row = task >> 7, block b = (task & 127) >> 3 = (tid >> 3) + it*(T/8) (mod 16)
@@ -238,6 +261,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
     __syncthreads();
     // ---------------------------------- B' ---------------------------------------------------------
     constexpr int TASKS_BI = 2 * 128 / T > 0 ? 2 * 128 / T : 1;
+#ifdef MB200_ABL_NOPASSB
+    if (a_i < 0)
+#endif
 #pragma unroll
     for (int it = 0; it < TASKS_BI; ++it) {
       double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
@@ -276,6 +302,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(
   }
 
   // ---- epilogue: sample extraction at index 0 (trlwe.c:540-552) or the raw accumulator -------------
+  if (!live) return;
   if (A.extract) {
     u64 *o = A.out + (size_t)ct * (N + 1);
     for (int c = tid; c < N; c += T) o[c] = (c == 0) ? acc[0] : (0ull - acc[N - c]);
@@ -351,36 +378,40 @@ bool k1_supported(const Params &p) {
   return p.Bg_bit >= 1 && p.Bg_bit <= 32;
 }
 
-static char g_name[80];
+static char g_name[96];
+static int g_last_grp = 1;
 const char *k1_variant_name(const Params &p) {
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
-  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d>", p.N, p.l, v.lb, v.minb,
-           (int)(p.l * p.Bg_bit <= 32), v.pf);
+  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d,g=%d>", p.N, p.l, v.lb, v.minb,
+           (int)(p.l * p.Bg_bit <= 32), v.pf, g_last_grp);
   return g_name;
 }
 
-template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
-static void launch_one(const K1Args &a, int count, cudaStream_t st) {
+template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G>
+static bool launch_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
-  const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
+  const size_t region = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
+  const size_t smem = region * G;
+  if (G > 1 && smem > 227 * 1024) return false;        // caller falls back to one ciphertext per CTA
   static size_t configured = 0;
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1 kernel: %zu B of shared memory needed (blind rotation too long)", smem);
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF>,
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF, G>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF><<<count, M / 8, smem, st>>>(a);
+  blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF, G><<<(count + G - 1) / G, G * (M / 8), smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
+  return true;
 }
 
-template <int LOGM, int L, int LB, int MINB, int PF>
-static void launch_pk(const K1Args &a, int count, cudaStream_t st) {
+template <int LOGM, int L, int LB, int MINB, int PF, int G>
+static bool launch_pk(const K1Args &a, int count, cudaStream_t st) {
   // all l levels fit one 32-bit word per coefficient -> pack once per step; otherwise once per batch
-  if (L * a.Bg_bit <= 32) launch_one<LOGM, L, LB, MINB, true, PF>(a, count, st);
-  else launch_one<LOGM, L, LB, MINB, false, PF>(a, count, st);
+  if (L * a.Bg_bit <= 32) return launch_one<LOGM, L, LB, MINB, true, PF, G>(a, count, st);
+  return launch_one<LOGM, L, LB, MINB, false, PF, G>(a, count, st);
 }
 
 void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
@@ -391,11 +422,23 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   a.bsk = b.bsk->d; a.tab = k1_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
   a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
+  a.count = b.count;
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");
+  // ciphertexts per CTA in lockstep, sharing key rows through L1.  MEASURED SLOWER (profiles/r1h_k1_groups.log:
+  // 71 ms vs 51 ms at level 1, 233 vs 141 at level 2): independent CTAs drift into different phases and overlap
+  // the FP64-heavy and shared-memory-heavy passes of different ciphertexts; lockstep removes that.  Opt-in only.
+  int grp = 1;
+  if (const char *e = getenv("MB200_K1_G")) grp = atoi(e);
+#define MB_K1_GCASE(LM, LL, LBB, MB_, PF_, G_) \
+  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_ && grp == G_) { \
+    if (launch_pk<LM, LL, LBB, MB_, PF_, G_>(a, b.count, st)) { g_last_grp = G_; return; } grp = 1; }
+  MB_K1_GCASE(9, 3, 3, 1, 1, 3) MB_K1_GCASE(9, 3, 3, 1, 1, 2) MB_K1_GCASE(10, 4, 2, 1, 0, 2)
+#undef MB_K1_GCASE
+  g_last_grp = 1;
 #define MB_K1_CASE(LM, LL, LBB, MB_, PF_) \
-  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_>(a, b.count, st); return; }
+  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_, 1>(a, b.count, st); return; }
   // N = 512, 1024: batch = all levels (double-buffered keys for l <= 3), or 2 / 1 levels when l*Bg_bit > 32
   MB_K1_CASE(8, 1, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1, 1) MB_K1_CASE(8, 3, 3, 1, 1) MB_K1_CASE(8, 4, 4, 1, 0)
   MB_K1_CASE(8, 2, 1, 1, 0) MB_K1_CASE(8, 3, 2, 1, 0) MB_K1_CASE(8, 3, 1, 1, 0) MB_K1_CASE(8, 4, 2, 1, 0) MB_K1_CASE(8, 4, 1, 1, 0)

@@ -310,6 +310,7 @@ void launch_blind_rotate_k1h(const BlindRotateLaunch &b, cudaStream_t st) {
   a.bsk = b.bsk->d; a.tab = k1h_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
   a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
+  a.count = b.count;
   const int logm = ilog2i(p.N) - 1;
   int minb = 3;
   if (const char *e = getenv("MB200_K1H_MINB")) minb = atoi(e);

@@ -90,6 +90,7 @@ struct K1Args {
   u64 prec_offset;
   int preprocess, kappa, theta;
   int Bg_bit;
+  int count;              // ciphertexts in the launch (kernels with several ciphertexts per CTA)
 };
 
 // f64 -> u64 mod 2^64, round to nearest (AVX-512 path of the reference, fft_processor_spqlios.c:158-164)
