@@ -152,9 +152,12 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
       if (!PKALL) pack_digits(lev0 + NB);
       // pass-A twiddles w^q * W_M^(q*k1): the same 16 values for every level of the batch -- loaded once
       // (the L1/shared-memory data pipe, not FP64, is the busiest unit of this kernel: ncu r1e)
-      double2 twA[16];
+      constexpr bool HOIST_TW = (LOGM <= 9);          // N = 2048+: registers are needed elsewhere (pass C key buffers)
+      double2 twA[HOIST_TW ? 16 : 1];
+      if (HOIST_TW) {
 #pragma unroll
-      for (int pos = 0; pos < 16; ++pos) twA[pos] = __ldg(&TA[brev(pos, 4) * S + qA]);
+        for (int pos = 0; pos < 16; ++pos) twA[HOIST_TW ? pos : 0] = __ldg(&TA[brev(pos, 4) * S + qA]);
+      }
 #pragma unroll(PA_UNROLL)
       for (int lb = 0; lb < NB; ++lb) {
         const int sh = (PKALL ? (L - 1 - lev0 - lb) : (NB - 1 - lb)) * Bg_bit;
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
         double2 *row = buf + (pA * NB + lb) * M;
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) {
-          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], twA[pos]);
+          const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
+          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
         }
       }
       __syncthreads();

@@ -7,7 +7,7 @@ from mosfhet_b200.params import NAMED
 
 api.init(0)
 B = int(os.environ.get("BATCH", "4096"))
-for wl, variants in (("level1", [(3, 1, 1), (3, 1, 0), (2, 4, 1)]),
+for wl, variants in (("level1", [(3, 1, 1)]),
                      ("level2", [(2, 1, 0), (2, 1, 1)])):
     P = NAMED[wl]
     lwe_key, rlwe_key = syn.binary_key(P.n, 1), syn.binary_key(P.N, 2)

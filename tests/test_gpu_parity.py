@@ -12,6 +12,10 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
+import os as _os
+TESTS_DIR = _os.path.dirname(_os.path.abspath(__file__))
+ROOT_DIR = _os.path.dirname(TESTS_DIR)
+
 TOL_EXTPROD_RAW = 1 << 29      # one external product, raw coefficients (units of 2^-64)
 TOL_PHASE = 1 << 44            # blind rotation / bootstrap, phase under the secret key
 TOL_TEST = 1 << 58             # the reference's own test tolerance (tests.c:1602)
@@ -467,3 +471,95 @@ def test_multivalue_phases_dropin(golden_mv, policy):
         api.multivalue_bootstrap_phase2(out, g["mv_luts"][0], rots, tb, log_tb)
         assert sdiff(np.uint64(O.tlwe_phase(out.flat(), g["ext_key"])), np.uint64((int(g["mv_luts"][0][m]) << 61) % 2**64)) <= TOL_TEST
     api.release_bootstrap_key(hbsk)
+
+
+# ------------------------------------------------------------------------------------------------
+# Batched handle entry points: each must equal the single-ciphertext drop-in call element by element
+# (the kernels are deterministic, so equality is bit for bit)
+# ------------------------------------------------------------------------------------------------
+def test_batched_entry_points_equal_singles(golden):
+    g, P = golden, golden["P"]
+    k, N, n = P["k"], P["N"], P["n"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, P["l"], P["Bg_bit"])
+    api.register_bootstrap_key(hbsk)
+    B = g["tlwe_in"].shape[0]
+    tv = abi.HostTRLWE(g["tv"])
+    ins = [abi.HostTLWE(g["tlwe_in"][b]) for b in range(B)]
+
+    # functional_bootstrap_wo_extract_batch / programmable_bootstrap_batch vs singles
+    wo_b = [abi.HostTRLWE.zeros(k, N) for _ in range(B)]
+    api.functional_bootstrap_wo_extract_batch(wo_b, tv, ins, hbsk, 4)
+    pb_b = [abi.HostTLWE.zeros(k * N) for _ in range(B)]
+    prec, kappa, theta = (int(x) for x in g["pb_args"])
+    api.programmable_bootstrap_batch(pb_b, tv, ins, hbsk, prec, kappa, theta)
+    for b in range(B):
+        wo = abi.HostTRLWE.zeros(k, N)
+        api.functional_bootstrap_wo_extract(wo, tv, ins[b], hbsk, 4)
+        assert np.array_equal(wo.polys, wo_b[b].polys)
+        pb = abi.HostTLWE.zeros(k * N)
+        api.programmable_bootstrap(pb, tv, ins[b], hbsk, prec, kappa, theta)
+        assert np.array_equal(pb.flat(), pb_b[b].flat())
+
+    # blind_rotate_batch (in place on each accumulator) vs singles
+    accs = [abi.HostTRLWE(g["tv"]) for _ in range(B)]
+    a_list = [np.ascontiguousarray(g["tlwe_in"][b][:n]) for b in range(B)]
+    api.blind_rotate_batch(accs, a_list, hbsk.struct.s, n)
+    for b in range(B):
+        acc = abi.HostTRLWE(g["tv"])
+        api.blind_rotate(acc, a_list[b], hbsk.struct.s, n)
+        assert np.array_equal(acc.polys, accs[b].polys)
+
+    # trgsw_mul_trlwe_DFT_batch with one TRGSW per input, then trlwe_from_DFT_batch
+    cnt = min(4, n)
+    trgsws = [abi.HostTRGSWDFT(g["bsk_host"][i], P["l"], P["Bg_bit"]) for i in range(cnt)]
+    cins = [abi.HostTRLWE(g["fb_wo_extract_out"][i % B]) for i in range(cnt)]
+    dfts = [abi.HostTRLWEDFT.zeros(k, N) for _ in range(cnt)]
+    api.trgsw_mul_trlwe_DFT_batch(dfts, cins, trgsws)
+    outs = [abi.HostTRLWE.zeros(k, N) for _ in range(cnt)]
+    api.trlwe_from_DFT_batch(outs, dfts)
+    nat = O.permute_from_host(g["bsk_host"], g["layout"])
+    for i in range(cnt):
+        d1 = abi.HostTRLWEDFT.zeros(k, N)
+        api.trgsw_mul_trlwe_DFT(d1, cins[i], trgsws[i])
+        assert np.array_equal(d1.polys, dfts[i].polys)
+        want = O.trlwe_from_dft(O.trgsw_mul_trlwe_dft(cins[i].polys, nat[i], P["l"], P["Bg_bit"]))
+        assert sdiff(outs[i].polys, want).max() <= TOL_EXTPROD_RAW
+
+    # multivalue_bootstrap_CLOT21_batch
+    tb, n_luts = (int(x) for x in g["mv_args"])
+    mv_outs = [[abi.HostTLWE.zeros(k * N) for _ in range(n_luts)] for _ in range(2)]
+    import ctypes as C
+    arrs = [abi.handle_array(o, abi.TLWE) for o in mv_outs]
+    pp = (C.POINTER(abi.TLWE) * 2)(*[C.cast(a, C.POINTER(abi.TLWE)) for a in arrs])
+    mv_in = [abi.HostTLWE(g["mv_in"]), abi.HostTLWE(g["mv_in"])]
+    mv_tv = abi.HostTRLWE(g["mv_tv"])
+    api.lib().multivalue_bootstrap_CLOT21_batch(pp, abi.handle_array([mv_tv], abi.TRLWE), 1,
+                                                abi.handle_array(mv_in, abi.TLWE), hbsk.handle, tb, n_luts, 2)
+    single = [abi.HostTLWE.zeros(k * N) for _ in range(n_luts)]
+    api.multivalue_bootstrap_CLOT21(single, mv_tv, mv_in[0], hbsk, tb, n_luts)
+    for c in range(2):
+        for i in range(n_luts):
+            assert np.array_equal(mv_outs[c][i].flat(), single[i].flat())
+    api.release_bootstrap_key(hbsk)
+
+
+def test_dimension_mismatch_aborts():
+    """The reference asserts on dimension mismatches (trlwe.c:542, tlwe.c:293); the library aborts the
+    same way.  Run in a child process so the abort is observable."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from conftest import load_golden
+        from mosfhet_b200 import abi, api
+        g = load_golden("tiny_k1_spqlios"); P = g["P"]
+        api.init(0); api.set_host_fft_layout(g["layout"])
+        hbsk = abi.HostBootstrapKey(g["bsk_host"], P["k"], P["l"], P["Bg_bit"])
+        out = abi.HostTLWE.zeros(P["k"] * P["N"] - 1)          # wrong output dimension
+        api.functional_bootstrap(out, abi.HostTRLWE(g["tv"]), abi.HostTLWE(g["tlwe_in"][0]), hbsk, 4)
+        print("NOT REACHED")
+    """) % (ROOT_DIR, TESTS_DIR)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "NOT REACHED" not in r.stdout
+    assert "mosfhet_b200:" in r.stderr and "dimension" in r.stderr
