@@ -272,10 +272,12 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
 void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   if (a.count <= 0) return;
   const bool can_k1 = g_policy == 0 && !a.direct && mb::k1_supported(a.bsk->p);
-  // policy 0: fastest available; 2: force the T = M/8 kernel; 3: force the T = M/4 kernel
+  // policy 0: fastest available; 2: force the T = M/8 kernel; 3: force the T = M/4 kernel.
+  // The T = M/4 kernel has half the serial work per thread: faster while the GPU is not full (small
+  // batches / latency, profiles/r1j_latency.log), slower at full occupancy (profiles/r1f_k1h_variants.log).
   const char *eh = getenv("MB200_K1H");
-  // (measured slower than the T = M/8 kernel on B200 -- profiles/r1f_k1h_variants.log -- so opt-in only)
-  const bool want_h = g_policy == 3 || (g_policy == 0 && eh && eh[0] == '1');
+  bool want_h = g_policy == 3 || (g_policy == 0 && a.count <= 2 * mb::sm_count() && a.bsk->p.N <= 1024);
+  if (g_policy == 0 && eh) want_h = eh[0] == '1';
   if ((g_policy == 0 || g_policy == 3) && !a.direct && want_h && mb::k1h_supported(a.bsk->p)) {
     mb::launch_blind_rotate_k1h(a, st);
     g_last_kernel = mb::k1h_variant_name(a.bsk->p);

@@ -289,16 +289,25 @@ static void launch_h(const K1Args &a, int count, cudaStream_t st) {
   count_launch();
 }
 
+// Levels per shared-memory batch: all of them when they fit the 32-bit packed-digit word, else 2, else 1
+static int k1h_lb(int logm, int l, int Bg_bit) {
+  int lb = l;
+  if (logm == 10 && lb > 2) lb = 2;
+  while (lb > 1 && lb * Bg_bit > 32) --lb;
+  if (lb == 3 && l == 4) lb = 2;
+  return lb;
+}
+
 bool k1h_supported(const Params &p) {
   if (p.k != 1) return false;
   const int logm = ilog2i(p.N) - 1;
-  if (!(logm >= 8 && logm <= 9 && (1 << (logm + 1)) == p.N && p.l >= 1 && p.l <= 3)) return false;
-  return p.l * p.Bg_bit <= 32;
+  if (!(logm >= 8 && logm <= 10 && (1 << (logm + 1)) == p.N && p.l >= 1 && p.l <= 4)) return false;
+  return p.Bg_bit >= 1 && p.Bg_bit <= 32;
 }
 
 static char g_hname[80];
 const char *k1h_variant_name(const Params &p) {
-  snprintf(g_hname, sizeof(g_hname), "k1h<N=%d,l=%d,T=%d>", p.N, p.l, p.N / 8);
+  snprintf(g_hname, sizeof(g_hname), "k1h<N=%d,l=%d,lb=%d,T=%d>", p.N, p.l, k1h_lb(ilog2i(p.N) - 1, p.l, p.Bg_bit), p.N / 8);
   return g_hname;
 }
 
@@ -312,16 +321,18 @@ void launch_blind_rotate_k1h(const BlindRotateLaunch &b, cudaStream_t st) {
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   a.count = b.count;
   const int logm = ilog2i(p.N) - 1;
-  int minb = 3;
-  if (const char *e = getenv("MB200_K1H_MINB")) minb = atoi(e);
-#define MB_K1H_CASE(LM, LL, MB_) if (logm == LM && p.l == LL && minb == MB_) { launch_h<LM, LL, LL, MB_>(a, b.count, st); return; }
-  MB_K1H_CASE(8, 1, 3) MB_K1H_CASE(8, 2, 3) MB_K1H_CASE(8, 3, 3)
-  MB_K1H_CASE(9, 1, 3) MB_K1H_CASE(9, 2, 3) MB_K1H_CASE(9, 3, 3)
-#ifdef MB200_K1_EXPERIMENTS
-  MB_K1H_CASE(9, 3, 2) MB_K1H_CASE(9, 3, 4)
-#endif
+  const int lb = k1h_lb(logm, p.l, p.Bg_bit);
+  // one register-rich variant per shape: this kernel is the small-batch / low-latency path
+  // (profiles/r1j_latency.log: 2.7 ms vs 4.4 ms per PBS at batch <= 148 for N = 1024)
+#define MB_K1H_CASE(LM, LL, LBB, MB_) if (logm == LM && p.l == LL && lb == LBB) { launch_h<LM, LL, LBB, MB_>(a, b.count, st); return; }
+  MB_K1H_CASE(8, 1, 1, 2) MB_K1H_CASE(8, 2, 2, 2) MB_K1H_CASE(8, 3, 3, 2) MB_K1H_CASE(8, 4, 4, 2)
+  MB_K1H_CASE(8, 2, 1, 2) MB_K1H_CASE(8, 3, 2, 2) MB_K1H_CASE(8, 3, 1, 2) MB_K1H_CASE(8, 4, 2, 2) MB_K1H_CASE(8, 4, 1, 2)
+  MB_K1H_CASE(9, 1, 1, 2) MB_K1H_CASE(9, 2, 2, 2) MB_K1H_CASE(9, 3, 3, 2) MB_K1H_CASE(9, 4, 4, 2)
+  MB_K1H_CASE(9, 2, 1, 2) MB_K1H_CASE(9, 3, 2, 2) MB_K1H_CASE(9, 3, 1, 2) MB_K1H_CASE(9, 4, 2, 2) MB_K1H_CASE(9, 4, 1, 2)
+  MB_K1H_CASE(10, 1, 1, 1) MB_K1H_CASE(10, 2, 2, 1) MB_K1H_CASE(10, 3, 2, 1) MB_K1H_CASE(10, 4, 2, 1)
+  MB_K1H_CASE(10, 2, 1, 1) MB_K1H_CASE(10, 3, 1, 1) MB_K1H_CASE(10, 4, 1, 1)
 #undef MB_K1H_CASE
-  MB_FATAL("k1h kernel: no instantiation for N=%d l=%d minb=%d", p.N, p.l, minb);
+  MB_FATAL("k1h kernel: no instantiation for N=%d l=%d lb=%d", p.N, p.l, lb);
 }
 
 }  // namespace mb

@@ -28,31 +28,38 @@ __device__ __forceinline__ ulonglong2 ldg_u128(const u64 *p) {
   return v;
 }
 
+// `slices` > 1 (small batches): the sweep over the input coefficients of one ciphertext is split over
+// `slices` warps (in different CTAs), each adding its partial sum into the zero-initialised output with
+// 64-bit integer atomics -- still exact and order independent.
 template <int NV>
 __global__ void __launch_bounds__(KS_MAX_WARPS * 32, 1)
 keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u64 *__restrict__ ksk, int count,
-                      int n_in, int n_out, int t, int base_bit, int row_stride, int cts_per_cta) {
+                      int n_in, int n_out, int t, int base_bit, int row_stride, int cts_per_cta, int slices,
+                      int i_per) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ct = blockIdx.x * cts_per_cta + warp;
+  const int vct = blockIdx.x * cts_per_cta + warp;          // (ciphertext, slice) pair
+  const int ct = vct / slices, sl = vct - ct * slices;
   const bool live = warp < cts_per_cta && ct < count;
   const int bm1 = (1 << base_bit) - 1;
   const u64 prec_offset = 1ull << (64 - (1 + base_bit * t));
   const u64 *a = in + (size_t)(live ? ct : 0) * (n_in + 1);
+  const int i_begin = sl * i_per, i_end = min(n_in, i_begin + i_per);
 
   u64 acc[2 * NV];
 #pragma unroll
   for (int q = 0; q < 2 * NV; ++q) acc[q] = 0ull;
 
-  for (int i0 = 0; i0 < n_in; i0 += 32) {
+  for (int i0 = i_begin; i0 < i_begin + i_per; i0 += 32) {   // same trip count for every warp (block barriers inside)
     const int i_mine = i0 + lane;
-    const u64 a_mine = (live && i_mine < n_in) ? a[i_mine] + prec_offset : 0ull;   // tlwe.c:297
-    const int ni = min(32, n_in - i0);
+    const u64 a_mine = (live && i_mine < i_end) ? a[i_mine] + prec_offset : 0ull;   // tlwe.c:297
+    const int ni = min(32, i_begin + i_per - i0);
     for (int il = 0; il < ni; ++il) {
       const u64 ai = __shfl_sync(0xffffffffu, a_mine, il);
+      const bool valid = live && (i0 + il) < i_end;
       const u64 *base_row = ksk + (size_t)(i0 + il) * t * bm1 * row_stride + 2 * lane;
       for (int j = 0; j < t; ++j) {
         const unsigned d = (unsigned)(ai >> (64 - (j + 1) * base_bit)) & (unsigned)bm1;
-        if (d != 0 && live) {                       // warp-uniform
+        if (d != 0 && valid) {                      // warp-uniform
           const u64 *row = base_row + (size_t)(j * bm1 + (int)d - 1) * row_stride;
 #pragma unroll
           for (int q0 = 0; q0 < NV; q0 += 5) {      // 5 x 128-bit loads in flight keeps the kernel under 72 registers
@@ -71,14 +78,18 @@ keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u
   }
   if (live) {
     u64 *o = out + (size_t)ct * (n_out + 1);
-    const u64 b = a[n_in];
+    const u64 b = (sl == 0) ? a[n_in] : 0ull;
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
       const int c = 2 * (lane + 32 * q);
-      if (c < n_out) o[c] = acc[2 * q];
-      else if (c == n_out) o[c] = acc[2 * q] + b;
-      if (c + 1 < n_out) o[c + 1] = acc[2 * q + 1];
-      else if (c + 1 == n_out) o[c + 1] = acc[2 * q + 1] + b;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = c + h;
+        if (cc > n_out) continue;
+        const u64 v = acc[2 * q + h] + (cc == n_out ? b : 0ull);
+        if (slices == 1) o[cc] = v;
+        else atomicAdd(&o[cc], v);
+      }
     }
   }
 }
@@ -86,21 +97,33 @@ keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u
 template <int NV>
 static void launch_ks_nv(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
   const Params &p = ksk->p;
-  const int sms = sm_count();
+  const int sms = sm_count(), n_in = p.k * p.N;
+  // small batches: split each ciphertext's sweep so that about 8 warps per SM are busy
+  int slices = 1;
+  if (count < 4 * sms) {
+    slices = (8 * sms + count - 1) / count;
+    const int max_slices = (n_in + 31) / 32;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+  }
+  const int i_per = (((n_in + slices - 1) / slices) + 31) & ~31;
+  slices = (n_in + i_per - 1) / i_per;
+  const int vcount = count * slices;
   // one CTA per SM when the batch allows; as few waves as possible otherwise
-  int waves = (count + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
-  int per = (count + sms * waves - 1) / (sms * waves);
+  int waves = (vcount + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
+  int per = (vcount + sms * waves - 1) / (sms * waves);
   if (per < 1) per = 1;
   if (per > KS_MAX_WARPS) per = KS_MAX_WARPS;
-  const int grid = (count + per - 1) / per;
+  const int grid = (vcount + per - 1) / per;
   static bool configured = false;
   if (!configured) {
     // no shared memory needed: give the whole unified array to L1, which is what shares rows between warps
     MB_CHECK(cudaFuncSetAttribute(keyswitch_warp_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     configured = true;
   }
-  keyswitch_warp_kernel<NV><<<grid, per * 32, 0, st>>>(out, in, ksk->d, count, p.k * p.N, p.n, p.t, p.base_bit,
-                                                     ksk->row_stride, per);
+  if (slices > 1) MB_CHECK(cudaMemsetAsync(out, 0, sizeof(u64) * (size_t)count * (p.n + 1), st));
+  keyswitch_warp_kernel<NV><<<grid, per * 32, 0, st>>>(out, in, ksk->d, count, n_in, p.n, p.t, p.base_bit,
+                                                     ksk->row_stride, per, slices, i_per);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }

@@ -70,7 +70,9 @@ int main(int argc, char **argv) {
     functional_bootstrap(out, lut, c, bk, torus_base);          /* CUDA (interposed) */
     ref_fb(out_ref, lut, c, bk, torus_base);                     /* reference CPU, private namespace */
     const Torus ph = tlwe_phase(out, key_ext), ph_ref = tlwe_phase(out_ref, key_ext);
-    if (sdist(ph, ph_ref) > (1LL << 44)) { printf("PBS %d: phase differs by %lld\n", i, sdist(ph, ph_ref)); bad++; }
+    /* two FFT implementations agree in phase up to the gadget's rounding step times ~2^7
+       (tests/test_gpu_parity.py:phase_tol): 2^(64 - l*Bg_bit + 7) = 2^53 here; messages must be identical */
+    if (sdist(ph, ph_ref) > (1LL << (64 - l * Bg_bit + 7))) { printf("PBS %d: phase differs by %lld\n", i, sdist(ph, ph_ref)); bad++; }
     if (((ph + (1ULL << 60)) >> 61) != ((ph_ref + (1ULL << 60)) >> 61)) { printf("PBS %d: message differs\n", i); bad++; }
     TLWE ko = tlwe_alloc_sample(n), ko_ref = tlwe_alloc_sample(n);
     tlwe_keyswitch(ko, out_ref, ksk);                            /* CUDA (interposed) */

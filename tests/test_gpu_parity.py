@@ -21,6 +21,19 @@ TOL_PHASE = 1 << 44            # blind rotation / bootstrap, phase under the sec
 TOL_TEST = 1 << 58             # the reference's own test tolerance (tests.c:1602)
 
 
+def phase_tol(l, Bg_bit):
+    """Phase tolerance between two FFT implementations of the same blind rotation.
+
+    2^44 is the SURVEY 8(c) bound, measured at the 36-bit gadget of the Level-2 parameters.  It cannot
+    hold for coarse gadgets: whenever the f64 rounding of two implementations puts one accumulator
+    coefficient on different sides of a digit boundary, the rounded value moves by h_l = 2^(64-l*Bg_bit)
+    and from then on the two runs carry different (equally valid) decomposition-rounding noise, whose
+    size in the phase is about h_l*sqrt(N/2) (2^50..2^52 for the 18-bit gadget of the Level-1-style set;
+    measured: k1 vs generic vs k1h on 64 ciphertexts, scripts/debug_k1h.py).  Decrypted messages stay
+    identical -- message spacing is 2^61."""
+    return max(TOL_PHASE, 1 << min(58, 64 - l * Bg_bit + 7))
+
+
 @pytest.fixture(scope="module", autouse=True)
 def _gpu():
     api.require_gpu()
@@ -159,7 +172,7 @@ def test_blind_rotate_dropin(golden, policy):
         a = np.ascontiguousarray(g["tlwe_in"][b][: P["n"]])
         api.blind_rotate(acc, a, hbsk.struct.s, P["n"])
         d = sdiff(O.trlwe_phase(acc.polys, g["rlwe_key"]), O.trlwe_phase(g["blind_rotate_out"][b], g["rlwe_key"]))
-        assert d.max() <= TOL_PHASE
+        assert d.max() <= phase_tol(P["l"], P["Bg_bit"])
 
 
 def test_functional_bootstrap_dropin(golden, policy):
@@ -174,11 +187,11 @@ def test_functional_bootstrap_dropin(golden, policy):
         wo = abi.HostTRLWE.zeros(P["k"], P["N"])
         api.functional_bootstrap_wo_extract(wo, tv, cin, hbsk, 4)
         d = sdiff(O.trlwe_phase(wo.polys, g["rlwe_key"]), O.trlwe_phase(g["fb_wo_extract_out"][b], g["rlwe_key"]))
-        assert d.max() <= TOL_PHASE
+        assert d.max() <= phase_tol(P["l"], P["Bg_bit"])
         out = abi.HostTLWE.zeros(P["k"] * P["N"])
         api.functional_bootstrap(out, tv, cin, hbsk, 4)
         ph, ph_ref = O.tlwe_phase(out.flat(), g["ext_key"]), O.tlwe_phase(g["fb_out"][b], g["ext_key"])
-        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= TOL_PHASE
+        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= phase_tol(P["l"], P["Bg_bit"])
         assert sdiff(np.uint64(ph), g["lut_vals"][g["msgs"][b]]) <= TOL_TEST
         assert O.torus2int(ph, 6) == O.torus2int(ph_ref, 6)        # decrypted message identical
         assert np.array_equal(tv.polys, g["tv"])                     # tv untouched (bootstrap.c:195)
@@ -198,13 +211,13 @@ def test_programmable_and_multivalue(golden, policy):
         out = abi.HostTLWE.zeros(P["k"] * P["N"])
         api.programmable_bootstrap(out, tv, abi.HostTLWE(g["tlwe_in"][b]), hbsk, prec, kappa, theta)
         ph, ph_ref = O.tlwe_phase(out.flat(), g["ext_key"]), O.tlwe_phase(g["pb_out"][b], g["ext_key"])
-        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= TOL_PHASE
+        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= phase_tol(P["l"], P["Bg_bit"])
     tb, n_luts = (int(x) for x in g["mv_args"])
     outs = [abi.HostTLWE.zeros(P["k"] * P["N"]) for _ in range(n_luts)]
     api.multivalue_bootstrap_CLOT21(outs, abi.HostTRLWE(g["mv_tv"]), abi.HostTLWE(g["mv_in"]), hbsk, tb, n_luts)
     for i in range(n_luts):
         ph, ph_ref = O.tlwe_phase(outs[i].flat(), g["ext_key"]), O.tlwe_phase(g["mv_out"][i], g["ext_key"])
-        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= TOL_PHASE
+        assert sdiff(np.uint64(ph), np.uint64(ph_ref)) <= phase_tol(P["l"], P["Bg_bit"])
     api.release_bootstrap_key(hbsk)
 
 
@@ -304,7 +317,7 @@ def test_edge_cases(golden, policy):
     nat = O.permute_from_host(g["bsk_host"], g["layout"])
     for b in range(2):
         want = O.functional_bootstrap(g["tv"], cin2[b], nat, Pm.l, Pm.Bg_bit, 4)
-        assert sdiff(np.uint64(O.tlwe_phase(got2[b], g["ext_key"])), np.uint64(O.tlwe_phase(want, g["ext_key"]))) <= TOL_PHASE
+        assert sdiff(np.uint64(O.tlwe_phase(got2[b], g["ext_key"])), np.uint64(O.tlwe_phase(want, g["ext_key"]))) <= phase_tol(Pm.l, Pm.Bg_bit)
     bsk.free()
 
 
@@ -348,7 +361,7 @@ def test_short_rotation_vs_oracle(base, policy):
     for c in range(count):
         want = O.functional_bootstrap(tv, cts[c], nat, P.l, P.Bg_bit, torus_base)
         ph, ph_o = O.tlwe_phase(got[c], rlwe_key), O.tlwe_phase(want, rlwe_key)
-        assert sdiff(np.uint64(ph), np.uint64(ph_o)) <= TOL_PHASE
+        assert sdiff(np.uint64(ph), np.uint64(ph_o)) <= phase_tol(P.l, P.Bg_bit)
         assert sdiff(np.uint64(ph), lut[msgs[c]]) <= TOL_TEST
     bsk.free()
 
@@ -424,9 +437,7 @@ def test_k1_instantiations_vs_generic(N, l, Bg_bit):
     api.set_kernel_policy(0)
     assert outs["generic_kernel"] == "generic"
     assert outs["k1_kernel"].startswith("k1<"), outs["k1_kernel"]
-    # 2^44 is the SURVEY 8(c) bound for 36-bit gadgets; with a 23-bit gadget the digits (and with them the
-    # f64 rounding of every product) are 2^14 times larger, so two FFT orders differ by up to ~2^48 there
-    tol = TOL_PHASE if l * Bg_bit >= 27 else (1 << 48)
+    tol = phase_tol(l, Bg_bit)
     ph_g = syn.tlwe_phase(outs["generic"], rlwe_key)
     for name in ("k1", "k1h"):
         ph = syn.tlwe_phase(outs[name], rlwe_key)
@@ -463,7 +474,7 @@ def test_multivalue_phases_dropin(golden_mv, policy):
         api.multivalue_bootstrap_phase1(rots, abi.HostTLWE(g["mv_in"][m]), hbsk, tb)
         for i in range(tb + 1):
             e_got, e_ref = O.extract_tlwe(rots[i].polys, 0), O.extract_tlwe(g["mv_phase1"][m][i], 0)
-            assert sdiff(np.uint64(O.tlwe_phase(e_got, g["ext_key"])), np.uint64(O.tlwe_phase(e_ref, g["ext_key"]))) <= TOL_PHASE
+            assert sdiff(np.uint64(O.tlwe_phase(e_got, g["ext_key"])), np.uint64(O.tlwe_phase(e_ref, g["ext_key"]))) <= phase_tol(P["l"], P["Bg_bit"])
         # rotations are exact given out[0]
         want = O.mul_by_xai(rots[0].polys[P["k"]], 2 * P["N"] // tb)
         assert np.array_equal(rots[2].polys[P["k"]], want)
