@@ -93,6 +93,9 @@ void programmable_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, 
 void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count);
 void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int in2_count, int count);
 void trlwe_from_DFT_batch(TRLWE *out, TRLWE_DFT *in, int count);
+/* CMUX over arrays with one selector: out[i] = in1[i] + selector (.) (in2[i] - in1[i]); out[i] may be in1[i]
+ * (applications/leveled_lut/vertical_packing.c:24-33) */
+void trgsw_cmux_batch(TRLWE *out, TRLWE *in1, TRLWE *in2, TRGSW_DFT selector, int count);
 void trlwe_extract_tlwe_batch(TLWE *out, TRLWE *in, const int *idx, int idx_count, int count);
 void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count);
 /* The BASELINE metric's unit of work: functional_bootstrap followed by tlwe_keyswitch
@@ -198,6 +201,12 @@ void mb200_pbs_ks_dev(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *d_out /* [coun
 /* One external product + inverse transform per ciphertext: out = TRGSW_i (.) in (trgsw.c:385 + trlwe.c:629) */
 void mb200_extprod_dev(mb200_bsk_t trgsw_set, const int *h_sel /* [count] index into the set */,
                        uint64_t *d_out_trlwe, const uint64_t *d_in_trlwe, int count, void *stream);
+/* CMUX on device-resident TRLWEs, selector = sample `sel` of a resident TRGSW set; d_out may alias d_in1 */
+void mb200_cmux_dev(mb200_bsk_t trgsw_set, int sel, uint64_t *d_out, const uint64_t *d_in1, const uint64_t *d_in2,
+                    int count, void *stream);
+/* CGGI vertical packing (vertical_packing.c:36-52): bits = TRGSW(bit i), i < size; d_luts holds
+ * 2^(size - log2 N) TRLWE LUTs (consumed); d_out_tlwe receives the TLWE (dimension k*N) of LUT[input]. */
+void mb200_vertical_packing_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_out_tlwe, int size, void *stream);
 /* Negacyclic transforms in the library's internal slot order (bit-reversed, e = 1+4*bitrev(s)). */
 void mb200_torus_to_dft_dev(double *d_out /* [count][N] Re|Im */, const uint64_t *d_in, int N, int count, void *stream);
 void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int count, void *stream);

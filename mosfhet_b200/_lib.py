@@ -40,6 +40,7 @@ PROTOTYPES = {
     "programmable_bootstrap_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int, C.c_int, C.c_int]),
     "blind_rotate_batch": (None, [_P(abi.TRLWE), _P(_u64p), _P(abi.TRGSW_DFT), C.c_int, C.c_int]),
     "trgsw_mul_trlwe_DFT_batch": (None, [_P(abi.TRLWE_DFT), _P(abi.TRLWE), _P(abi.TRGSW_DFT), C.c_int, C.c_int]),
+    "trgsw_cmux_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE), _P(abi.TRLWE), abi.TRGSW_DFT, C.c_int]),
     "trlwe_from_DFT_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE_DFT), C.c_int]),
     "trlwe_extract_tlwe_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), _P(C.c_int), C.c_int, C.c_int]),
     "tlwe_keyswitch_batch": (None, [_P(abi.TLWE), _P(abi.TLWE), abi.TLWE_KS_Key, C.c_int]),
@@ -78,6 +79,8 @@ PROTOTYPES = {
     "mb200_ks_dev": (None, [_vp, _vp, _vp, C.c_int, _vp]),
     "mb200_pbs_ks_dev": (None, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_extprod_dev": (None, [_vp, _P(C.c_int), _vp, _vp, C.c_int, _vp]),
+    "mb200_cmux_dev": (None, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
+    "mb200_vertical_packing_dev": (None, [_vp, _vp, _vp, C.c_int, _vp]),
     "mb200_torus_to_dft_dev": (None, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_dft_to_torus_dev": (None, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_pbs_ks_host": (None, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]),

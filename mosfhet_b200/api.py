@@ -199,6 +199,12 @@ def trgsw_mul_trlwe_DFT_batch(out, in1, in2) -> None:
                                     abi.handle_array(in2s, abi.TRGSW_DFT), len(in2s), len(in1))
 
 
+def trgsw_cmux_batch(out, in1, in2, selector) -> None:
+    """out[i] = in1[i] + selector (.) (in2[i] - in1[i])  (vertical_packing.c:24-33)."""
+    lib().trgsw_cmux_batch(abi.handle_array(out, abi.TRLWE), abi.handle_array(in1, abi.TRLWE),
+                           abi.handle_array(in2, abi.TRLWE), _h(selector), len(in1))
+
+
 def trlwe_from_DFT_batch(out, in_) -> None:
     lib().trlwe_from_DFT_batch(abi.handle_array(out, abi.TRLWE), abi.handle_array(in_, abi.TRLWE_DFT), len(in_))
 
@@ -380,6 +386,15 @@ def extprod_dev(trgsw_set, sel, d_out, d_in, count, stream=None):
     sel = np.ascontiguousarray(sel, np.int32)
     lib().mb200_extprod_dev(trgsw_set.handle, sel.ctypes.data_as(C.POINTER(C.c_int)), _ptr(d_out), _ptr(d_in), count,
                             _ptr(stream))
+
+
+def cmux_dev(trgsw_set, sel: int, d_out, d_in1, d_in2, count, stream=None):
+    lib().mb200_cmux_dev(trgsw_set.handle, sel, _ptr(d_out), _ptr(d_in1), _ptr(d_in2), count, _ptr(stream))
+
+
+def vertical_packing_dev(bits, d_luts, d_out_tlwe, size: int, stream=None):
+    """CGGI vertical packing over resident TRGSW bit encryptions; consumes d_luts (vertical_packing.c:36-52)."""
+    lib().mb200_vertical_packing_dev(bits.handle, _ptr(d_luts), _ptr(d_out_tlwe), size, _ptr(stream))
 
 
 def torus_to_dft_dev(d_out, d_in, N, count, stream=None):

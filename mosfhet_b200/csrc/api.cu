@@ -512,10 +512,45 @@ void mb200_extprod_dev(mb200_bsk_t set, const int *h_sel, uint64_t *d_out, const
   MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
   mb::BlindRotateLaunch a{};
   a.bsk = set; a.tv = (const u64 *)d_in; a.tv_count = count; a.size = 1; a.out = (u64 *)d_out; a.count = count;
-  a.direct = 1; a.sel = d_sel;
+  a.direct = 1; a.sel = d_sel; a.sel_const = -1;
   if (count == 1) a.tv_count = 1;
   mb::launch_blind_rotate_generic(a, st);
   g_last_kernel = "generic";
+}
+
+/* CMUX: out[c] = in1[c] + TRGSW[sel] (.) (in2[c] - in1[c])  (vertical_packing.c:24-33); out may alias in1 */
+void mb200_cmux_dev(mb200_bsk_t trgsw_set, int sel, uint64_t *d_out, const uint64_t *d_in1, const uint64_t *d_in2,
+                    int count, void *stream) {
+  MB_REQUIRE(sel >= 0 && sel < trgsw_set->p.n, "cmux: selector %d out of range", sel);
+  if (count <= 0) return;
+  mb::BlindRotateLaunch a{};
+  a.bsk = trgsw_set; a.tv = (const u64 *)d_in2; a.tv_count = count > 1 ? count : 1; a.size = 1; a.out = (u64 *)d_out;
+  a.count = count; a.direct = 1; a.sel_const = sel; a.sub = (const u64 *)d_in1; a.add = (const u64 *)d_in1;
+  mb::launch_blind_rotate_generic(a, as_stream(stream));
+  g_last_kernel = "generic";
+}
+
+/* CGGI vertical packing (vertical_packing.c:36-52): `bits` holds TRGSW(bit i) for i < size; the n_luts =
+ * 2^(size - log2 N) TRLWE LUTs in d_luts are consumed (CMUX tree, one launch per level), then the low
+ * log2 N bits select the coefficient with a short blind rotation; out = TLWE of dimension k*N. */
+void mb200_vertical_packing_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_out_tlwe, int size, void *stream) {
+  const mb::Params &p = bits->p;
+  cudaStream_t st = as_stream(stream);
+  const int log_N = mb::ilog2i(p.N), log_N2 = log_N + 1;
+  MB_REQUIRE(size <= p.n && size >= 1 && size <= 30, "vertical packing: %d input bits but %d TRGSW samples", size, p.n);
+  const size_t W = (size_t)(p.k + 1) * p.N;
+  for (int i = 0; i < size - log_N; ++i) {
+    const int half = 1 << (size - log_N - i - 1);
+    mb200_cmux_dev(bits, size - i - 1, d_luts, d_luts, d_luts + (size_t)half * W, half, st);
+  }
+  const int rot_bits = size > log_N ? log_N : size;
+  u64 h_a[32];
+  for (int i = 0; i < rot_bits; ++i) h_a[i] = (u64)(2 * p.N - (1 << i)) << (64 - log_N2);     // int2torus(2N - 2^i, log 2N)
+  u64 *d_a = (u64 *)t_scratch[S_MISC2].dev(sizeof(u64) * 32);
+  MB_CHECK(cudaMemcpyAsync(d_a, h_a, sizeof(u64) * rot_bits, cudaMemcpyHostToDevice, st));
+  mb200_blind_rotate_dev(bits, d_luts, (const uint64_t *)d_a, rot_bits, rot_bits, 1, st);
+  const int idx0 = 0;
+  mb200_extract_dev(d_out_tlwe, d_luts, &idx0, 1, p.N, p.k, 1, st);
 }
 void mb200_torus_to_dft_dev(double *d_out, const uint64_t *d_in, int N, int count, void *stream) {
   mb::launch_torus_to_dft(d_out, (const u64 *)d_in, N, count, as_stream(stream));
@@ -713,6 +748,7 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
   MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
   mb::BlindRotateLaunch a{};
   a.bsk = set; a.tv = d_in; a.tv_count = count; a.size = 1; a.out = nullptr; a.count = count; a.direct = 1; a.sel = d_sel;
+  a.sel_const = -1;
   a.dft_out = d_out; a.dft_perm = maps.stored_to_host; a.dft_conj = maps.stored_conj;
   mb::launch_blind_rotate_generic(a, st);
   g_last_kernel = "generic";
@@ -729,6 +765,32 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
     if (set->owned) cudaFree(set->d);
     delete set;
   }
+}
+
+/* CMUX over arrays of handles with one selector (vertical_packing.c:24-33); out[i] may be in1[i] */
+void trgsw_cmux_batch(TRLWE *out, TRLWE *in1, TRLWE *in2, TRGSW_DFT selector, int count) {
+  if (count <= 0) return;
+  const int k = in1[0]->k, N = in1[0]->b->N;
+  struct _Bootstrap_Key tmp;
+  tmp.s = &selector; tmp.su = nullptr; tmp.n = 1; tmp.k = k; tmp.N = N; tmp.Bg_bit = selector->Bg_bit; tmp.l = selector->l;
+  tmp.unfolding = 1;
+  mb200_bsk *set = lookup_bsk(&tmp);
+  cudaStream_t st = mb::default_stream();
+  const size_t b = sizeof(u64) * (size_t)count * (k + 1) * N;
+  u64 *h1 = (u64 *)t_scratch[S_TV].host(b), *d1 = (u64 *)t_scratch[S_TV].dev(b);
+  u64 *h2 = (u64 *)t_scratch[S_MID].host(b), *d2 = (u64 *)t_scratch[S_MID].dev(b);
+  gather_trlwe(h1, in1, count, k, N);
+  gather_trlwe(h2, in2, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d1, h1, b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d2, h2, b, cudaMemcpyHostToDevice, st));
+  mb200_cmux_dev(set, 0, (uint64_t *)d1, (const uint64_t *)d1, (const uint64_t *)d2, count, st);
+  MB_CHECK(cudaMemcpyAsync(h1, d1, b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(out, h1, count, k, N);
+  std::lock_guard<std::mutex> lk(g_mu);          // the selector is a ciphertext, not a key: do not keep it resident
+  g_bsk_cache.erase((const void *)&selector);
+  if (set->owned) cudaFree(set->d);
+  delete set;
 }
 
 void trlwe_from_DFT_batch(TRLWE *out, TRLWE_DFT *in, int count) {

@@ -39,6 +39,8 @@ struct GenArgs {
   double *dft_out;
   const int *dft_perm;
   const int *dft_conj;
+  const u64 *sub, *add;
+  int sel_const;
 };
 
 // in-place radix-2 DIF, positive exponent, `nb` polynomials of M complex points; output bit-reversed
@@ -111,9 +113,12 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
     if (A.preprocess) b = pb_preprocess(b, A.kappa, A.theta, log_N2);
     rot0 = (2 * N - (int)torus2int(b + A.prec_offset, log_N2)) & (2 * N - 1);
   }
+  const u64 *sub = A.sub ? A.sub + (size_t)ct * polys * N : nullptr;
   for (int c = threadIdx.x; c < polys * N; c += blockDim.x) {
     const int p = c / N, i = c - p * N;
-    acc[c] = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
+    u64 v = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
+    if (sub) v -= sub[c];                            // CMUX operand in2 - in1 (trlwe_sub, vertical_packing.c:27)
+    acc[c] = v;
   }
   __syncthreads();
 
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
       a_i = (int)torus2int(av, log_N2) & (2 * N - 1);
       if (a_i == 0) continue;                       // bootstrap.c:114 (uniform across the CTA)
     }
-    const int key_idx = A.sel ? A.sel[ct] : step;
+    const int key_idx = A.sel_const >= 0 ? A.sel_const : (A.sel ? A.sel[ct] : step);
     const double2 *key = A.bsk + (size_t)key_idx * rows * polys * M;
 
     for (int c = threadIdx.x; c < polys * Mp; c += blockDim.x) { are[c] = 0.0; aim[c] = 0.0; }
@@ -211,7 +216,8 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
     if (threadIdx.x == 0) o[k * N] = acc[k * N];
   } else {
     u64 *o = A.out + (size_t)ct * polys * N;
-    for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = acc[c];
+    const u64 *add = A.add ? A.add + (size_t)ct * polys * N : nullptr;   // CMUX: + in1 (trlwe_add, :30)
+    for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = add ? acc[c] + add[c] : acc[c];
   }
 }
 
@@ -242,6 +248,7 @@ void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st) {
   g.preprocess = a.preprocess; g.kappa = a.kappa; g.theta = a.theta;
   g.N = p.N; g.k = p.k; g.l = p.l; g.Bg_bit = p.Bg_bit; g.rows_batch = rb;
   g.direct = a.direct; g.sel = a.sel; g.dft_out = a.dft_out; g.dft_perm = a.dft_perm; g.dft_conj = a.dft_conj;
+  g.sub = a.sub; g.add = a.add; g.sel_const = a.direct ? a.sel_const : -1;
   int threads = p.N / 2;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;

@@ -90,6 +90,10 @@ struct BlindRotateLaunch {
   double *dft_out;      // when non-null: write the Fourier-domain result [count][(k+1)][N] (Re|Im) in
   const int *dft_perm;  //   host slot order via dft_perm/dft_conj (device [M]) instead of inverting
   const int *dft_conj;
+  // CMUX (vertical_packing.c:24-33), direct mode only: operand = tv - sub, result = product + add
+  const u64 *sub;       // [count][(k+1)*N] or nullptr
+  const u64 *add;       // [count][(k+1)*N] or nullptr (may alias `out`)
+  int sel_const;        // >= 0: every ciphertext uses TRGSW number sel_const (no `sel` array)
 };
 
 void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);

@@ -574,3 +574,77 @@ def test_dimension_mismatch_aborts():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "NOT REACHED" not in r.stdout
     assert "mosfhet_b200:" in r.stderr and "dimension" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------
+# CMUX and vertical packing (applications/leveled_lut/vertical_packing.c)
+# ------------------------------------------------------------------------------------------------
+def _oracle_cmux(in1, in2, trgsw_nat, l, Bg_bit):
+    d = (in2 - in1).astype(np.uint64)
+    return (in1 + O.trlwe_from_dft(O.trgsw_mul_trlwe_dft(d, trgsw_nat, l, Bg_bit))).astype(np.uint64)
+
+
+def _resident_to_natural(bsk, P):
+    M = P.N // 2
+    key_t = _tensor_from_ptr(bsk.device_ptr, P.n * (P.k + 1) * P.l * (P.k + 1) * M * 2)
+    res = key_t.cpu().numpy().reshape(P.n, (P.k + 1) * P.l, P.k + 1, M, 2)
+    idx = np.arange(M)
+    freq = bitrev_perm(M)[((idx % (M // 8)) << 3) + idx // (M // 8)]
+    nat = np.empty((P.n, (P.k + 1) * P.l, P.k + 1, P.N))
+    nat[..., freq] = res[..., 0]
+    nat[..., freq + M] = res[..., 1]
+    return nat
+
+
+@pytest.mark.parametrize("N,l,Bg_bit", [(512, 2, 10), (2048, 1, 23)])
+def test_cmux_and_vertical_packing(N, l, Bg_bit):
+    import torch
+    log_N = N.bit_length() - 1
+    size = log_N + 3                                    # 8 LUT polynomials, 3 CMUX levels + log N rotations
+    value = 0b101 << log_N | 0b1011001 % N             # the cleartext input
+    bits = np.array([(value >> i) & 1 for i in range(size)], np.uint64)
+    P = Params(size, N, 1, l, Bg_bit, 3, 2, 2.0 ** -30, 2.0 ** -55)
+    rlwe_key = syn.binary_key(N, 77)
+    trgsw_bits = api.BootstrapKey.synthesize(P, bits, rlwe_key, seed=N + 5)     # TRGSW(bit i), as encrypt_bits (:9-22)
+    nat = _resident_to_natural(trgsw_bits, P)
+    rng = np.random.default_rng(N)
+    out_prec = 10
+    lut = rng.integers(0, 1 << out_prec, size=(8, N), dtype=np.uint64)
+    luts = np.zeros((8, 2, N), np.uint64)
+    luts[:, 1, :] = lut << np.uint64(64 - out_prec)      # trivial TRLWE samples of int2torus(LUT, out_prec)
+    tol_raw = 1 << (Bg_bit + 20)                         # one external product, raw (2^29 at Bg_bit = 9)
+
+    # CMUX alone, batch of 4 with the top bit as selector, device and handle forms
+    d1, d2 = torch_dev(luts[:4]), torch_dev(luts[4:])
+    d_out = torch.empty_like(d1)
+    api.cmux_dev(trgsw_bits, size - 1, d_out, d1, d2, 4)
+    api.synchronize()
+    got = to_np(d_out)
+    for c in range(4):
+        want = _oracle_cmux(luts[c], luts[4 + c], nat[size - 1], l, Bg_bit)
+        assert sdiff(got[c], want).max() <= tol_raw
+    sel = abi.HostTRGSWDFT(O.permute_to_host(nat[size - 1], api.FFT_SPQLIOS), l, Bg_bit)
+    api.set_host_fft_layout(api.FFT_SPQLIOS)
+    outs = [abi.HostTRLWE.zeros(1, N) for _ in range(4)]
+    api.trgsw_cmux_batch(outs, [abi.HostTRLWE(luts[c]) for c in range(4)], [abi.HostTRLWE(luts[4 + c]) for c in range(4)], sel)
+    for c in range(4):
+        assert np.array_equal(outs[c].polys, got[c])     # same kernel, same (exactly permuted) selector
+
+    # the whole vertical packing: result decrypts to LUT[value] and matches the oracle composition in phase
+    d_luts = torch_dev(luts)
+    d_res = torch.empty(N + 1, dtype=torch.int64, device="cuda")
+    api.vertical_packing_dev(trgsw_bits, d_luts, d_res, size)
+    api.synchronize()
+    res = to_np(d_res)
+    work = luts.copy()
+    for i in range(size - log_N):
+        half = 1 << (size - log_N - i - 1)
+        for j in range(half):
+            work[j] = _oracle_cmux(work[j], work[j + half], nat[size - i - 1], l, Bg_bit)
+    a = np.array([(2 * N - (1 << i)) << (64 - log_N - 1) for i in range(log_N)], np.uint64)
+    want = O.extract_tlwe(O.blind_rotate(work[0], a, nat[:log_N], l, Bg_bit), 0)
+    ph, ph_o = O.tlwe_phase(res, rlwe_key), O.tlwe_phase(want, rlwe_key)
+    assert sdiff(np.uint64(ph), np.uint64(ph_o)) <= phase_tol(l, Bg_bit)
+    expect = int(lut.reshape(-1)[value])
+    assert O.torus2int(ph, out_prec) % (1 << out_prec) == expect
+    trgsw_bits.free()
