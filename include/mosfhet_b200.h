@@ -51,6 +51,11 @@ typedef struct _TRLWE_DFT { DFT_Polynomial  *a, b; int k; } *TRLWE_DFT;      /* 
 typedef struct _TRGSW     { TRLWE     *samples; int l, Bg_bit; } *TRGSW;     /* mosfhet.h:106 */
 typedef struct _TRGSW_DFT { TRLWE_DFT *samples; int l, Bg_bit; } *TRGSW_DFT; /* mosfhet.h:111 */
 
+typedef struct _Generic_KS_Key {                                             /* mosfhet.h:100 */
+  TRLWE ***s;             /* s[i][j][d-1], i < n + include_b: TRLWE rows (possibly seed-compressed) */
+  int base_bit, t, n, include_b;
+} *Generic_KS_Key;
+
 typedef struct _Bootstrap_Key {                                              /* mosfhet.h:129 */
   TRGSW_DFT *s;           /* s[i], i < n: Fourier-domain TRGSW of LWE key bit i (unfolding==1) */
   TRGSW     *su;          /* torus-domain keys for unfolding > 1 (not accelerated; rejected)   */
@@ -76,6 +81,11 @@ void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx);                           
 void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key);                                           /* mosfhet.h:227, tlwe.c:289      */
 void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key,
                                  int torus_base, int n_luts);                                         /* mosfhet.h:424, bootstrap.c:222 */
+/* circuit bootstrap: TLWE -> TRGSW through one packed-LUT blind rotation, l
+ * extractions and 2*l table key switches over TRLWE rows */
+void trlwe_packing1_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key);                             /* mosfhet.h:384, keyswitch.c:458 */
+void trlwe_priv_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key);                                 /* mosfhet.h:386, keyswitch.c:639 */
+void circuit_bootstrap_2(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb); /* mosfhet.h:421, bootstrap.c:324 */
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base);             /* mosfhet.h:413, bootstrap.c:232 */
 void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base,
                                  int log_torus_base);                                                 /* mosfhet.h:414, bootstrap.c:245 */
@@ -108,6 +118,9 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
                                        Bootstrap_Key key, int torus_base, int n_luts, int count);
 /* out[c] points to torus_base+1 TRLWEs; lut[c] (lut_count == count) or lut[0] (lut_count == 1) holds
  * torus_base integers (the cleartext LUT of bootstrap.c:245). */
+void trlwe_packing1_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count);
+void trlwe_priv_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count);
+void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count);
 void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count);
 void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLWE **rotated_tv,
                                        int torus_base, int log_torus_base, int count);
@@ -138,6 +151,11 @@ void mb200_register_bootstrap_key(Bootstrap_Key key);   /* upload now (otherwise
 void mb200_release_bootstrap_key(Bootstrap_Key key);
 void mb200_register_ks_key(TLWE_KS_Key key);
 void mb200_release_ks_key(TLWE_KS_Key key);
+/* Seed-compressed rows (the reference's default A_PRNG=vaes build, keyswitch.c:231-241) are expanded at
+ * upload by calling the host's own trlwe_compressed_subto through dlsym; the AES key is process-global in
+ * the reference (rnd/aes_rng.c:88-93), so this must happen in the process that generated the key. */
+void mb200_register_generic_ks_key(Generic_KS_Key key);
+void mb200_release_generic_ks_key(Generic_KS_Key key);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Flat API.  Layouts (all little-endian u64 / f64, contiguous):
@@ -180,6 +198,26 @@ mb200_bsk_t mb200_bsk_synthesize(const mb200_params *p, const uint64_t *h_lwe_ke
 mb200_ksk_t mb200_ksk_synthesize(const mb200_params *p, const uint64_t *h_rlwe_key /* k*N, input key  */,
                                  const uint64_t *h_lwe_key  /* n, output key */,
                                  double lwe_sigma, uint64_t seed);
+
+/* trgsw_to_DFT (trgsw.c:345) for a set of p->n torus-domain TRGSW samples already on the device
+ * ([n][(k+1)l][(k+1)][N] words, e.g. the output of mb200_circuit_bootstrap_dev): returns a resident set usable
+ * with mb200_extprod_dev / mb200_cmux_dev / mb200_vertical_packing_dev / mb200_blind_rotate_dev. */
+mb200_bsk_t mb200_bsk_from_torus_dev(const mb200_params *p, const uint64_t *d_trgsw, void *stream);
+
+/* TRLWE-row key-switching keys (k = 1): host form [n_in + include_b][t][2^base_bit-1][2][N]; synthetic keys
+ * are generated on the device from binary secrets (bench / test support, replaces keyswitch.c:368-390, 611-637) */
+typedef struct mb200_gksk *mb200_gksk_t;
+mb200_gksk_t mb200_gksk_from_host(const uint64_t *h_rows, int n_in, int include_b, int N, int t, int base_bit);
+mb200_gksk_t mb200_gksk_synthesize(const uint64_t *h_in_key /* n_in */, const uint64_t *h_out_rlwe_key /* N */,
+                                   int n_in, int include_b, int N, int t, int base_bit, double sigma, uint64_t seed);
+void        *mb200_gksk_device_ptr(mb200_gksk_t k);   /* [n_in + include_b][t][2^base_bit-1][2][N] words */
+void         mb200_gksk_free(mb200_gksk_t k);
+/* trlwe_packing1_keyswitch (include_b = 0 keys) / trlwe_priv_keyswitch (include_b = 1 keys) on device buffers */
+void mb200_trlwe_ks_dev(mb200_gksk_t ksk, uint64_t *d_out_trlwe /* [count][2N] */, const uint64_t *d_in_tlwe /* [count][n_in+1] */,
+                        int count, void *stream);
+/* circuit_bootstrap_2 on device buffers: d_out_trgsw [count][2l][2][N] (rows 0..l-1 private, l..2l-1 packing) */
+void mb200_circuit_bootstrap_dev(mb200_bsk_t bsk, mb200_gksk_t kska, mb200_gksk_t kskb, uint64_t *d_out_trgsw,
+                                 const uint64_t *d_in /* [count][n+1] */, int Bg_bit_out, int count, void *stream);
 
 /* Device-resident batch ops (inputs/outputs already in HBM; asynchronous on `stream`). */
 void mb200_pbs_dev(mb200_bsk_t bsk, uint64_t *d_out_tlwe /* [count][k*N+1] */,

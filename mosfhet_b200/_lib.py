@@ -30,6 +30,14 @@ PROTOTYPES = {
     "trlwe_extract_tlwe": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
     "tlwe_keyswitch": (None, [abi.TLWE, abi.TLWE, abi.TLWE_KS_Key]),
     "multivalue_bootstrap_CLOT21": (None, [_P(abi.TLWE), abi.TRLWE, abi.TLWE, abi.Bootstrap_Key, C.c_int, C.c_int]),
+    "trlwe_packing1_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
+    "trlwe_priv_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
+    "circuit_bootstrap_2": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+    "trlwe_packing1_keyswitch_batch": (None, [_P(abi.TRLWE), _P(abi.TLWE), abi.Generic_KS_Key, C.c_int]),
+    "trlwe_priv_keyswitch_batch": (None, [_P(abi.TRLWE), _P(abi.TLWE), abi.Generic_KS_Key, C.c_int]),
+    "circuit_bootstrap_2_batch": (None, [_P(abi.TRGSW), _P(abi.TLWE), abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key, C.c_int]),
+    "mb200_register_generic_ks_key": (None, [abi.Generic_KS_Key]),
+    "mb200_release_generic_ks_key": (None, [abi.Generic_KS_Key]),
     "multivalue_bootstrap_phase1": (None, [_P(abi.TRLWE), abi.TLWE, abi.Bootstrap_Key, C.c_int]),
     "multivalue_bootstrap_phase2": (None, [abi.TLWE, _P(C.c_int), _P(abi.TRLWE), C.c_int, C.c_int]),
     # (2) batched
@@ -72,6 +80,13 @@ PROTOTYPES = {
     "mb200_ksk_free": (None, [_vp]),
     "mb200_bsk_synthesize": (_vp, [_params_p, _u64p, _u64p, C.c_double, C.c_uint64]),
     "mb200_ksk_synthesize": (_vp, [_params_p, _u64p, _u64p, C.c_double, C.c_uint64]),
+    "mb200_bsk_from_torus_dev": (_vp, [_params_p, _vp, _vp]),
+    "mb200_gksk_from_host": (_vp, [_u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mb200_gksk_synthesize": (_vp, [_u64p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64]),
+    "mb200_gksk_device_ptr": (_vp, [_vp]),
+    "mb200_gksk_free": (None, [_vp]),
+    "mb200_trlwe_ks_dev": (None, [_vp, _vp, _vp, C.c_int, _vp]),
+    "mb200_circuit_bootstrap_dev": (None, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_pbs_dev": (None, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "mb200_pbs_wo_extract_dev": (None, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "mb200_blind_rotate_dev": (None, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

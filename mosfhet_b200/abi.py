@@ -82,6 +82,11 @@ class TRGSWKeyS(C.Structure):                 # mosfhet.h:116-119
     _fields_ = [("trlwe_key", C.POINTER(TRLWEKeyS)), ("l", C.c_int), ("Bg_bit", C.c_int)]
 
 
+class GenericKSKeyS(C.Structure):             # mosfhet.h:100-103
+    _fields_ = [("s", C.POINTER(C.POINTER(C.POINTER(TRLWE)))),
+                ("base_bit", C.c_int), ("t", C.c_int), ("n", C.c_int), ("include_b", C.c_int)]
+
+
 class BootstrapKeyS(C.Structure):             # mosfhet.h:129-133
     _fields_ = [("s", C.POINTER(TRGSW_DFT)), ("su", C.POINTER(TRGSW)),
                 ("n", C.c_int), ("k", C.c_int), ("N", C.c_int), ("Bg_bit", C.c_int),
@@ -93,6 +98,7 @@ TLWE_KS_Key = C.POINTER(TLWEKSKeyS)
 TRLWE_Key = C.POINTER(TRLWEKeyS)
 TRGSW_Key = C.POINTER(TRGSWKeyS)
 Bootstrap_Key = C.POINTER(BootstrapKeyS)
+Generic_KS_Key = C.POINTER(GenericKSKeyS)
 
 
 class ParamsS(C.Structure):                   # include/mosfhet_b200.h: mb200_params
@@ -221,6 +227,44 @@ class HostKSKey:
         self._lvl0 = (C.POINTER(C.POINTER(TLWE)) * n_in)(*[C.cast(a, C.POINTER(C.POINTER(TLWE))) for a in self._lvl1])
         self.struct = TLWEKSKeyS(C.cast(self._lvl0, C.POINTER(C.POINTER(C.POINTER(TLWE)))), base_bit, t, n_in)
         self.handle = C.pointer(self.struct)
+
+
+class HostGenericKSKey:
+    """A ``Generic_KS_Key`` over a ``[n + include_b, t, 2^base_bit-1, k+1, N]`` uint64 array (uncompressed rows)."""
+
+    def __init__(self, ksk: np.ndarray, base_bit: int, include_b: int):
+        ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+        ne, t, bm1 = ksk.shape[:3]
+        self.rows = [[[HostTRLWE(ksk[i, j, d]) for d in range(bm1)] for j in range(t)] for i in range(ne)]
+        self._lvl2 = [[(TRLWE * bm1)(*[r.handle for r in self.rows[i][j]]) for j in range(t)] for i in range(ne)]
+        self._lvl1 = [(C.POINTER(TRLWE) * t)(*[C.cast(a, C.POINTER(TRLWE)) for a in self._lvl2[i]]) for i in range(ne)]
+        self._lvl0 = (C.POINTER(C.POINTER(TRLWE)) * ne)(*[C.cast(a, C.POINTER(C.POINTER(TRLWE))) for a in self._lvl1])
+        self.struct = GenericKSKeyS(C.cast(self._lvl0, C.POINTER(C.POINTER(C.POINTER(TRLWE)))), base_bit, t,
+                                    ne - include_b, include_b)
+        self.handle = C.pointer(self.struct)
+
+
+class HostTRGSW:
+    """A torus-domain ``TRGSW`` handle over a ``[(k+1)*l, (k+1), N]`` uint64 array."""
+
+    def __init__(self, rows: np.ndarray, l: int, Bg_bit: int):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        self.rows = [HostTRLWE(rows[r]) for r in range(rows.shape[0])]
+        self._samples = (TRLWE * len(self.rows))(*[r.handle for r in self.rows])
+        self.struct = TRGSWS(C.cast(self._samples, C.POINTER(TRLWE)), l, Bg_bit)
+        self.handle = C.pointer(self.struct)
+
+    def flat(self) -> np.ndarray:
+        return np.stack([r.polys for r in self.rows])
+
+
+def generic_ks_key_to_flat(h) -> np.ndarray:
+    """Uncompressed Generic_KS_Key -> [n + include_b, t, 2^base_bit-1, k+1, N]."""
+    s = h.contents
+    bm1 = (1 << s.base_bit) - 1
+    ne = s.n + s.include_b
+    return np.stack([np.stack([np.stack([trlwe_to_flat(s.s[i][j][d]) for d in range(bm1)]) for j in range(s.t)])
+                     for i in range(ne)])
 
 
 def handle_array(handles, ctype):

@@ -126,6 +126,36 @@ def multivalue_bootstrap_CLOT21(out_list, tv, in_, key, torus_base: int, n_luts:
     lib().multivalue_bootstrap_CLOT21(abi.handle_array(out_list, abi.TLWE), _h(tv), _h(in_), _h(key), torus_base, n_luts)
 
 
+def trlwe_packing1_keyswitch(out, in_, ks_key) -> None:
+    lib().trlwe_packing1_keyswitch(_h(out), _h(in_), _h(ks_key))
+
+
+def trlwe_priv_keyswitch(out, in_, ks_key) -> None:
+    lib().trlwe_priv_keyswitch(_h(out), _h(in_), _h(ks_key))
+
+
+def trlwe_packing1_keyswitch_batch(outs, ins, ks_key) -> None:
+    lib().trlwe_packing1_keyswitch_batch(abi.handle_array(outs, abi.TRLWE), abi.handle_array(ins, abi.TLWE), _h(ks_key), len(ins))
+
+
+def trlwe_priv_keyswitch_batch(outs, ins, ks_key) -> None:
+    lib().trlwe_priv_keyswitch_batch(abi.handle_array(outs, abi.TRLWE), abi.handle_array(ins, abi.TLWE), _h(ks_key), len(ins))
+
+
+def circuit_bootstrap_2(out, in_, key, kska, kskb) -> None:
+    """TLWE -> torus-domain TRGSW (bootstrap.c:324-345)."""
+    lib().circuit_bootstrap_2(_h(out), _h(in_), _h(key), _h(kska), _h(kskb))
+
+
+def circuit_bootstrap_2_batch(outs, ins, key, kska, kskb) -> None:
+    lib().circuit_bootstrap_2_batch(abi.handle_array(outs, abi.TRGSW), abi.handle_array(ins, abi.TLWE), _h(key),
+                                    _h(kska), _h(kskb), len(ins))
+
+
+def release_generic_ks_key(key) -> None:
+    lib().mb200_release_generic_ks_key(_h(key))
+
+
 def multivalue_bootstrap_phase1(out_list, in_, key, torus_base: int) -> None:
     """out_list: torus_base + 1 TRLWEs (bootstrap.c:232-243)."""
     lib().multivalue_bootstrap_phase1(abi.handle_array(out_list, abi.TRLWE), _h(in_), _h(key), torus_base)
@@ -256,6 +286,12 @@ class BootstrapKey:
         return cls(params, h)
 
     @classmethod
+    def from_torus_dev(cls, params: Params, d_trgsw, stream=None) -> "BootstrapKey":
+        """trgsw_to_DFT (trgsw.c:345) of ``params.n`` torus-domain TRGSW samples held in device memory."""
+        p = params.c()
+        return cls(params, lib().mb200_bsk_from_torus_dev(C.byref(p), _ptr(d_trgsw), _ptr(stream)))
+
+    @classmethod
     def adopt(cls, params: Params, device_buffer) -> "BootstrapKey":
         """Wrap caller-owned device memory already in the resident layout (e.g. an NCCL receive buffer)."""
         p = params.c()
@@ -320,6 +356,52 @@ class KeySwitchKey:
         if self.handle:
             lib().mb200_ksk_free(self.handle)
             self.handle = None
+
+
+class GenericKSKey:
+    """TRLWE-row key-switching key resident in HBM (``mb200_gksk_t``; k = 1)."""
+
+    def __init__(self, handle, n_in, include_b, N, t, base_bit):
+        self.handle, self.n_in, self.include_b, self.N, self.t, self.base_bit = handle, n_in, include_b, N, t, base_bit
+
+    @classmethod
+    def from_host(cls, rows: np.ndarray, include_b: int, base_bit: int) -> "GenericKSKey":
+        rows = np.ascontiguousarray(rows, np.uint64)
+        ne, t, _, kp1, N = rows.shape
+        assert kp1 == 2
+        h = lib().mb200_gksk_from_host(rows.ctypes.data_as(C.POINTER(C.c_uint64)), ne - include_b, include_b, N, t, base_bit)
+        return cls(h, ne - include_b, include_b, N, t, base_bit)
+
+    @classmethod
+    def synthesize(cls, in_key, out_rlwe_key, include_b, t, base_bit, sigma, seed=5) -> "GenericKSKey":
+        in_key = np.ascontiguousarray(in_key, np.uint64)
+        out_rlwe_key = np.ascontiguousarray(out_rlwe_key, np.uint64).reshape(-1)
+        u = C.POINTER(C.c_uint64)
+        h = lib().mb200_gksk_synthesize(in_key.ctypes.data_as(u), out_rlwe_key.ctypes.data_as(u), in_key.shape[0],
+                                        include_b, out_rlwe_key.shape[0], t, base_bit, sigma, seed)
+        return cls(h, in_key.shape[0], include_b, out_rlwe_key.shape[0], t, base_bit)
+
+    @property
+    def device_ptr(self) -> int:
+        return int(lib().mb200_gksk_device_ptr(self.handle))
+
+    @property
+    def shape(self):
+        return (self.n_in + self.include_b, self.t, (1 << self.base_bit) - 1, 2, self.N)
+
+    def free(self) -> None:
+        if self.handle:
+            lib().mb200_gksk_free(self.handle)
+            self.handle = None
+
+
+def trlwe_ks_dev(ksk: GenericKSKey, d_out, d_in, count, stream=None):
+    lib().mb200_trlwe_ks_dev(ksk.handle, _ptr(d_out), _ptr(d_in), count, _ptr(stream))
+
+
+def circuit_bootstrap_dev(bsk, kska, kskb, d_out_trgsw, d_in, Bg_bit_out, count, stream=None):
+    lib().mb200_circuit_bootstrap_dev(bsk.handle, kska.handle, kskb.handle, _ptr(d_out_trgsw), _ptr(d_in), Bg_bit_out,
+                                      count, _ptr(stream))
 
 
 # ---- host-buffer batches (numpy or pinned torch tensors in, numpy out) ------------------------

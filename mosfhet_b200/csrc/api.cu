@@ -35,6 +35,11 @@ int g_policy = 0;
 std::string g_last_kernel = "none";
 std::map<const void *, mb200_bsk *> g_bsk_cache;   // keyed by Bootstrap_Key->s (the TRGSW_DFT array)
 std::map<const void *, mb200_ksk *> g_ksk_cache;   // keyed by TLWE_KS_Key->s
+struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; };
+}  // namespace
+struct mb200_gksk : GkskDev {};
+namespace {
+std::map<const void *, GkskDev *> g_gksk_cache;    // keyed by Generic_KS_Key->s
 
 mb::Params to_params(const mb200_params *p) {
   mb::Params q;
@@ -78,7 +83,7 @@ struct Scratch {
     h = d = nullptr; hcap = dcap = 0;
   }
 };
-enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_COUNT };
+enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_COUNT };
 thread_local Scratch t_scratch[S_COUNT];
 
 // ---- host FFT slot order ----------------------------------------------------------------------
@@ -268,6 +273,72 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
   return k;
 }
 
+// Generic (TRLWE-row) key-switching key: u64 [n + include_b][t][2^base_bit-1][(k+1)*N]
+GkskDev *lookup_gksk(Generic_KS_Key key) {
+  MB_REQUIRE(key != nullptr, "Generic_KS_Key is NULL");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_gksk_cache.find((const void *)key->s);
+    if (it != g_gksk_cache.end()) return it->second;
+  }
+  mb::ensure_init();
+  GkskDev *g = new GkskDev();
+  TRLWE r0 = key->s[0][0][0];
+  g->k = r0->k; g->N = r0->b->N; g->t = key->t; g->base_bit = key->base_bit; g->n_in = key->n; g->include_b = key->include_b;
+  g->n_entries = key->n + key->include_b;
+  MB_REQUIRE(g->k == 1 || r0->a[0]->N == g->N, "compressed TRLWE rows exist for k = 1 only");
+  const int bm1 = (1 << g->base_bit) - 1, N = g->N, W = (g->k + 1) * N;
+  MB_REQUIRE(W % 64 == 0, "generic key switch: (k+1)*N = %d must be a multiple of 64", W);
+  const bool compressed = r0->a[0]->N != N;          // 16-byte seed instead of N words (trlwe_compressed_vaes.c:23-31)
+  typedef void (*subto_t)(TRLWE, TRLWE);
+  subto_t expand = nullptr;
+  struct _TorusPolynomial pa, pb;
+  TorusPolynomial pap = &pa;
+  struct _TRLWE tmp;
+  void *bufa = nullptr, *bufb = nullptr;
+  if (compressed) {
+    expand = (subto_t)dlsym(RTLD_DEFAULT, "trlwe_compressed_subto");
+    MB_REQUIRE(expand != nullptr, "Generic_KS_Key rows are seed-compressed and the host's trlwe_compressed_subto is not "
+                                  "resolvable in this process: cannot expand them");
+    MB_REQUIRE(!posix_memalign(&bufa, 64, sizeof(u64) * N) && !posix_memalign(&bufb, 64, sizeof(u64) * N), "out of memory");
+    pa.coeffs = (Torus *)bufa; pa.N = N; pb.coeffs = (Torus *)bufb; pb.N = N;
+    tmp.a = &pap; tmp.b = &pb; tmp.k = 1;
+  }
+  const size_t rows = (size_t)g->n_entries * g->t * bm1;
+  std::vector<u64> flat(rows * W);
+  size_t o = 0;
+  for (int i = 0; i < g->n_entries; ++i)
+    for (int j = 0; j < g->t; ++j)
+      for (int d = 0; d < bm1; ++d) {
+        TRLWE row = key->s[i][j][d];
+        if (compressed) {
+          memset(bufa, 0, sizeof(u64) * N); memset(bufb, 0, sizeof(u64) * N);
+          expand(&tmp, row);                                    // tmp = 0 - row  (exact)
+          for (int c = 0; c < N; ++c) { flat[o + c] = 0ull - pa.coeffs[c]; flat[o + N + c] = 0ull - pb.coeffs[c]; }
+        } else {
+          for (int q = 0; q < g->k; ++q) memcpy(&flat[o + (size_t)q * N], row->a[q]->coeffs, sizeof(u64) * N);
+          memcpy(&flat[o + (size_t)g->k * N], row->b->coeffs, sizeof(u64) * N);
+        }
+        o += W;
+      }
+  free(bufa); free(bufb);
+  cudaStream_t st = mb::default_stream();
+  MB_CHECK(cudaMalloc(&g->d, sizeof(u64) * flat.size()));
+  MB_CHECK(cudaMemcpyAsync(g->d, flat.data(), sizeof(u64) * flat.size(), cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_gksk_cache[(const void *)key->s] = g;
+  return g;
+}
+
+// mode 0: trlwe_packing1_keyswitch (b[0] += in.b, n entries); mode 1: trlwe_priv_keyswitch (n+1 entries)
+void table_ks_trlwe_dev(GkskDev *g, int mode, u64 *d_out, const u64 *d_in, int count, cudaStream_t st) {
+  const int W = (g->k + 1) * g->N;
+  MB_REQUIRE((mode == 1) == (g->include_b == 1), "Generic_KS_Key include_b=%d does not match the key switch requested", g->include_b);
+  mb::launch_table_keyswitch(g->d, W, g->n_entries, g->t, g->base_bit, d_out, W, W, mode == 0 ? g->k * g->N : -1, d_in,
+                             g->n_in + 1, g->n_in, count, st);
+}
+
 // ---- dispatch ----------------------------------------------------------------------------------
 void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   if (a.count <= 0) return;
@@ -375,8 +446,10 @@ void mb200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto &kv : g_bsk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
   for (auto &kv : g_ksk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
+  for (auto &kv : g_gksk_cache) { cudaFree(kv.second->d); delete kv.second; }
   g_bsk_cache.clear();
   g_ksk_cache.clear();
+  g_gksk_cache.clear();
   for (auto &kv : g_dft_maps) cudaFree(kv.second.stored_to_host);
   g_dft_maps.clear();
   for (int i = 0; i < S_COUNT; ++i) t_scratch[i].release();
@@ -455,6 +528,17 @@ void mb200_ksk_free(mb200_ksk_t ksk) {
   delete ksk;
 }
 
+mb200_bsk_t mb200_bsk_from_torus_dev(const mb200_params *p, const uint64_t *d_trgsw, void *stream) {
+  mb200_bsk *b = bsk_alloc(to_params(p));
+  cudaStream_t st = as_stream(stream);
+  const size_t npolys = (size_t)b->p.n * (b->p.k + 1) * b->p.l * (b->p.k + 1);
+  double *d_dft = nullptr;
+  MB_CHECK(cudaMalloc(&d_dft, sizeof(double) * npolys * b->p.N));
+  mb::bsk_from_torus(b, (const u64 *)d_trgsw, d_dft, st);
+  MB_CHECK(cudaStreamSynchronize(st));
+  MB_CHECK(cudaFree(d_dft));
+  return b;
+}
 mb200_bsk_t mb200_bsk_synthesize(const mb200_params *p, const uint64_t *h_lwe_key, const uint64_t *h_rlwe_key,
                                  double rlwe_sigma, uint64_t seed) {
   mb200_bsk *b = bsk_alloc(to_params(p));
@@ -899,6 +983,117 @@ void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLW
   scatter_tlwe(out, h_out, count, k * N);
 }
 
+static void trlwe_table_ks_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count, int mode) {
+  if (count <= 0) return;
+  GkskDev *g = lookup_gksk(ks_key);
+  cudaStream_t st = mb::default_stream();
+  const int W = (g->k + 1) * g->N;
+  const size_t in_b = sizeof(u64) * (size_t)count * (g->n_in + 1), out_b = sizeof(u64) * (size_t)count * W;
+  u64 *h_in = (u64 *)t_scratch[S_MID].host(in_b), *d_in = (u64 *)t_scratch[S_MID].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_tlwe(h_in, in, count, g->n_in);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  table_ks_trlwe_dev(g, mode, d_out, d_in, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(out, h_out, count, g->k, g->N);     // asserts out->k / out->b->N as keyswitch.c:462-463
+}
+void trlwe_packing1_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count) { trlwe_table_ks_batch(out, in, ks_key, count, 0); }
+void trlwe_priv_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count) { trlwe_table_ks_batch(out, in, ks_key, count, 1); }
+
+// device-side core of circuit_bootstrap_2 (shared by the handle and the flat entry points)
+static void circuit_bootstrap_core(mb200_bsk *bsk, GkskDev *ga, GkskDev *gb, u64 *d_out, const u64 *d_in, int Bgo,
+                                   int count, cudaStream_t st) {
+  const mb::Params &p = bsk->p;
+  const int lo = p.l;
+  MB_REQUIRE(p.k == 1, "circuit bootstrap: k = 1 only");
+  MB_REQUIRE(ga->n_in == p.k * p.N && gb->n_in == p.k * p.N, "circuit bootstrap: key switch input dimension mismatch");
+  MB_REQUIRE(ga->N == gb->N && ga->k == gb->k, "circuit bootstrap: the two key switches must target the same TRLWE shape");
+  const size_t W = (size_t)(p.k + 1) * p.N, Wo = (size_t)(ga->k + 1) * ga->N;
+  const size_t tv_b = sizeof(u64) * W;
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  // trlwe_torus_packing(tv, lut, 2l) with lut[i] = 0, lut[l+i] = 2^(64-(i+1)*Bg_out)  (bootstrap.c:330-334)
+  memset(h_tv, 0, tv_b);
+  const int slot = p.N / (2 * lo);
+  for (int i = 0; i < p.N; ++i) {
+    const int s_ = i / slot;
+    h_tv[(size_t)p.k * p.N + i] = (s_ >= lo && s_ < 2 * lo) ? (1ull << (64 - (s_ - lo + 1) * Bgo)) : 0ull;
+  }
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  u64 *d_acc = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * count * W);
+  pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, 2 * p.l, count, st);
+  std::vector<int> idx(lo);
+  for (int i = 0; i < lo; ++i) idx[i] = i * slot;
+  const int n_tl = count * lo;                                   // TLWEs [count][l][kN+1]
+  u64 *d_tl = (u64 *)t_scratch[S_MISC].dev(sizeof(u64) * (size_t)n_tl * (p.k * p.N + 1));
+  mb200_extract_dev((uint64_t *)d_tl, (const uint64_t *)d_acc, idx.data(), lo, p.N, p.k, count, st);
+  // key switches write straight into the TRGSW layout [count][2l][Wo]: private rows first, packing rows after
+  // -> two strided passes: outputs of ciphertext c, level i at ((c*2l) + i) and ((c*2l) + l + i)
+  u64 *d_ks = (u64 *)t_scratch[S_KS].dev(sizeof(u64) * (size_t)2 * n_tl * Wo);
+  table_ks_trlwe_dev(ga, 1, d_ks, d_tl, n_tl, st);                           // trlwe_priv_keyswitch     -> samples[i]
+  table_ks_trlwe_dev(gb, 0, d_ks + (size_t)n_tl * Wo, d_tl, n_tl, st);       // trlwe_packing1_keyswitch -> samples[l+i]
+  for (int half = 0; half < 2; ++half)
+    MB_CHECK(cudaMemcpy2DAsync(d_out + (size_t)half * lo * Wo, sizeof(u64) * 2 * lo * Wo,
+                               d_ks + (size_t)half * n_tl * Wo, sizeof(u64) * lo * Wo, sizeof(u64) * lo * Wo, count,
+                               cudaMemcpyDeviceToDevice, st));
+}
+
+/* circuit_bootstrap_2 (bootstrap.c:324-345): one blind rotation of the packed test vector
+ * (0,..,0, h_0,..,h_{l-1}), l extractions at i*N/(2l), then per level the private key switch (rows 0..l-1
+ * of the TRGSW) and the packing key switch (rows l..2l-1). */
+void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  GkskDev *ga = lookup_gksk(kska), *gb = lookup_gksk(kskb);
+  const mb::Params &p = bsk->p;
+  const int lo = out[0]->l, Bgo = out[0]->Bg_bit;
+  MB_REQUIRE(lo == p.l, "circuit_bootstrap_2: needs out->l == key->l (the reference indexes the LUT with both)");
+  cudaStream_t st = mb::default_stream();
+  const size_t Wo = (size_t)(ga->k + 1) * ga->N;
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), out_b = sizeof(u64) * (size_t)count * 2 * lo * Wo;
+  u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_tlwe(h_in, in, count, p.n);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  circuit_bootstrap_core(bsk, ga, gb, d_out, d_in, Bgo, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int c = 0; c < count; ++c) scatter_trlwe(out[c]->samples, h_out + (size_t)c * 2 * lo * Wo, 2 * lo, ga->k, ga->N);
+}
+
+mb200_gksk_t mb200_gksk_from_host(const uint64_t *h_rows, int n_in, int include_b, int N, int t, int base_bit) {
+  mb::ensure_init();
+  mb200_gksk *g = new mb200_gksk();
+  g->k = 1; g->N = N; g->t = t; g->base_bit = base_bit; g->n_in = n_in; g->include_b = include_b; g->n_entries = n_in + include_b;
+  const size_t words = (size_t)g->n_entries * t * ((1 << base_bit) - 1) * 2 * N;
+  cudaStream_t st = mb::default_stream();
+  MB_CHECK(cudaMalloc(&g->d, sizeof(u64) * words));
+  MB_CHECK(cudaMemcpyAsync(g->d, h_rows, sizeof(u64) * words, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  return g;
+}
+mb200_gksk_t mb200_gksk_synthesize(const uint64_t *h_in_key, const uint64_t *h_out_rlwe_key, int n_in, int include_b, int N,
+                                   int t, int base_bit, double sigma, uint64_t seed) {
+  mb::ensure_init();
+  mb200_gksk *g = new mb200_gksk();
+  g->k = 1; g->N = N; g->t = t; g->base_bit = base_bit; g->n_in = n_in; g->include_b = include_b; g->n_entries = n_in + include_b;
+  const size_t words = (size_t)g->n_entries * t * ((1 << base_bit) - 1) * 2 * N;
+  MB_CHECK(cudaMalloc(&g->d, sizeof(u64) * words));
+  mb::synth_gksk(g->d, (const u64 *)h_in_key, (const u64 *)h_out_rlwe_key, n_in, include_b, N, t, base_bit, sigma, seed,
+                 mb::default_stream());
+  return g;
+}
+void *mb200_gksk_device_ptr(mb200_gksk_t k) { return k->d; }
+void mb200_gksk_free(mb200_gksk_t k) { if (!k) return; cudaFree(k->d); delete k; }
+void mb200_trlwe_ks_dev(mb200_gksk_t ksk, uint64_t *d_out, const uint64_t *d_in, int count, void *stream) {
+  table_ks_trlwe_dev(ksk, ksk->include_b, (u64 *)d_out, (const u64 *)d_in, count, as_stream(stream));
+}
+void mb200_circuit_bootstrap_dev(mb200_bsk_t bsk, mb200_gksk_t kska, mb200_gksk_t kskb, uint64_t *d_out_trgsw,
+                                 const uint64_t *d_in, int Bg_bit_out, int count, void *stream) {
+  if (count <= 0) return;
+  circuit_bootstrap_core(bsk, kska, kskb, (u64 *)d_out_trgsw, (const u64 *)d_in, Bg_bit_out, count, as_stream(stream));
+}
+
 // ---- drop-in single-ciphertext entry points (reference names) ------------------------------------------
 void functional_bootstrap(TLWE out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base) {
   functional_bootstrap_batch(&out, &tv, 1, &in, key, torus_base, 1);
@@ -916,6 +1111,20 @@ void trlwe_extract_tlwe(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_batch(
 void tlwe_keyswitch(TLWE out, TLWE in, TLWE_KS_Key ks_key) { tlwe_keyswitch_batch(&out, &in, ks_key, 1); }
 void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key, int torus_base, int n_luts) {
   multivalue_bootstrap_CLOT21_batch(&out, &tv, 1, &in, key, torus_base, n_luts, 1);
+}
+void trlwe_packing1_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key) { trlwe_packing1_keyswitch_batch(&out, &in, ks_key, 1); }
+void trlwe_priv_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key) { trlwe_priv_keyswitch_batch(&out, &in, ks_key, 1); }
+void circuit_bootstrap_2(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb) {
+  circuit_bootstrap_2_batch(&out, &in, key, kska, kskb, 1);
+}
+void mb200_register_generic_ks_key(Generic_KS_Key key) { (void)lookup_gksk(key); }
+void mb200_release_generic_ks_key(Generic_KS_Key key) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_gksk_cache.find((const void *)key->s);
+  if (it == g_gksk_cache.end()) return;
+  cudaFree(it->second->d);
+  delete it->second;
+  g_gksk_cache.erase(it);
 }
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base) {
   multivalue_bootstrap_phase1_batch(&out, &in, key, torus_base, 1);

@@ -105,6 +105,9 @@ void launch_blind_rotate_k1h(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1h_variant_name(const Params &p);
 
 void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st);
+void launch_table_keyswitch(const u64 *table, int row_stride, int n_entries, int t, int base_bit, u64 *out,
+                            int out_words, int out_stride, int b_index, const u64 *in, int in_stride, int b_word,
+                            int count, cudaStream_t st);
 void launch_extract(u64 *out, const u64 *trlwe, const int *d_idx, int idx_count, int N, int k, int count,
                     cudaStream_t st);
 void launch_torus_to_dft(double *out, const u64 *in, int N, int count, cudaStream_t st);
@@ -121,6 +124,9 @@ void import_bsk(BskDev *dst, const double *d_host_layout /* device copy of the h
                 cudaStream_t st);
 void synth_bsk(BskDev *dst, const u64 *h_lwe_key, const u64 *h_rlwe_key, double sigma, u64 seed, cudaStream_t st);
 void synth_ksk(KskDev *dst, const u64 *h_in_key, const u64 *h_out_key, double sigma, u64 seed, cudaStream_t st);
+void bsk_from_torus(BskDev *dst, const u64 *d_torus, double *d_dft, cudaStream_t st);
+void synth_gksk(u64 *d_out, const u64 *h_in_key, const u64 *h_out_key, int n_in, int include_b, int N, int t,
+                int base_bit, double sigma, u64 seed, cudaStream_t st);
 void host_slot_exponents(int layout, int N, int32_t *e);
 // host slot h -> (internal stored index, conj flag); used by import and by the DFT-boundary ops
 void slot_maps(int N, const int32_t *e, int *stored_to_host /* M */, int *stored_conj /* M */);

@@ -149,6 +149,17 @@ __global__ void tile_bsk_kernel(double2 *dst, const double *src, int N, size_t n
   }
 }
 
+// torus-domain TRGSW samples [n][(k+1)l][(k+1)][N] on the device -> resident Fourier layout (trgsw_to_DFT,
+// trgsw.c:345, for a whole set at once); d_dft is caller scratch of npolys*N doubles
+void bsk_from_torus(BskDev *dst, const u64 *d_torus, double *d_dft, cudaStream_t st) {
+  const Params &p = dst->p;
+  const size_t npolys = (size_t)p.n * (p.k + 1) * p.l * (p.k + 1);
+  launch_torus_to_dft(d_dft, d_torus, p.N, (int)npolys, st);
+  tile_bsk_kernel<<<sm_count() * 8, 256, 0, st>>>(dst->d, d_dft, p.N, npolys);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
 void synth_bsk(BskDev *dst, const u64 *h_lwe_key, const u64 *h_rlwe_key, double sigma, u64 seed, cudaStream_t st) {
   const Params &p = dst->p;
   MB_REQUIRE(p.N >= 16, "synth_bsk: N too small");
@@ -167,12 +178,56 @@ void synth_bsk(BskDev *dst, const u64 *h_lwe_key, const u64 *h_rlwe_key, double 
   synth_trgsw_rows_kernel<<<(unsigned)rows_total, 256, smem, st>>>(d_torus, d_lwe, d_rlwe, p.N, p.k, p.l, p.Bg_bit, sigma, seed);
   MB_CHECK(cudaGetLastError());
   count_launch();
-  launch_torus_to_dft(d_dft, d_torus, p.N, (int)npolys, st);
-  tile_bsk_kernel<<<sm_count() * 8, 256, 0, st>>>(dst->d, d_dft, p.N, npolys);
+  bsk_from_torus(dst, d_torus, d_dft, st);
+  MB_CHECK(cudaStreamSynchronize(st));
+  cudaFree(d_lwe); cudaFree(d_rlwe); cudaFree(d_torus); cudaFree(d_dft);
+}
+
+// ---- synthetic TRLWE-row key-switching keys (circuit bootstrap; k = 1) ------------------------------------
+// One CTA per row [i][j][d-1], i < n_in + include_b:  a uniform, b = a*s_out + e + msg  with
+//   packing1 (include_b = 0): msg = s_in[i]*d*2^(64-(j+1)b) at coefficient 0   (keyswitch.c:368-390)
+//   private  (include_b = 1): msg = (-s_out) * (s_i*d*2^(64-(j+1)b)), s_i = s_in[i] or -1 for the b entry (:611-637)
+__global__ void synth_gksk_kernel(u64 *out, const u64 *in_key, const u64 *out_key, int n_in, int include_b, int N,
+                                  int t, int base_bit, double sigma, u64 seed) {
+  extern __shared__ u64 sm[];
+  u64 *sa = sm, *ss = sm + N;
+  const int bm1 = (1 << base_bit) - 1;
+  const size_t row = blockIdx.x;
+  const int d = (int)(row % bm1) + 1, j = (int)((row / bm1) % t), i = (int)(row / ((size_t)bm1 * t));
+  u64 *o = out + row * 2 * N;
+  const int T = blockDim.x;
+  const u64 s_i = i < n_in ? in_key[i] : ~0ull;                       // -1 for the b entry
+  const u64 dec_key = s_i * (u64)d * (1ull << (64 - (j + 1) * base_bit));
+  for (int c = threadIdx.x; c < N; c += T) {
+    const u64 v = splitmix64(seed + 0x6b6bull + (row * (u64)N + c) * 0x9E3779B97F4A7C15ull);
+    sa[c] = v; ss[c] = out_key[c]; o[c] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += T) {
+    u64 acc = (u64)(i64)(gaussian(seed ^ 0x99ull, row * N + c, sigma) * 18446744073709551616.0);
+    for (int q = 0; q < N; ++q)
+      if (ss[q]) { const int src = c - q; acc += (src >= 0) ? sa[src] : (0ull - sa[src + N]); }
+    if (include_b) acc += (0ull - ss[c]) * dec_key;
+    else if (c == 0) acc += dec_key;
+    o[N + c] = acc;
+  }
+}
+
+void synth_gksk(u64 *d_out, const u64 *h_in_key, const u64 *h_out_key, int n_in, int include_b, int N, int t,
+                int base_bit, double sigma, u64 seed, cudaStream_t st) {
+  u64 *d_in, *d_ok;
+  MB_CHECK(cudaMalloc(&d_in, sizeof(u64) * n_in));
+  MB_CHECK(cudaMalloc(&d_ok, sizeof(u64) * N));
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in_key, sizeof(u64) * n_in, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_ok, h_out_key, sizeof(u64) * N, cudaMemcpyHostToDevice, st));
+  const size_t rows = (size_t)(n_in + include_b) * t * ((1 << base_bit) - 1);
+  const size_t smem = sizeof(u64) * 2 * N;
+  if (smem > 48 * 1024) MB_CHECK(cudaFuncSetAttribute(synth_gksk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  synth_gksk_kernel<<<(unsigned)rows, 256, smem, st>>>(d_out, d_in, d_ok, n_in, include_b, N, t, base_bit, sigma, seed);
   MB_CHECK(cudaGetLastError());
   count_launch();
   MB_CHECK(cudaStreamSynchronize(st));
-  cudaFree(d_lwe); cudaFree(d_rlwe); cudaFree(d_torus); cudaFree(d_dft);
+  cudaFree(d_in); cudaFree(d_ok);
 }
 
 // ---- synthetic key-switching table -------------------------------------------------------------------

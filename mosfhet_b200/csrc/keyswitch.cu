@@ -28,31 +28,51 @@ __device__ __forceinline__ ulonglong2 ldg_u128(const u64 *p) {
   return v;
 }
 
-// `slices` > 1 (small batches): the sweep over the input coefficients of one ciphertext is split over
-// `slices` warps (in different CTAs), each adding its partial sum into the zero-initialised output with
-// 64-bit integer atomics -- still exact and order independent.
+// The same kernel serves every table key switch of the reference:
+//   tlwe_keyswitch (tlwe.c:289)            rows = TLWE(n) padded to 64 words, b added at word n
+//   trlwe_packing1_keyswitch (keyswitch.c:458) rows = TRLWE (k+1)*N words, in.b added at word k*N (b[0])
+//   trlwe_priv_keyswitch (keyswitch.c:639)  same rows, n+1 input entries (the last one is in.b), nothing added
+// A warp handles one (ciphertext, input slice, column chunk): `chunks` > 1 splits rows wider than 1024
+// words over several warps; `slices` > 1 (small batches) splits the sweep over the input coefficients,
+// the partial sums being added into the zero-initialised output with 64-bit integer atomics -- exact
+// and order independent either way.
+struct TableKsArgs {
+  u64 *out;
+  const u64 *in;
+  const u64 *table;
+  int count;
+  int n_entries;      // input words swept (n_in, or n_in + 1 when the key has an entry for b)
+  int in_stride;      // words between consecutive input TLWEs (n_in + 1)
+  int b_word;         // index of b in the input TLWE (n_in)
+  int out_words;      // valid output words per ciphertext
+  int out_stride;
+  int b_index;        // output word that receives + in.b, or -1
+  int t, base_bit, row_stride;
+  int per_cta, slices, i_per, chunks;
+};
+
 template <int NV>
-__global__ void __launch_bounds__(KS_MAX_WARPS * 32, 1)
-keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u64 *__restrict__ ksk, int count,
-                      int n_in, int n_out, int t, int base_bit, int row_stride, int cts_per_cta, int slices,
-                      int i_per) {
+__global__ void __launch_bounds__(KS_MAX_WARPS * 32, 1) keyswitch_warp_kernel(TableKsArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vct = blockIdx.x * cts_per_cta + warp;          // (ciphertext, slice) pair
-  const int ct = vct / slices, sl = vct - ct * slices;
-  const bool live = warp < cts_per_cta && ct < count;
+  const int vct = blockIdx.x * A.per_cta + warp;             // (ciphertext, slice, chunk)
+  const int ch = vct % A.chunks, cs = vct / A.chunks;
+  const int ct = cs / A.slices, sl = cs - ct * A.slices;
+  const bool live = warp < A.per_cta && ct < A.count;
+  const int t = A.t, base_bit = A.base_bit, row_stride = A.row_stride;
   const int bm1 = (1 << base_bit) - 1;
   const u64 prec_offset = 1ull << (64 - (1 + base_bit * t));
-  const u64 *a = in + (size_t)(live ? ct : 0) * (n_in + 1);
-  const int i_begin = sl * i_per, i_end = min(n_in, i_begin + i_per);
+  const u64 *a = A.in + (size_t)(live ? ct : 0) * A.in_stride;
+  const int i_begin = sl * A.i_per, i_end = min(A.n_entries, i_begin + A.i_per);
+  const u64 *__restrict__ ksk = A.table + (size_t)ch * (64 * NV);
 
   u64 acc[2 * NV];
 #pragma unroll
   for (int q = 0; q < 2 * NV; ++q) acc[q] = 0ull;
 
-  for (int i0 = i_begin; i0 < i_begin + i_per; i0 += 32) {   // same trip count for every warp (block barriers inside)
+  for (int i0 = i_begin; i0 < i_begin + A.i_per; i0 += 32) { // same trip count for every warp (block barriers inside)
     const int i_mine = i0 + lane;
     const u64 a_mine = (live && i_mine < i_end) ? a[i_mine] + prec_offset : 0ull;   // tlwe.c:297
-    const int ni = min(32, i_begin + i_per - i0);
+    const int ni = min(32, i_begin + A.i_per - i0);
     for (int il = 0; il < ni; ++il) {
       const u64 ai = __shfl_sync(0xffffffffu, a_mine, il);
       const bool valid = live && (i0 + il) < i_end;
@@ -77,17 +97,16 @@ keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u
     }
   }
   if (live) {
-    u64 *o = out + (size_t)ct * (n_out + 1);
-    const u64 b = (sl == 0) ? a[n_in] : 0ull;
+    u64 *o = A.out + (size_t)ct * A.out_stride;
+    const u64 b = (sl == 0 && A.b_index >= 0) ? a[A.b_word] : 0ull;
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-      const int c = 2 * (lane + 32 * q);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int cc = c + h;
-        if (cc > n_out) continue;
-        const u64 v = acc[2 * q + h] + (cc == n_out ? b : 0ull);
-        if (slices == 1) o[cc] = v;
+        const int cc = ch * (64 * NV) + 2 * (lane + 32 * q) + h;
+        if (cc >= A.out_words) continue;
+        const u64 v = acc[2 * q + h] + (cc == A.b_index ? b : 0ull);
+        if (A.slices == 1) o[cc] = v;
         else atomicAdd(&o[cc], v);
       }
     }
@@ -95,25 +114,26 @@ keyswitch_warp_kernel(u64 *__restrict__ out, const u64 *__restrict__ in, const u
 }
 
 template <int NV>
-static void launch_ks_nv(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
-  const Params &p = ksk->p;
-  const int sms = sm_count(), n_in = p.k * p.N;
+static void launch_ks_nv(TableKsArgs A, cudaStream_t st) {
+  const int sms = sm_count();
+  const int work = A.count * A.chunks;
   // small batches: split each ciphertext's sweep so that about 8 warps per SM are busy
   int slices = 1;
-  if (count < 4 * sms) {
-    slices = (8 * sms + count - 1) / count;
-    const int max_slices = (n_in + 31) / 32;
+  if (work < 4 * sms) {
+    slices = (8 * sms + work - 1) / work;
+    const int max_slices = (A.n_entries + 31) / 32;
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
   }
-  const int i_per = (((n_in + slices - 1) / slices) + 31) & ~31;
-  slices = (n_in + i_per - 1) / i_per;
-  const int vcount = count * slices;
+  A.i_per = (((A.n_entries + slices - 1) / slices) + 31) & ~31;
+  A.slices = (A.n_entries + A.i_per - 1) / A.i_per;
+  const int vcount = work * A.slices;
   // one CTA per SM when the batch allows; as few waves as possible otherwise
   int waves = (vcount + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
   int per = (vcount + sms * waves - 1) / (sms * waves);
   if (per < 1) per = 1;
   if (per > KS_MAX_WARPS) per = KS_MAX_WARPS;
+  A.per_cta = per;
   const int grid = (vcount + per - 1) / per;
   static bool configured = false;
   if (!configured) {
@@ -121,27 +141,48 @@ static void launch_ks_nv(const KskDev *ksk, u64 *out, const u64 *in, int count, 
     MB_CHECK(cudaFuncSetAttribute(keyswitch_warp_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     configured = true;
   }
-  if (slices > 1) MB_CHECK(cudaMemsetAsync(out, 0, sizeof(u64) * (size_t)count * (p.n + 1), st));
-  keyswitch_warp_kernel<NV><<<grid, per * 32, 0, st>>>(out, in, ksk->d, count, n_in, p.n, p.t, p.base_bit,
-                                                     ksk->row_stride, per, slices, i_per);
+  if (A.slices > 1) {
+    MB_CHECK(cudaMemset2DAsync(A.out, sizeof(u64) * A.out_stride, 0, sizeof(u64) * A.out_words, A.count, st));
+  }
+  keyswitch_warp_kernel<NV><<<grid, per * 32, 0, st>>>(A);
   MB_CHECK(cudaGetLastError());
   count_launch();
+}
+
+// table: [n_entries][t][2^base_bit-1][row_stride]; row_stride a multiple of 64 words
+void launch_table_keyswitch(const u64 *table, int row_stride, int n_entries, int t, int base_bit, u64 *out,
+                            int out_words, int out_stride, int b_index, const u64 *in, int in_stride, int b_word,
+                            int count, cudaStream_t st) {
+  MB_REQUIRE(base_bit >= 1 && base_bit <= 8, "keyswitch: base_bit=%d unsupported (1..8)", base_bit);
+  MB_REQUIRE(t >= 1 && t * base_bit < 64, "keyswitch: t*base_bit must be < 64");
+  MB_REQUIRE(row_stride % 64 == 0, "keyswitch: resident rows must be padded to 64 words");
+  if (count <= 0) return;
+  TableKsArgs A;
+  A.out = out; A.in = in; A.table = table; A.count = count; A.n_entries = n_entries; A.in_stride = in_stride;
+  A.b_word = b_word; A.out_words = out_words; A.out_stride = out_stride; A.b_index = b_index;
+  A.t = t; A.base_bit = base_bit; A.row_stride = row_stride;
+  int nv = row_stride / 64;
+  A.chunks = 1;
+  if (nv > 10 && nv % 8 == 0) {                    // wide (TRLWE) rows: 512-word column chunks, 16 accumulators per lane
+    A.chunks = nv / 8;
+    nv = 8;
+  }
+  MB_REQUIRE(nv <= 16, "keyswitch: row stride %d unsupported (above 1024 words it must be a multiple of 512)", row_stride);
+  switch (nv) {
+#define MB_KS_CASE(NV_) case NV_: launch_ks_nv<NV_>(A, st); break;
+    MB_KS_CASE(1) MB_KS_CASE(2) MB_KS_CASE(3) MB_KS_CASE(4) MB_KS_CASE(5) MB_KS_CASE(6) MB_KS_CASE(7) MB_KS_CASE(8)
+    MB_KS_CASE(9) MB_KS_CASE(10) MB_KS_CASE(11) MB_KS_CASE(12) MB_KS_CASE(13) MB_KS_CASE(14) MB_KS_CASE(15) MB_KS_CASE(16)
+#undef MB_KS_CASE
+    default: MB_FATAL("keyswitch: row stride %d unsupported", row_stride);
+  }
 }
 
 void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st) {
   const Params &p = ksk->p;
   MB_REQUIRE(p.n + 1 <= 1024, "keyswitch: output dimension n=%d too large (max 1023)", p.n);
-  MB_REQUIRE(p.base_bit >= 1 && p.base_bit <= 8, "keyswitch: base_bit=%d unsupported (1..8)", p.base_bit);
-  MB_REQUIRE(p.t >= 1 && p.t * p.base_bit < 64, "keyswitch: t*base_bit must be < 64");
-  MB_REQUIRE(ksk->row_stride % 64 == 0, "keyswitch: resident rows must be padded to 64 words");
-  if (count <= 0) return;
-  switch (ksk->row_stride / 64) {
-#define MB_KS_CASE(NV_) case NV_: launch_ks_nv<NV_>(ksk, out, in, count, st); break;
-    MB_KS_CASE(1) MB_KS_CASE(2) MB_KS_CASE(3) MB_KS_CASE(4) MB_KS_CASE(5) MB_KS_CASE(6) MB_KS_CASE(7) MB_KS_CASE(8)
-    MB_KS_CASE(9) MB_KS_CASE(10) MB_KS_CASE(11) MB_KS_CASE(12) MB_KS_CASE(13) MB_KS_CASE(14) MB_KS_CASE(15) MB_KS_CASE(16)
-#undef MB_KS_CASE
-    default: MB_FATAL("keyswitch: row stride %d unsupported", ksk->row_stride);
-  }
+  const int n_in = p.k * p.N;
+  launch_table_keyswitch(ksk->d, ksk->row_stride, n_in, p.t, p.base_bit, out, p.n + 1, p.n + 1, p.n, in, n_in + 1, n_in,
+                         count, st);
 }
 
 }  // namespace mb

@@ -455,3 +455,50 @@ void oracle_multivalue_phase2(Torus *out_tlwe, const int *in, const Torus *rot, 
   }
   free(tmp);
 }
+
+/* ---------- circuit bootstrap ------------------------------------------- */
+
+/* keyswitch.c:458-475 trlwe_packing1_keyswitch (include_b = 0) and keyswitch.c:639-656 trlwe_priv_keyswitch
+ * (include_b = 1): out = (0, in.b at b[0] | nothing) - sum over entries, digits of KSK[i][j][d-1]
+ * table: [n_in + include_b][t][2^base_bit-1][(k+1)*N] */
+void oracle_table_keyswitch_trlwe(Torus *out, const Torus *in_tlwe, const Torus *table, int n_in, int include_b,
+                                  int N, int k, int t, int base_bit) {
+  const size_t W = (size_t)(k + 1) * N;
+  const Torus prec_offset = 1ULL << (64 - (1 + base_bit * t));
+  const Torus mask = (1ULL << base_bit) - 1;
+  const int bm1 = (1 << base_bit) - 1;
+  memset(out, 0, sizeof(Torus) * W);
+  if (!include_b) out[(size_t)k * N] = in_tlwe[n_in];
+  for (int i = 0; i < n_in + include_b; i++) {
+    const Torus ai = (i < n_in ? in_tlwe[i] : in_tlwe[n_in]) + prec_offset;
+    for (int j = 0; j < t; j++) {
+      const Torus aij = (ai >> (64 - (j + 1) * base_bit)) & mask;
+      if (aij != 0) {
+        const Torus *row = table + (((size_t)i * t + j) * bm1 + (aij - 1)) * W;
+        for (size_t c = 0; c < W; c++) out[c] -= row[c];
+      }
+    }
+  }
+}
+
+/* bootstrap.c:324-345 circuit_bootstrap_2 (out->l == key->l == l, gadget of the output = Bg_out) */
+void oracle_circuit_bootstrap_2(Torus *out_trgsw, const Torus *in_tlwe, const double *bsk, const Torus *kska,
+                                const Torus *kskb, int n, int N, int k, int l, int Bg_bit, int Bg_out, int t,
+                                int base_bit, int mode) {
+  const size_t W = (size_t)(k + 1) * N;
+  const int slot = N / (2 * l);
+  Torus *tv = (Torus *)calloc(W, sizeof(Torus));
+  Torus *acc = (Torus *)malloc(sizeof(Torus) * W);
+  Torus *tl = (Torus *)malloc(sizeof(Torus) * (k * N + 1));
+  for (int i = 0; i < N; i++) {                        /* trlwe_torus_packing(tv, lut, 2l), trlwe.c:662-667 */
+    const int s = i / slot;
+    tv[(size_t)k * N + i] = (s >= l && s < 2 * l) ? (1ULL << (64 - (s - l + 1) * Bg_out)) : 0;
+  }
+  oracle_functional_bootstrap_wo_extract(acc, tv, in_tlwe, bsk, n, N, k, l, Bg_bit, 2 * l, mode);
+  for (int i = 0; i < l; i++) {
+    oracle_extract_tlwe(tl, acc, N, k, i * slot);
+    oracle_table_keyswitch_trlwe(out_trgsw + (size_t)i * W, tl, kska, k * N, 1, N, k, t, base_bit);
+    oracle_table_keyswitch_trlwe(out_trgsw + (size_t)(l + i) * W, tl, kskb, k * N, 0, N, k, t, base_bit);
+  }
+  free(tv); free(acc); free(tl);
+}

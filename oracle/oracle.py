@@ -62,6 +62,8 @@ def lib():
             "oracle_multivalue_bootstrap_CLOT21": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 8),
             "oracle_multivalue_phase1": (None, [_u64p, _u64p, _f64p] + [_int] * 7),
             "oracle_multivalue_phase2": (None, [_u64p, _i32p, _u64p, _int, _int, _int, _int]),
+            "oracle_table_keyswitch_trlwe": (None, [_u64p, _u64p, _u64p] + [_int] * 6),
+            "oracle_circuit_bootstrap_2": (None, [_u64p, _u64p, _f64p, _u64p, _u64p] + [_int] * 9),
             "oracle_tlwe_keyswitch": (None, [_u64p, _u64p, _u64p, _int, _int, _int, _int]),
             "oracle_tlwe_phase": (C.c_uint64, [_u64p, _u64p, _int]),
             "oracle_trlwe_phase": (None, [_u64p, _u64p, _u64p, _int, _int]),
@@ -251,6 +253,27 @@ def multivalue_phase2(lut_ints, rot, torus_base, log_torus_base):
     k, N = rot.shape[1] - 1, rot.shape[2]
     out = np.empty(k * N + 1, np.uint64)
     lib().oracle_multivalue_phase2(out, lut, rot, N, k, torus_base, log_torus_base)
+    return out
+
+
+def table_keyswitch_trlwe(tlwe_in, table, include_b, base_bit):
+    """table: [n_in + include_b, t, 2^base_bit-1, k+1, N] (trlwe_packing1_keyswitch / trlwe_priv_keyswitch)."""
+    tlwe_in = _c(tlwe_in, np.uint64)
+    table = _c(table, np.uint64)
+    ne, t, _, kp1, N = table.shape
+    out = np.empty((kp1, N), np.uint64)
+    lib().oracle_table_keyswitch_trlwe(out, tlwe_in, table, ne - include_b, include_b, N, kp1 - 1, t, base_bit)
+    return out
+
+
+def circuit_bootstrap_2(tlwe_in, bsk, kska, kskb, l, Bg_bit, Bg_out, base_bit, mode=0):
+    tlwe_in = _c(tlwe_in, np.uint64)
+    bsk = _c(bsk, np.float64)
+    kska, kskb = _c(kska, np.uint64), _c(kskb, np.uint64)
+    n = tlwe_in.shape[0] - 1
+    t, kp1, N = kskb.shape[1], kskb.shape[3], kskb.shape[4]
+    out = np.empty((2 * l, kp1, N), np.uint64)
+    lib().oracle_circuit_bootstrap_2(out, tlwe_in, bsk, kska, kskb, n, N, kp1 - 1, l, Bg_bit, Bg_out, t, base_bit, mode)
     return out
 
 

@@ -36,5 +36,10 @@ def golden_mv():
 
 
 @pytest.fixture
+def golden_cb():
+    return load_golden("tiny_cb_spqlios")
+
+
+@pytest.fixture
 def golden_ffnt():
     return load_golden("tiny_k1_ffnt")

@@ -231,7 +231,61 @@ def gen_mv(P, variant):
     return out
 
 
+def gen_cb(variant):
+    """circuit_bootstrap_2 (bootstrap.c:324-345) and its two table key switches, from a build with
+    UNCOMPRESSED key-switching rows (A_PRNG=none: the fma / portable variants)."""
+    R = reflib.load(variant)
+    sig = {
+        "trlwe_new_priv_SK_KS_key_N2": (abi.Generic_KS_Key, [abi.TRLWE_Key, abi.TLWE_Key, C.c_int, C.c_int]),
+        "trlwe_new_packing1_KS_key": (abi.Generic_KS_Key, [abi.TRLWE_Key, abi.TLWE_Key, C.c_int, C.c_int]),
+        "trlwe_priv_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
+        "trlwe_packing1_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
+        "circuit_bootstrap_2": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+        "trgsw_alloc_new_sample": (abi.TRGSW, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(R.lib, name); fn.restype, fn.argtypes = res, args
+    n, N, k, l, Bg_bit, t, base_bit = 10, 64, 1, 2, 8, 6, 2
+    R.init_fft(N)
+    out = dict(params=np.array([n, N, k, l, Bg_bit, t, base_bit], np.int32), layout=np.int32(R.layout))
+    key_lwe = R.tlwe_new_binary_key(n, 2.0 ** -30)
+    key_rlwe = R.trlwe_new_binary_key(N, k, 2.0 ** -45)
+    key_ext = R.tlwe_new_binary_key(k * N, 2.0 ** -45)
+    R.trlwe_extract_tlwe_key(key_ext, key_rlwe)
+    trgsw_key = R.trgsw_new_key(key_rlwe, l, Bg_bit)
+    bk = R.new_bootstrap_key(trgsw_key, key_lwe, 1)
+    kska = R.lib.trlwe_new_priv_SK_KS_key_N2(key_rlwe, key_ext, t, base_bit)
+    kskb = R.lib.trlwe_new_packing1_KS_key(key_rlwe, key_ext, t, base_bit)
+    out["lwe_key"] = key_words(key_lwe.contents.s, n)
+    out["rlwe_key"] = np.stack([key_words(key_rlwe.contents.s[i].contents.coeffs, N) for i in range(k)])
+    out["bsk_host"] = abi.bootstrap_key_to_flat(bk)
+    out["kska"] = abi.generic_ks_key_to_flat(kska)
+    out["kskb"] = abi.generic_ks_key_to_flat(kskb)
+    ins, cbs, pk, pv, tls = [], [], [], [], []
+    for m in (0, 1, 0, 1):
+        c = R.tlwe_new_sample(m << 62, key_lwe)            # LWE(m/4), as tests.c:980, 998
+        ins.append(abi.tlwe_to_flat(c))
+        o = R.lib.trgsw_alloc_new_sample(l, Bg_bit, k, N)
+        R.lib.circuit_bootstrap_2(o, c, bk, kska, kskb)
+        cbs.append(abi.trgsw_to_flat(o, k))
+        tl = rand_u64(R, k * N + 1)                          # the key switches alone on a random TLWE
+        tls.append(tl.copy())
+        ht = abi.HostTLWE(tl)
+        a = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_priv_keyswitch(a.handle, ht.handle, kska); pv.append(a.polys.copy())
+        b = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_packing1_keyswitch(b.handle, ht.handle, kskb); pk.append(b.polys.copy())
+    out["cb_in"] = np.stack(ins); out["cb_out"] = np.stack(cbs)
+    out["ks_in"] = np.stack(tls); out["priv_out"] = np.stack(pv); out["pack_out"] = np.stack(pk)
+    out["cb_msgs"] = np.array([0, 1, 0, 1], np.int32)
+    return out
+
+
 def main():
+    if "--cb-only" in sys.argv:
+        data = gen_cb("fma")
+        path = os.path.join(HERE, "tiny_cb_spqlios.npz")
+        np.savez_compressed(path, **data)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+        return
     if "--mv-only" in sys.argv:
         data = gen_mv(SETS["tiny_k1"], "avx512")
         path = os.path.join(HERE, "tiny_k1_mv_spqlios.npz")

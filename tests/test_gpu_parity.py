@@ -648,3 +648,129 @@ def test_cmux_and_vertical_packing(N, l, Bg_bit):
     expect = int(lut.reshape(-1)[value])
     assert O.torus2int(ph, out_prec) % (1 << out_prec) == expect
     trgsw_bits.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# Circuit bootstrap: the two TRLWE-row table key switches and circuit_bootstrap_2
+# ------------------------------------------------------------------------------------------------
+def test_trlwe_table_keyswitches_bit_exact(golden_cb):
+    """trlwe_priv_keyswitch (keyswitch.c:639-657) / trlwe_packing1_keyswitch (keyswitch.c:458-476) through the
+    struct entry points, their _batch forms and the flat device form: integer only, bit-exact against the
+    reference's outputs.  4 ciphertexts is the small-batch path (input sweep sliced, 64-bit atomics)."""
+    import torch
+    g, P = golden_cb, golden_cb["P"]
+    N, k = P["N"], P["k"]
+    ka = abi.HostGenericKSKey(g["kska"], P["base_bit"], 1)
+    kb = abi.HostGenericKSKey(g["kskb"], P["base_bit"], 0)
+    ins = [abi.HostTLWE(x) for x in g["ks_in"]]
+    for i, cin in enumerate(ins):
+        out = abi.HostTRLWE.zeros(k, N)
+        api.trlwe_priv_keyswitch(out, cin, ka)
+        assert np.array_equal(out.polys, g["priv_out"][i])
+        out = abi.HostTRLWE.zeros(k, N)
+        api.trlwe_packing1_keyswitch(out, cin, kb)
+        assert np.array_equal(out.polys, g["pack_out"][i])
+    outs = [abi.HostTRLWE.zeros(k, N) for _ in ins]
+    api.trlwe_priv_keyswitch_batch(outs, ins, ka)
+    assert all(np.array_equal(o.polys, w) for o, w in zip(outs, g["priv_out"]))
+    outs = [abi.HostTRLWE.zeros(k, N) for _ in ins]
+    api.trlwe_packing1_keyswitch_batch(outs, ins, kb)
+    assert all(np.array_equal(o.polys, w) for o, w in zip(outs, g["pack_out"]))
+    api.release_generic_ks_key(ka)
+    api.release_generic_ks_key(kb)
+    # flat device form, with a batch large enough for the un-sliced path (the 4 inputs repeated)
+    reps = 200
+    d_in = torch_dev(np.tile(g["ks_in"], (reps, 1)))
+    for table, inc, want in ((g["kska"], 1, g["priv_out"]), (g["kskb"], 0, g["pack_out"])):
+        key = api.GenericKSKey.from_host(table, inc, P["base_bit"])
+        d_out = torch.empty((4 * reps, k + 1, N), dtype=torch.int64, device="cuda")
+        api.trlwe_ks_dev(key, d_out, d_in, 4 * reps)
+        api.synchronize()
+        got = to_np(d_out)
+        assert np.array_equal(got, np.tile(want, (reps, 1, 1)))
+        key.free()
+
+
+def test_circuit_bootstrap_dropin(golden_cb):
+    """circuit_bootstrap_2 (bootstrap.c:324-345) against the reference's output, every TRGSW row in phase.
+    The tolerance is the one of tests/test_oracle_golden.py::test_circuit_bootstrap_2 (key-switch digits of
+    weight 2^52 move when the blind rotations differ by rounding)."""
+    g, P = golden_cb, golden_cb["P"]
+    N, k, l, Bg_bit = P["N"], P["k"], P["l"], P["Bg_bit"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, l, Bg_bit)
+    ka = abi.HostGenericKSKey(g["kska"], P["base_bit"], 1)
+    kb = abi.HostGenericKSKey(g["kskb"], P["base_bit"], 0)
+    ins = [abi.HostTLWE(x) for x in g["cb_in"]]
+    singles = []
+    for c, cin in enumerate(ins):
+        out = abi.HostTRGSW(np.zeros((2 * l, k + 1, N), np.uint64), l, Bg_bit)
+        api.circuit_bootstrap_2(out, cin, hbsk, ka, kb)
+        got = out.flat()
+        singles.append(got)
+        for r in range(2 * l):
+            d = sdiff(O.trlwe_phase(got[r], g["rlwe_key"]), O.trlwe_phase(g["cb_out"][c][r], g["rlwe_key"]))
+            assert d.max() <= (1 << 57), (c, r, int(d.max()))
+    outs = [abi.HostTRGSW(np.zeros((2 * l, k + 1, N), np.uint64), l, Bg_bit) for _ in ins]
+    api.circuit_bootstrap_2_batch(outs, ins, hbsk, ka, kb)
+    for o, s in zip(outs, singles):
+        assert np.array_equal(o.flat(), s)               # same kernels on the same inputs
+    api.release_bootstrap_key(hbsk)
+    api.release_generic_ks_key(ka)
+    api.release_generic_ks_key(kb)
+
+
+def _trlwe_encrypt(p, rlwe_key, seed):
+    """TRLWE sample (a, a*s + p) of the torus polynomial p under a binary key (k = 1), noise-free."""
+    N = p.shape[0]
+    a = syn.splitmix64_stream(seed, N)
+    a_s = (np.uint64(0) - O.trlwe_phase(np.stack([a, np.zeros(N, np.uint64)]), rlwe_key)).astype(np.uint64)
+    return np.stack([a, a_s + p])
+
+
+@pytest.mark.parametrize("N,l,Bg_bit,t,base_bit", [(1024, 4, 9, 7, 4), (2048, 4, 9, 7, 4), (512, 3, 10, 10, 3)])
+def test_circuit_bootstrap_full_size(N, l, Bg_bit, t, base_bit):
+    """The reference's own check (tests.c:965-1007) at full ring sizes, batched and wholly on the device:
+    LWE(m/4) -> circuit bootstrap -> TRGSW(m); TRGSW(m) (.) TRLWE(p) must decrypt to m*p within 2^58."""
+    import torch
+    n, count = 632, 8
+    P = Params(n, N, 1, l, Bg_bit, t, base_bit, 2.0 ** -30, 2.0 ** -55)
+    lwe_key = syn.binary_key(n, 11)
+    rlwe_key = syn.binary_key(N, 12)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=N)
+    kska = api.GenericKSKey.synthesize(rlwe_key, rlwe_key, 1, t, base_bit, 2.0 ** -55, seed=21)
+    kskb = api.GenericKSKey.synthesize(rlwe_key, rlwe_key, 0, t, base_bit, 2.0 ** -55, seed=22)
+    msgs = np.arange(count) % 2
+    cts = syn.tlwe_encrypt((msgs.astype(np.uint64) << np.uint64(62)), lwe_key, P.lwe_sigma, seed=13)
+    d_in = torch_dev(cts)
+    d_trgsw = torch.empty((count, 2 * l, 2, N), dtype=torch.int64, device="cuda")
+    api.circuit_bootstrap_dev(bsk, kska, kskb, d_trgsw, d_in, Bg_bit, count)
+    api.synchronize()
+    assert api.last_blind_rotate_kernel() in ("k1", "k1h")
+    trgsw = to_np(d_trgsw)
+    # each TRGSW row decrypts to m * h_i on the right polynomial (trgsw.c:152-168)
+    for c in range(count):
+        for r in range(2 * l):
+            ph = O.trlwe_phase(trgsw[c][r], rlwe_key)
+            h = np.uint64(int(msgs[c]) << (64 - (r % l + 1) * Bg_bit))
+            want = (np.uint64(0) - rlwe_key * h) if r < l else np.concatenate([[h], np.zeros(N - 1, np.uint64)])
+            # row noise = bootstrap noise + key-switch rounding (2^(63 - t*base_bit) * sqrt(N/6)); the external
+            # product below amplifies it by about 2^(Bg_bit - 2) * sqrt(l*N), so 2^44 keeps the result under 2^58
+            assert sdiff(ph, want.astype(np.uint64)).max() <= (1 << 44), (c, r)
+    # use as selectors: trgsw_to_DFT on the device, then one external product per ciphertext
+    Pset = Params(count, N, 1, l, Bg_bit, t, base_bit, 2.0 ** -30, 2.0 ** -55)
+    tset = api.BootstrapKey.from_torus_dev(Pset, d_trgsw)
+    rng = np.random.default_rng(N + l)
+    polys = rng.integers(0, 1 << 63, size=(count, N), dtype=np.uint64) << np.uint64(1)
+    samples = np.stack([_trlwe_encrypt(polys[c], rlwe_key, 100 + c) for c in range(count)])
+    d_s = torch_dev(samples)
+    d_o = torch.empty_like(d_s)
+    api.extprod_dev(tset, np.arange(count, dtype=np.int32), d_o, d_s, count)
+    api.synchronize()
+    res = to_np(d_o)
+    for c in range(count):
+        ph = O.trlwe_phase(res[c], rlwe_key)
+        want = polys[c] if msgs[c] else np.zeros(N, np.uint64)
+        assert sdiff(ph, want).max() <= TOL_TEST, c
+    for h in (bsk, kska, kskb, tset):
+        h.free()

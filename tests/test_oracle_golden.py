@@ -160,3 +160,30 @@ def test_multivalue_phases(golden_mv):
         want = (int(g["mv_luts"][0][m]) << 61) % 2**64
         d = (O.tlwe_phase(out, g["ext_key"]) - want) % 2**64
         assert abs(int(np.int64(np.uint64(d)))) <= (1 << 58)
+
+
+def test_trlwe_table_keyswitches_bit_exact(golden_cb):
+    """trlwe_priv_keyswitch (keyswitch.c:639-657) and trlwe_packing1_keyswitch (keyswitch.c:458-476): integer
+    only, so bit-exact against the reference's outputs on the same random TLWE inputs."""
+    g, P = golden_cb, golden_cb["P"]
+    for i in range(g["ks_in"].shape[0]):
+        assert np.array_equal(O.table_keyswitch_trlwe(g["ks_in"][i], g["kska"], 1, P["base_bit"]), g["priv_out"][i])
+        assert np.array_equal(O.table_keyswitch_trlwe(g["ks_in"][i], g["kskb"], 0, P["base_bit"]), g["pack_out"][i])
+
+
+def test_circuit_bootstrap_2(golden_cb):
+    """circuit_bootstrap_2 (bootstrap.c:324-345): every TRGSW row compared in phase under the TRLWE key.  The
+    blind rotation differs from the reference's by floating-point rounding, which moves a few key-switch digits
+    (weight 2^(64 - t*base_bit) = 2^52 each), hence the 2^57 bound."""
+    g, P = golden_cb, golden_cb["P"]
+    nat = O.permute_from_host(g["bsk_host"], g["layout"])
+    worst = []
+    for c in range(g["cb_in"].shape[0]):
+        got = O.circuit_bootstrap_2(g["cb_in"][c], nat, g["kska"], g["kskb"], P["l"], P["Bg_bit"], P["Bg_bit"], P["base_bit"])
+        assert got.shape == g["cb_out"][c].shape
+        for r in range(2 * P["l"]):
+            d = O.signed_diff(O.trlwe_phase(got[r], g["rlwe_key"]), O.trlwe_phase(g["cb_out"][c][r], g["rlwe_key"]))
+            assert np.abs(d).max() <= (1 << 57), (c, r, int(np.abs(d).max()))
+            worst.append(int(np.abs(d).max()))
+    # no digit moved in most rows: those agree to the rounding of the blind rotation itself
+    assert sorted(worst)[len(worst) // 2] <= (1 << 40)
