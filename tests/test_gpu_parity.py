@@ -746,7 +746,7 @@ def test_circuit_bootstrap_full_size(N, l, Bg_bit, t, base_bit):
     d_trgsw = torch.empty((count, 2 * l, 2, N), dtype=torch.int64, device="cuda")
     api.circuit_bootstrap_dev(bsk, kska, kskb, d_trgsw, d_in, Bg_bit, count)
     api.synchronize()
-    assert api.last_blind_rotate_kernel() in ("k1", "k1h")
+    assert api.last_blind_rotate_kernel().startswith("k1")
     trgsw = to_np(d_trgsw)
     # each TRGSW row decrypts to m * h_i on the right polynomial (trgsw.c:152-168)
     for c in range(count):
