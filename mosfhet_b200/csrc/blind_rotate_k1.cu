@@ -45,12 +45,20 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
   constexpr int PKL = PKALL ? L : LB;                 // gadget levels packed into one 32-bit word per coefficient
 #ifdef MB200_PB_FULL
   constexpr int PB_UNROLL = 16;
+#elif defined(MB200_PB_UNROLL)
+  constexpr int PB_UNROLL = MB200_PB_UNROLL;
 #else
-  constexpr int PB_UNROLL = R2 <= 4 ? 4 : 2;          // independent pass-B butterflies in flight per thread
+  // independent pass-B butterflies in flight per thread; 4 measured 3 % slower than 2 at N = 1024 (code size:
+  // profiles/r1k_k1_occupancy.log)
+  constexpr int PB_UNROLL = 2;
 #endif
 #ifndef MB200_PA_UNROLL
 #define MB200_PA_UNROLL 1
 #endif
+#ifndef MB200_PC_UNROLL
+#define MB200_PC_UNROLL 2
+#endif
+  constexpr int PC_UNROLL = MB200_PC_UNROLL;          // pass-C rows unrolled together when keys are not double buffered
   constexpr int PA_UNROLL = MB200_PA_UNROLL;          // gadget levels of pass A unrolled together
   static_assert(LB >= 1 && LB <= L, "levels per batch");
   static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
         const int p = rb / NB, lev = lev0 + (rb - p * NB);
         return key + (size_t)((p * L + lev) * 2) * M + tid;            // TRGSW row order of trgsw.c:394-419
       };
-      double2 kv[PF ? 2 : 1][16];
+      double2 kv[PF == 1 ? 2 : 1][16];
       auto load_keys = [&](double2 (&dst)[16], int rb) {
         const double2 *__restrict__ k0 = key_row(rb);
 #pragma unroll
@@ -192,12 +200,25 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
         (void)k0;
 #else
         for (int i = 0; i < 8; ++i) {
-          if (G > 1) { dst[i] = __ldg(k0 + i * C8); dst[8 + i] = __ldg(k0 + M + i * C8); }      // L1-allocating: shared by the groups
+          if (G > 1 || PF == 2) { dst[i] = __ldg(k0 + i * C8); dst[8 + i] = __ldg(k0 + M + i * C8); }   // L1-allocating
           else { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }          // streaming
         }
 #endif
       };
-      if (PF) load_keys(kv[0], 0);                                      // in flight across pass B
+      // PF == 2: no register double buffer; the next row is pulled into L1 (one lane per 128-byte line) while
+      // the current one computes, so the demand loads hit L1 instead of waiting for L2
+      auto prefetch_keys = [&](int rb) {
+        if ((tid & 7) == 0) {
+          const double2 *__restrict__ k0 = key_row(rb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(k0 + i * C8));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(k0 + M + i * C8));
+          }
+        }
+      };
+      if (PF == 1) load_keys(kv[0], 0);                                 // in flight across pass B
+      if (PF == 2) prefetch_keys(0);
       // ------------------------------- pass B -------------------------------------------------
       constexpr int TASKS_B = ROWS_B * 128 / T;
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
       }
       __syncthreads();
       // ------------------------------- pass C + MAC ----------------------------------------------
-      if (PF) {
+      if (PF == 1) {
         // fully unrolled on purpose: a 2-row ping-pong loop (smaller code) measured 10 % slower
 #pragma unroll
         for (int rb = 0; rb < ROWS_B; ++rb) {
@@ -235,9 +256,10 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
           for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[rb & 1][i]); cfma(fa[1][i], x[i], kv[rb & 1][8 + i]); }
         }
       } else {
-#pragma unroll 2
+#pragma unroll(PC_UNROLL)
         for (int rb = 0; rb < ROWS_B; ++rb) {
           load_keys(kv[0], rb);
+          if (PF == 2 && rb + 1 < ROWS_B) prefetch_keys(rb + 1);
           const double2 *row = buf + rb * M;
           double2 x[8];
 #pragma unroll
@@ -249,10 +271,87 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
       }
       __syncthreads();
     };
-    // full batches of LB levels, then the ragged remainder (compile-time structure: constant shifts and rows)
+    // The same batch with the number of levels as a run-time value: ONE copy of the pass A/B/C code for the
+    // full and the ragged batch (the kernel is instruction-cache sensitive: ncu shows 64-72 % GCC instruction
+    // requests and 12 % no_instruction stalls in pass A).  Used when the batches are ragged and the keys are
+    // not double buffered in registers (that path needs compile-time buffer indices).
+    auto batch_rt = [&](const int nb, const int lev0) {
+      if (!PKALL) pack_digits(lev0 + nb);
+      constexpr bool HOIST_TW = (LOGM <= 9);
+      double2 twA[HOIST_TW ? 16 : 1];
+      if (HOIST_TW) {
 #pragma unroll
-    for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
-    if constexpr (L % LB != 0) batch(std::integral_constant<int, L % LB>{}, L - L % LB);
+        for (int pos = 0; pos < 16; ++pos) twA[HOIST_TW ? pos : 0] = __ldg(&TA[brev(pos, 4) * S + qA]);
+      }
+#pragma unroll 1
+      for (int lb = 0; lb < nb; ++lb) {
+        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (nb - 1 - lb)) * Bg_bit;
+        double2 x[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
+          const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
+          x[m] = mul_w64(make_double2(d0, d1), m, false);
+        }
+        reg_dif<16>(x);
+        double2 *row = buf + (pA * nb + lb) * M;
+#pragma unroll
+        for (int pos = 0; pos < 16; ++pos) {
+          const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
+          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
+        }
+      }
+      __syncthreads();
+      const int tasks_b = 2 * nb * 128 / T;
+#pragma unroll(PB_UNROLL)
+      for (int it = 0; it < tasks_b; ++it) {
+        double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
+        double2 x[R2];
+#pragma unroll
+        for (int m = 0; m < R2; ++m) x[m] = blk[8 * m + qx[m]];
+        reg_dif<R2>(x);
+#pragma unroll
+        for (int pos = 0; pos < R2; ++pos) {
+          const int k = brev(pos, LOGR2);
+          const double2 y = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
+          blk[8 * pos + qx[pos]] = y;
+        }
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int p = 0; p < 2; ++p) {
+#pragma unroll(PC_UNROLL)
+        for (int lv = 0; lv < nb; ++lv) {
+          const double2 *__restrict__ k0 = key + (size_t)((p * L + lev0 + lv) * 2) * M + tid;
+          double2 kv[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { kv[i] = ldg_key(k0 + i * C8); kv[8 + i] = ldg_key(k0 + M + i * C8); }
+          const double2 *row = buf + (p * nb + lv) * M;
+          double2 x[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
+          reg_dif<8>(x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[i]); cfma(fa[1][i], x[i], kv[8 + i]); }
+        }
+      }
+      __syncthreads();
+    };
+    // measured: no faster than the two unrolled copies (47.2-47.8 ms vs 46.5-48.0 ms at level 1) -> opt-in
+#ifdef MB200_ROLLED_BATCH
+    constexpr bool ROLLED = (L % LB != 0) && PF == 0 && G == 1;
+#else
+    constexpr bool ROLLED = false;
+#endif
+    if constexpr (ROLLED) {
+#pragma unroll 1
+      for (int lev0 = 0; lev0 < L; lev0 += LB) batch_rt(min(LB, L - lev0), lev0);
+    } else {
+      // full batches of LB levels, then the ragged remainder (compile-time structure: constant shifts and rows)
+#pragma unroll
+      for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
+      if constexpr (L % LB != 0) batch(std::integral_constant<int, L % LB>{}, L - L % LB);
+    }
 
     // ---------------------------------- inverse: C' ------------------------------------------------
 #pragma unroll
@@ -362,6 +461,9 @@ static K1Variant default_variant(int logm, int l, int Bg_bit) {
   if (logm == 11) lb = 1;
   while (lb > 1 && lb * Bg_bit > 32) --lb;
   if (lb == 3 && l == 4) lb = 2;                        // instantiated batch sizes: l, 2, 1
+  // N = 1024, l = 3: batches of 2 + 1 levels need 49 KB of shared memory instead of 65 KB -> 4 CTAs per SM
+  // instead of 3; 47.7 ms vs 51.7 ms per 4096 bootstraps (profiles/r1k_k1_occupancy.log)
+  if (logm == 9 && l == 3 && lb == 3) lb = 2;
   // double-buffered key rows in pass C pay off while they fit the register file (profiles/r1b_k1_variants.log)
   const int pf = (logm <= 9 && lb == l && l <= 3) ? 1 : 0;
   return {lb, 1, pf};
@@ -454,6 +556,7 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   MB_K1_CASE(11, 1, 1, 1, 0) MB_K1_CASE(11, 2, 1, 1, 0) MB_K1_CASE(11, 3, 1, 1, 0) MB_K1_CASE(11, 4, 1, 1, 0)
 #ifdef MB200_K1_EXPERIMENTS
   MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 3, 3, 1, 0)
+  MB_K1_CASE(9, 3, 2, 1, 2) MB_K1_CASE(9, 3, 3, 1, 2) MB_K1_CASE(10, 4, 2, 1, 2)
 #endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
