@@ -56,6 +56,11 @@ typedef struct _Generic_KS_Key {                                             /* 
   int base_bit, t, n, include_b;
 } *Generic_KS_Key;
 
+typedef struct _TRLWE_KS_Key {                                               /* mosfhet.h:90 */
+  TRLWE_DFT **s;          /* s[i][j], i < k (input mask polynomials), j < t: Fourier-domain TRLWE rows */
+  int base_bit, t, k;
+} *TRLWE_KS_Key;
+
 typedef struct _Bootstrap_Key {                                              /* mosfhet.h:129 */
   TRGSW_DFT *s;           /* s[i], i < n: Fourier-domain TRGSW of LWE key bit i (unfolding==1) */
   TRGSW     *su;          /* torus-domain keys for unfolding > 1 (not accelerated; rejected)   */
@@ -86,6 +91,10 @@ void multivalue_bootstrap_CLOT21(TLWE *out, TRLWE tv, TLWE in, Bootstrap_Key key
 void trlwe_packing1_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key);                             /* mosfhet.h:384, keyswitch.c:458 */
 void trlwe_priv_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key);                                 /* mosfhet.h:386, keyswitch.c:639 */
 void circuit_bootstrap_2(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb); /* mosfhet.h:421, bootstrap.c:324 */
+void circuit_bootstrap(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb);   /* mosfhet.h:420, bootstrap.c:309 */
+void circuit_bootstrap_3(TRGSW out, TLWE in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb);  /* mosfhet.h:422, bootstrap.c:347 */
+void trlwe_keyswitch(TRLWE out, TRLWE in, TRLWE_KS_Key ks_key);                                           /* mosfhet.h:375, keyswitch.c:162 (out may alias in) */
+void trlwe_priv_keyswitch_2(TRLWE out, TRLWE in, TRLWE_KS_Key *ks_key);                                   /* mosfhet.h:399, keyswitch.c:52 */
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base);             /* mosfhet.h:413, bootstrap.c:232 */
 void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base,
                                  int log_torus_base);                                                 /* mosfhet.h:414, bootstrap.c:245 */
@@ -121,6 +130,10 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
 void trlwe_packing1_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count);
 void trlwe_priv_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count);
 void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count);
+void circuit_bootstrap_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count);
+void circuit_bootstrap_3_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb, int count);
+void trlwe_keyswitch_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key ks_key, int count);
+void trlwe_priv_keyswitch_2_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key *ks_key, int count);
 void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count);
 void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLWE **rotated_tv,
                                        int torus_base, int log_torus_base, int count);
@@ -156,6 +169,10 @@ void mb200_release_ks_key(TLWE_KS_Key key);
  * the reference (rnd/aes_rng.c:88-93), so this must happen in the process that generated the key. */
 void mb200_register_generic_ks_key(Generic_KS_Key key);
 void mb200_release_generic_ks_key(Generic_KS_Key key);
+void mb200_register_trlwe_ks_key(TRLWE_KS_Key key);              /* keyed by key->s */
+void mb200_release_trlwe_ks_key(TRLWE_KS_Key key);
+void mb200_register_trlwe_priv_ks_key(TRLWE_KS_Key *keys);       /* the TRLWE_KS_Key[2] of trlwe_new_priv_KS_key, keyed by the array */
+void mb200_release_trlwe_priv_ks_key(TRLWE_KS_Key *keys);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Flat API.  Layouts (all little-endian u64 / f64, contiguous):
@@ -218,6 +235,17 @@ void mb200_trlwe_ks_dev(mb200_gksk_t ksk, uint64_t *d_out_trlwe /* [count][2N] *
 /* circuit_bootstrap_2 on device buffers: d_out_trgsw [count][2l][2][N] (rows 0..l-1 private, l..2l-1 packing) */
 void mb200_circuit_bootstrap_dev(mb200_bsk_t bsk, mb200_gksk_t kska, mb200_gksk_t kskb, uint64_t *d_out_trgsw,
                                  const uint64_t *d_in /* [count][n+1] */, int Bg_bit_out, int count, void *stream);
+
+/* FFT-based TRLWE key switches on device buffers.  `row_set` is a TRGSW-shaped resident set with n = 1, l = t,
+ * Bg_bit = base_bit (mb200_bsk_from_host): rows [i*t + j] = TRLWE_KS_Key->s[i][j]; the k*t.. rows are zero for
+ * mode 1 (trlwe_keyswitch, keyswitch.c:162) or the second key of the pair for mode 2 (trlwe_priv_keyswitch_2, :52). */
+void mb200_trlwe_fft_ks_dev(mb200_bsk_t row_set, int mode, uint64_t *d_out /* [count][(k+1)N], may alias d_in */,
+                            const uint64_t *d_in, int count, void *stream);
+/* circuit_bootstrap (variant 1, bootstrap.c:309), _2 (variant 2, :324) or _3 (variant 3, :347; private key switch =
+ * `kska_fft` row set of the TRLWE_KS_Key pair, `kska` unused) on device buffers; d_out_trgsw [count][2*l_out][2][N] */
+void mb200_circuit_bootstrap_variant_dev(int variant, mb200_bsk_t bsk, mb200_gksk_t kska, mb200_bsk_t kska_fft,
+                                         mb200_gksk_t kskb, uint64_t *d_out_trgsw, const uint64_t *d_in, int l_out,
+                                         int Bg_bit_out, int count, void *stream);
 
 /* Device-resident batch ops (inputs/outputs already in HBM; asynchronous on `stream`). */
 void mb200_pbs_dev(mb200_bsk_t bsk, uint64_t *d_out_tlwe /* [count][k*N+1] */,

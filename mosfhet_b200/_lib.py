@@ -33,6 +33,20 @@ PROTOTYPES = {
     "trlwe_packing1_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
     "trlwe_priv_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
     "circuit_bootstrap_2": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+    "circuit_bootstrap": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+    "circuit_bootstrap_3": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, _P(abi.TRLWE_KS_Key), abi.Generic_KS_Key]),
+    "trlwe_keyswitch": (None, [abi.TRLWE, abi.TRLWE, abi.TRLWE_KS_Key]),
+    "trlwe_priv_keyswitch_2": (None, [abi.TRLWE, abi.TRLWE, _P(abi.TRLWE_KS_Key)]),
+    "circuit_bootstrap_batch": (None, [_P(abi.TRGSW), _P(abi.TLWE), abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key, C.c_int]),
+    "circuit_bootstrap_3_batch": (None, [_P(abi.TRGSW), _P(abi.TLWE), abi.Bootstrap_Key, _P(abi.TRLWE_KS_Key), abi.Generic_KS_Key, C.c_int]),
+    "trlwe_keyswitch_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE), abi.TRLWE_KS_Key, C.c_int]),
+    "trlwe_priv_keyswitch_2_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE), _P(abi.TRLWE_KS_Key), C.c_int]),
+    "mb200_register_trlwe_ks_key": (None, [abi.TRLWE_KS_Key]),
+    "mb200_release_trlwe_ks_key": (None, [abi.TRLWE_KS_Key]),
+    "mb200_register_trlwe_priv_ks_key": (None, [_P(abi.TRLWE_KS_Key)]),
+    "mb200_release_trlwe_priv_ks_key": (None, [_P(abi.TRLWE_KS_Key)]),
+    "mb200_trlwe_fft_ks_dev": (None, [_vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "mb200_circuit_bootstrap_variant_dev": (None, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "trlwe_packing1_keyswitch_batch": (None, [_P(abi.TRLWE), _P(abi.TLWE), abi.Generic_KS_Key, C.c_int]),
     "trlwe_priv_keyswitch_batch": (None, [_P(abi.TRLWE), _P(abi.TLWE), abi.Generic_KS_Key, C.c_int]),
     "circuit_bootstrap_2_batch": (None, [_P(abi.TRGSW), _P(abi.TLWE), abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key, C.c_int]),

@@ -87,6 +87,10 @@ class GenericKSKeyS(C.Structure):             # mosfhet.h:100-103
                 ("base_bit", C.c_int), ("t", C.c_int), ("n", C.c_int), ("include_b", C.c_int)]
 
 
+class TRLWEKSKeyS(C.Structure):               # mosfhet.h:90-93
+    _fields_ = [("s", C.POINTER(C.POINTER(TRLWE_DFT))), ("base_bit", C.c_int), ("t", C.c_int), ("k", C.c_int)]
+
+
 class BootstrapKeyS(C.Structure):             # mosfhet.h:129-133
     _fields_ = [("s", C.POINTER(TRGSW_DFT)), ("su", C.POINTER(TRGSW)),
                 ("n", C.c_int), ("k", C.c_int), ("N", C.c_int), ("Bg_bit", C.c_int),
@@ -99,6 +103,7 @@ TRLWE_Key = C.POINTER(TRLWEKeyS)
 TRGSW_Key = C.POINTER(TRGSWKeyS)
 Bootstrap_Key = C.POINTER(BootstrapKeyS)
 Generic_KS_Key = C.POINTER(GenericKSKeyS)
+TRLWE_KS_Key = C.POINTER(TRLWEKSKeyS)
 
 
 class ParamsS(C.Structure):                   # include/mosfhet_b200.h: mb200_params
@@ -244,6 +249,28 @@ class HostGenericKSKey:
         self.handle = C.pointer(self.struct)
 
 
+class HostTRLWEKSKey:
+    """A ``TRLWE_KS_Key`` over a ``[k_in, t, k_out+1, N]`` float64 array (host slot order)."""
+
+    def __init__(self, ksk: np.ndarray, base_bit: int):
+        ksk = np.ascontiguousarray(ksk, dtype=np.float64)
+        k_in, t = ksk.shape[:2]
+        self.rows = [[HostTRLWEDFT(ksk[i, j]) for j in range(t)] for i in range(k_in)]
+        self._lvl1 = [(TRLWE_DFT * t)(*[r.handle for r in self.rows[i]]) for i in range(k_in)]
+        self._lvl0 = (C.POINTER(TRLWE_DFT) * k_in)(*[C.cast(a, C.POINTER(TRLWE_DFT)) for a in self._lvl1])
+        self.struct = TRLWEKSKeyS(C.cast(self._lvl0, C.POINTER(C.POINTER(TRLWE_DFT))), base_bit, t, k_in)
+        self.handle = C.pointer(self.struct)
+
+
+class HostTRLWEKSKeyPair:
+    """The ``TRLWE_KS_Key[2]`` of ``trlwe_new_priv_KS_key`` over a ``[2, t, 2, N]`` float64 array."""
+
+    def __init__(self, ksk2: np.ndarray, base_bit: int):
+        self.keys = [HostTRLWEKSKey(ksk2[i][None], base_bit) for i in range(2)]
+        self._arr = (TRLWE_KS_Key * 2)(*[k.handle for k in self.keys])
+        self.handle = C.cast(self._arr, C.POINTER(TRLWE_KS_Key))
+
+
 class HostTRGSW:
     """A torus-domain ``TRGSW`` handle over a ``[(k+1)*l, (k+1), N]`` uint64 array."""
 
@@ -265,6 +292,12 @@ def generic_ks_key_to_flat(h) -> np.ndarray:
     ne = s.n + s.include_b
     return np.stack([np.stack([np.stack([trlwe_to_flat(s.s[i][j][d]) for d in range(bm1)]) for j in range(s.t)])
                      for i in range(ne)])
+
+
+def trlwe_ks_key_to_flat(h) -> np.ndarray:
+    """TRLWE_KS_Key -> [k_in, t, k_out+1, N] float64 (host slot order)."""
+    s = h.contents
+    return np.stack([np.stack([trlwe_dft_to_flat(s.s[i][j]) for j in range(s.t)]) for i in range(s.k)])
 
 
 def handle_array(handles, ctype):

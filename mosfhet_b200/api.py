@@ -152,6 +152,62 @@ def circuit_bootstrap_2_batch(outs, ins, key, kska, kskb) -> None:
                                     _h(kska), _h(kskb), len(ins))
 
 
+def circuit_bootstrap(out, in_, key, kska, kskb) -> None:
+    """One functional bootstrap per gadget level (bootstrap.c:309-322)."""
+    lib().circuit_bootstrap(_h(out), _h(in_), _h(key), _h(kska), _h(kskb))
+
+
+def circuit_bootstrap_3(out, in_, key, kska_pair, kskb) -> None:
+    """circuit_bootstrap_2 with the FFT-based private key switch (bootstrap.c:347-366); kska_pair: TRLWE_KS_Key[2]."""
+    lib().circuit_bootstrap_3(_h(out), _h(in_), _h(key), _h(kska_pair), _h(kskb))
+
+
+def circuit_bootstrap_batch(outs, ins, key, kska, kskb) -> None:
+    lib().circuit_bootstrap_batch(abi.handle_array(outs, abi.TRGSW), abi.handle_array(ins, abi.TLWE), _h(key),
+                                  _h(kska), _h(kskb), len(ins))
+
+
+def circuit_bootstrap_3_batch(outs, ins, key, kska_pair, kskb) -> None:
+    lib().circuit_bootstrap_3_batch(abi.handle_array(outs, abi.TRGSW), abi.handle_array(ins, abi.TLWE), _h(key),
+                                    _h(kska_pair), _h(kskb), len(ins))
+
+
+def trlwe_keyswitch(out, in_, ks_key) -> None:
+    """FFT-based TRLWE key switch (keyswitch.c:162-193); out may be in_."""
+    lib().trlwe_keyswitch(_h(out), _h(in_), _h(ks_key))
+
+
+def trlwe_priv_keyswitch_2(out, in_, ks_key_pair) -> None:
+    lib().trlwe_priv_keyswitch_2(_h(out), _h(in_), _h(ks_key_pair))
+
+
+def trlwe_keyswitch_batch(outs, ins, ks_key) -> None:
+    lib().trlwe_keyswitch_batch(abi.handle_array(outs, abi.TRLWE), abi.handle_array(ins, abi.TRLWE), _h(ks_key), len(ins))
+
+
+def trlwe_priv_keyswitch_2_batch(outs, ins, ks_key_pair) -> None:
+    lib().trlwe_priv_keyswitch_2_batch(abi.handle_array(outs, abi.TRLWE), abi.handle_array(ins, abi.TRLWE),
+                                       _h(ks_key_pair), len(ins))
+
+
+def release_trlwe_ks_key(key) -> None:
+    lib().mb200_release_trlwe_ks_key(_h(key))
+
+
+def release_trlwe_priv_ks_key(pair) -> None:
+    lib().mb200_release_trlwe_priv_ks_key(_h(pair))
+
+
+def trlwe_fft_ks_dev(row_set, mode: int, d_out, d_in, count, stream=None):
+    lib().mb200_trlwe_fft_ks_dev(row_set.handle, mode, _ptr(d_out), _ptr(d_in), count, _ptr(stream))
+
+
+def circuit_bootstrap_variant_dev(variant, bsk, kska, kska_fft, kskb, d_out_trgsw, d_in, l_out, Bg_bit_out, count, stream=None):
+    lib().mb200_circuit_bootstrap_variant_dev(variant, bsk.handle, kska.handle if kska else None,
+                                              kska_fft.handle if kska_fft else None, kskb.handle, _ptr(d_out_trgsw),
+                                              _ptr(d_in), l_out, Bg_bit_out, count, _ptr(stream))
+
+
 def release_generic_ks_key(key) -> None:
     lib().mb200_release_generic_ks_key(_h(key))
 

@@ -40,6 +40,7 @@ struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; };
 struct mb200_gksk : GkskDev {};
 namespace {
 std::map<const void *, GkskDev *> g_gksk_cache;    // keyed by Generic_KS_Key->s
+std::map<const void *, mb200_bsk *> g_rksk_cache;  // keyed by TRLWE_KS_Key->s, or by the TRLWE_KS_Key[2] array
 
 mb::Params to_params(const mb200_params *p) {
   mb::Params q;
@@ -450,6 +451,8 @@ void mb200_shutdown(void) {
   g_bsk_cache.clear();
   g_ksk_cache.clear();
   g_gksk_cache.clear();
+  for (auto &kv : g_rksk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
+  g_rksk_cache.clear();
   for (auto &kv : g_dft_maps) cudaFree(kv.second.stored_to_host);
   g_dft_maps.clear();
   for (int i = 0; i < S_COUNT; ++i) t_scratch[i].release();
@@ -1001,64 +1004,178 @@ static void trlwe_table_ks_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, in
 void trlwe_packing1_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count) { trlwe_table_ks_batch(out, in, ks_key, count, 0); }
 void trlwe_priv_keyswitch_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count) { trlwe_table_ks_batch(out, in, ks_key, count, 1); }
 
-// device-side core of circuit_bootstrap_2 (shared by the handle and the flat entry points)
-static void circuit_bootstrap_core(mb200_bsk *bsk, GkskDev *ga, GkskDev *gb, u64 *d_out, const u64 *d_in, int Bgo,
-                                   int count, cudaStream_t st) {
-  const mb::Params &p = bsk->p;
-  const int lo = p.l;
-  MB_REQUIRE(p.k == 1, "circuit bootstrap: k = 1 only");
-  MB_REQUIRE(ga->n_in == p.k * p.N && gb->n_in == p.k * p.N, "circuit bootstrap: key switch input dimension mismatch");
-  MB_REQUIRE(ga->N == gb->N && ga->k == gb->k, "circuit bootstrap: the two key switches must target the same TRLWE shape");
-  const size_t W = (size_t)(p.k + 1) * p.N, Wo = (size_t)(ga->k + 1) * ga->N;
-  const size_t tv_b = sizeof(u64) * W;
-  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
-  // trlwe_torus_packing(tv, lut, 2l) with lut[i] = 0, lut[l+i] = 2^(64-(i+1)*Bg_out)  (bootstrap.c:330-334)
-  memset(h_tv, 0, tv_b);
-  const int slot = p.N / (2 * lo);
-  for (int i = 0; i < p.N; ++i) {
-    const int s_ = i / slot;
-    h_tv[(size_t)p.k * p.N + i] = (s_ >= lo && s_ < 2 * lo) ? (1ull << (64 - (s_ - lo + 1) * Bgo)) : 0ull;
+// ---- FFT-based TRLWE key switches (keyswitch.c:162-193, 52-63) -------------------------------------------
+// A TRLWE_KS_Key is held as one TRGSW-shaped row set (l = t, Bg_bit = base_bit) so that the external-product
+// kernel serves it: rows [i*t + j] = s[i][j] for the mask polynomials; the rows of b are zero padding for
+// trlwe_keyswitch (never swept) or the second key of the trlwe_new_priv_KS_key pair for trlwe_priv_keyswitch_2.
+static mb200_bsk *rksk_build(TRLWE_KS_Key k0, TRLWE_KS_Key k1) {
+  MB_REQUIRE(k0 != nullptr && k0->s != nullptr, "TRLWE_KS_Key is NULL");
+  TRLWE_DFT r0 = k0->s[0][0];
+  mb::Params p{};
+  p.n = 1; p.k = r0->k; p.N = r0->b->N; p.l = k0->t; p.Bg_bit = k0->base_bit;
+  MB_REQUIRE(k0->k == p.k, "trlwe_keyswitch: input k=%d and output k=%d must match", k0->k, p.k);
+  if (k1) MB_REQUIRE(p.k == 1 && k1->k == 1 && k1->t == k0->t && k1->base_bit == k0->base_bit,
+                     "trlwe_priv_keyswitch_2: the two keys must share k = 1, t and base_bit");
+  const size_t per_row = (size_t)(p.k + 1) * p.N;
+  std::vector<double> flat((size_t)(p.k + 1) * p.l * per_row, 0.0);
+  auto put = [&](size_t row, TRLWE_DFT src) {
+    for (int q = 0; q <= p.k; ++q) {
+      DFT_Polynomial poly = q < p.k ? src->a[q] : src->b;
+      memcpy(&flat[row * per_row + (size_t)q * p.N], poly->coeffs, sizeof(double) * p.N);
+    }
+  };
+  for (int i = 0; i < p.k; ++i)
+    for (int j = 0; j < p.l; ++j) put((size_t)i * p.l + j, k0->s[i][j]);
+  if (k1)
+    for (int j = 0; j < p.l; ++j) put((size_t)p.k * p.l + j, k1->s[0][j]);
+  return bsk_from_host_array(p, flat.data(), -1);
+}
+static mb200_bsk *lookup_rksk(TRLWE_KS_Key key) {
+  MB_REQUIRE(key != nullptr, "TRLWE_KS_Key is NULL");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_rksk_cache.find((const void *)key->s);
+    if (it != g_rksk_cache.end()) return it->second;
   }
-  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
-  u64 *d_acc = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * count * W);
-  pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, 2 * p.l, count, st);
-  std::vector<int> idx(lo);
-  for (int i = 0; i < lo; ++i) idx[i] = i * slot;
-  const int n_tl = count * lo;                                   // TLWEs [count][l][kN+1]
-  u64 *d_tl = (u64 *)t_scratch[S_MISC].dev(sizeof(u64) * (size_t)n_tl * (p.k * p.N + 1));
-  mb200_extract_dev((uint64_t *)d_tl, (const uint64_t *)d_acc, idx.data(), lo, p.N, p.k, count, st);
-  // key switches write straight into the TRGSW layout [count][2l][Wo]: private rows first, packing rows after
-  // -> two strided passes: outputs of ciphertext c, level i at ((c*2l) + i) and ((c*2l) + l + i)
-  u64 *d_ks = (u64 *)t_scratch[S_KS].dev(sizeof(u64) * (size_t)2 * n_tl * Wo);
-  table_ks_trlwe_dev(ga, 1, d_ks, d_tl, n_tl, st);                           // trlwe_priv_keyswitch     -> samples[i]
-  table_ks_trlwe_dev(gb, 0, d_ks + (size_t)n_tl * Wo, d_tl, n_tl, st);       // trlwe_packing1_keyswitch -> samples[l+i]
-  for (int half = 0; half < 2; ++half)
-    MB_CHECK(cudaMemcpy2DAsync(d_out + (size_t)half * lo * Wo, sizeof(u64) * 2 * lo * Wo,
-                               d_ks + (size_t)half * n_tl * Wo, sizeof(u64) * lo * Wo, sizeof(u64) * lo * Wo, count,
-                               cudaMemcpyDeviceToDevice, st));
+  mb200_bsk *b = rksk_build(key, nullptr);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_rksk_cache[(const void *)key->s] = b;
+  return b;
+}
+static mb200_bsk *lookup_rksk_pair(TRLWE_KS_Key *keys) {
+  MB_REQUIRE(keys != nullptr && keys[0] != nullptr && keys[1] != nullptr, "TRLWE_KS_Key pair is NULL");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_rksk_cache.find((const void *)keys);
+    if (it != g_rksk_cache.end()) return it->second;
+  }
+  mb200_bsk *b = rksk_build(keys[0], keys[1]);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_rksk_cache[(const void *)keys] = b;
+  return b;
+}
+// mode 1: trlwe_keyswitch, mode 2: trlwe_priv_keyswitch_2; d_out may alias d_in
+static void trlwe_fft_ks_dev(mb200_bsk *set, int mode, u64 *d_out, const u64 *d_in, int count, cudaStream_t st) {
+  if (count <= 0) return;
+  mb::BlindRotateLaunch a{};
+  a.bsk = set; a.tv = d_in; a.tv_count = count > 1 ? count : 1; a.size = 1; a.out = d_out; a.count = count;
+  a.direct = 1; a.sel_const = 0; a.ks_mode = mode;
+  mb::launch_blind_rotate_generic(a, st);
+  g_last_kernel = "generic";
+}
+static void trlwe_fft_ks_batch(TRLWE *out, TRLWE *in, mb200_bsk *set, int mode, int count) {
+  if (count <= 0) return;
+  const mb::Params &p = set->p;
+  cudaStream_t st = mb::default_stream();
+  const size_t W = (size_t)(p.k + 1) * p.N, bytes = sizeof(u64) * (size_t)count * W;
+  u64 *h_in = (u64 *)t_scratch[S_MID].host(bytes), *d_in = (u64 *)t_scratch[S_MID].dev(bytes);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(bytes), *d_out = (u64 *)t_scratch[S_OUT].dev(bytes);
+  gather_trlwe(h_in, in, count, p.k, p.N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, st));
+  trlwe_fft_ks_dev(set, mode, d_out, d_in, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(out, h_out, count, p.k, p.N);
+}
+void trlwe_keyswitch_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key ks_key, int count) {
+  trlwe_fft_ks_batch(out, in, lookup_rksk(ks_key), 1, count);
+}
+void trlwe_priv_keyswitch_2_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key *ks_key, int count) {
+  trlwe_fft_ks_batch(out, in, lookup_rksk_pair(ks_key), 2, count);
 }
 
-/* circuit_bootstrap_2 (bootstrap.c:324-345): one blind rotation of the packed test vector
- * (0,..,0, h_0,..,h_{l-1}), l extractions at i*N/(2l), then per level the private key switch (rows 0..l-1
- * of the TRGSW) and the packing key switch (rows l..2l-1). */
-void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count) {
+// ---- circuit bootstraps (bootstrap.c:309-366): device-side core shared by the handle and the flat entry points
+//   variant 1  circuit_bootstrap    l_out functional bootstraps (LUT {0, h_i}, torus_base 2), both table key switches
+//   variant 2  circuit_bootstrap_2  ONE blind rotation of the packed LUT (0,..,0, h_0,..,h_{l-1}), l extractions
+//   variant 3  circuit_bootstrap_3  as 2, but the private rows come from the FFT key switch of the packing rows
+// d_out: [count][2*l_out][Wo] (rows 0..l-1 private, l..2l-1 packing).
+static void circuit_bootstrap_core(int variant, mb200_bsk *bsk, GkskDev *ga, mb200_bsk *ga2, GkskDev *gb, u64 *d_out,
+                                   const u64 *d_in, int lo, int Bgo, int count, cudaStream_t st) {
+  const mb::Params &p = bsk->p;
+  MB_REQUIRE(p.k == 1, "circuit bootstrap: k = 1 only");
+  MB_REQUIRE(variant == 1 || lo == p.l, "circuit_bootstrap_%d: needs out->l == key->l (the reference indexes the LUT with both)", variant);
+  MB_REQUIRE(gb->n_in == p.k * p.N && (!ga || ga->n_in == p.k * p.N), "circuit bootstrap: key switch input dimension mismatch");
+  MB_REQUIRE(!ga || (ga->N == gb->N && ga->k == gb->k), "circuit bootstrap: the two key switches must target the same TRLWE shape");
+  MB_REQUIRE(!ga2 || (ga2->p.N == gb->N && ga2->p.k == gb->k), "circuit_bootstrap_3: the private key switch must act on the packing output shape");
+  MB_REQUIRE(lo >= 1 && lo * Bgo < 64 && 2 * lo <= p.N, "circuit bootstrap: output gadget l=%d Bg_bit=%d invalid", lo, Bgo);
+  const size_t W = (size_t)(p.k + 1) * p.N, Wo = (size_t)(gb->k + 1) * gb->N;
+  const int n_tl = count * lo, tlw = p.k * p.N + 1;
+  u64 *d_tl = (u64 *)t_scratch[S_MISC].dev(sizeof(u64) * (size_t)n_tl * tlw);
+  u64 *d_ks = (u64 *)t_scratch[S_KS].dev(sizeof(u64) * (size_t)2 * n_tl * Wo);
+  u64 *d_ks_a = d_ks, *d_ks_b = d_ks + (size_t)n_tl * Wo;
+  if (variant == 1) {
+    // TLWEs in [level][count] order: one bootstrap launch per level, each with its own 2-slot test vector
+    const size_t tv_b = sizeof(u64) * W * lo;
+    u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+    memset(h_tv, 0, tv_b);
+    for (int i = 0; i < lo; ++i)                    // trlwe_torus_packing(tv, {0, h_i}, 2)  (bootstrap.c:314-315)
+      for (int c = p.N / 2; c < p.N; ++c) h_tv[(size_t)i * W + (size_t)p.k * p.N + c] = 1ull << (64 - (i + 1) * Bgo);
+    MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < lo; ++i)
+      pbs_dev_impl(bsk, d_tl + (size_t)i * count * tlw, 1, d_tv + (size_t)i * W, 1, d_in, 2, count, st);
+  } else {
+    const size_t tv_b = sizeof(u64) * W;
+    u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+    // trlwe_torus_packing(tv, lut, 2l) with lut[i] = 0, lut[l+i] = 2^(64-(i+1)*Bg_out)  (bootstrap.c:330-334)
+    memset(h_tv, 0, tv_b);
+    const int slot = p.N / (2 * lo);
+    for (int i = 0; i < p.N; ++i) {
+      const int s_ = i / slot;
+      h_tv[(size_t)p.k * p.N + i] = (s_ >= lo && s_ < 2 * lo) ? (1ull << (64 - (s_ - lo + 1) * Bgo)) : 0ull;
+    }
+    MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+    u64 *d_acc = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * count * W);
+    pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, 2 * p.l, count, st);
+    std::vector<int> idx(lo);
+    for (int i = 0; i < lo; ++i) idx[i] = i * slot;
+    mb200_extract_dev((uint64_t *)d_tl, (const uint64_t *)d_acc, idx.data(), lo, p.N, p.k, count, st);   // [count][l]
+  }
+  table_ks_trlwe_dev(gb, 0, d_ks_b, d_tl, n_tl, st);                     // trlwe_packing1_keyswitch -> samples[l+i]
+  if (variant == 3) trlwe_fft_ks_dev(ga2, 2, d_ks_a, d_ks_b, n_tl, st);  // trlwe_priv_keyswitch_2   -> samples[i]
+  else table_ks_trlwe_dev(ga, 1, d_ks_a, d_tl, n_tl, st);                // trlwe_priv_keyswitch     -> samples[i]
+  // into the TRGSW layout [count][2l][Wo]
+  for (int half = 0; half < 2; ++half) {
+    const u64 *src = half ? d_ks_b : d_ks_a;
+    if (variant == 1) {
+      for (int i = 0; i < lo; ++i)
+        MB_CHECK(cudaMemcpy2DAsync(d_out + ((size_t)half * lo + i) * Wo, sizeof(u64) * 2 * lo * Wo,
+                                   src + (size_t)i * count * Wo, sizeof(u64) * Wo, sizeof(u64) * Wo, count,
+                                   cudaMemcpyDeviceToDevice, st));
+    } else {
+      MB_CHECK(cudaMemcpy2DAsync(d_out + (size_t)half * lo * Wo, sizeof(u64) * 2 * lo * Wo, src, sizeof(u64) * lo * Wo,
+                                 sizeof(u64) * lo * Wo, count, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+}
+
+static void circuit_bootstrap_handles(int variant, TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska,
+                                      TRLWE_KS_Key *kska2, Generic_KS_Key kskb, int count) {
   if (count <= 0) return;
   mb200_bsk *bsk = lookup_bsk(key);
-  GkskDev *ga = lookup_gksk(kska), *gb = lookup_gksk(kskb);
+  GkskDev *ga = kska ? lookup_gksk(kska) : nullptr, *gb = lookup_gksk(kskb);
+  mb200_bsk *ga2 = kska2 ? lookup_rksk_pair(kska2) : nullptr;
   const mb::Params &p = bsk->p;
   const int lo = out[0]->l, Bgo = out[0]->Bg_bit;
-  MB_REQUIRE(lo == p.l, "circuit_bootstrap_2: needs out->l == key->l (the reference indexes the LUT with both)");
   cudaStream_t st = mb::default_stream();
-  const size_t Wo = (size_t)(ga->k + 1) * ga->N;
+  const size_t Wo = (size_t)(gb->k + 1) * gb->N;
   const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), out_b = sizeof(u64) * (size_t)count * 2 * lo * Wo;
   u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
   gather_tlwe(h_in, in, count, p.n);
   MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
-  circuit_bootstrap_core(bsk, ga, gb, d_out, d_in, Bgo, count, st);
+  circuit_bootstrap_core(variant, bsk, ga, ga2, gb, d_out, d_in, lo, Bgo, count, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
-  for (int c = 0; c < count; ++c) scatter_trlwe(out[c]->samples, h_out + (size_t)c * 2 * lo * Wo, 2 * lo, ga->k, ga->N);
+  for (int c = 0; c < count; ++c) scatter_trlwe(out[c]->samples, h_out + (size_t)c * 2 * lo * Wo, 2 * lo, gb->k, gb->N);
+}
+void circuit_bootstrap_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count) {
+  circuit_bootstrap_handles(1, out, in, key, kska, nullptr, kskb, count);
+}
+void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb, int count) {
+  circuit_bootstrap_handles(2, out, in, key, kska, nullptr, kskb, count);
+}
+void circuit_bootstrap_3_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb, int count) {
+  circuit_bootstrap_handles(3, out, in, key, nullptr, kska, kskb, count);
 }
 
 mb200_gksk_t mb200_gksk_from_host(const uint64_t *h_rows, int n_in, int include_b, int N, int t, int base_bit) {
@@ -1091,7 +1208,8 @@ void mb200_trlwe_ks_dev(mb200_gksk_t ksk, uint64_t *d_out, const uint64_t *d_in,
 void mb200_circuit_bootstrap_dev(mb200_bsk_t bsk, mb200_gksk_t kska, mb200_gksk_t kskb, uint64_t *d_out_trgsw,
                                  const uint64_t *d_in, int Bg_bit_out, int count, void *stream) {
   if (count <= 0) return;
-  circuit_bootstrap_core(bsk, kska, kskb, (u64 *)d_out_trgsw, (const u64 *)d_in, Bg_bit_out, count, as_stream(stream));
+  circuit_bootstrap_core(2, bsk, kska, nullptr, kskb, (u64 *)d_out_trgsw, (const u64 *)d_in, bsk->p.l, Bg_bit_out, count,
+                         as_stream(stream));
 }
 
 // ---- drop-in single-ciphertext entry points (reference names) ------------------------------------------
@@ -1116,6 +1234,38 @@ void trlwe_packing1_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key) { trlwe
 void trlwe_priv_keyswitch(TRLWE out, TLWE in, Generic_KS_Key ks_key) { trlwe_priv_keyswitch_batch(&out, &in, ks_key, 1); }
 void circuit_bootstrap_2(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb) {
   circuit_bootstrap_2_batch(&out, &in, key, kska, kskb, 1);
+}
+void circuit_bootstrap(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key kska, Generic_KS_Key kskb) {
+  circuit_bootstrap_batch(&out, &in, key, kska, kskb, 1);
+}
+void circuit_bootstrap_3(TRGSW out, TLWE in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb) {
+  circuit_bootstrap_3_batch(&out, &in, key, kska, kskb, 1);
+}
+void trlwe_keyswitch(TRLWE out, TRLWE in, TRLWE_KS_Key ks_key) { trlwe_keyswitch_batch(&out, &in, ks_key, 1); }
+void trlwe_priv_keyswitch_2(TRLWE out, TRLWE in, TRLWE_KS_Key *ks_key) { trlwe_priv_keyswitch_2_batch(&out, &in, ks_key, 1); }
+void mb200_register_trlwe_ks_key(TRLWE_KS_Key key) { (void)lookup_rksk(key); }
+void mb200_register_trlwe_priv_ks_key(TRLWE_KS_Key *keys) { (void)lookup_rksk_pair(keys); }
+static void release_rksk(const void *cache_key) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_rksk_cache.find(cache_key);
+  if (it == g_rksk_cache.end()) return;
+  mb200_bsk_free(it->second);
+  g_rksk_cache.erase(it);
+}
+void mb200_release_trlwe_ks_key(TRLWE_KS_Key key) { if (key) release_rksk((const void *)key->s); }
+void mb200_release_trlwe_priv_ks_key(TRLWE_KS_Key *keys) { release_rksk((const void *)keys); }
+void mb200_trlwe_fft_ks_dev(mb200_bsk_t row_set, int mode, uint64_t *d_out, const uint64_t *d_in, int count, void *stream) {
+  MB_REQUIRE(mode == 1 || mode == 2, "mb200_trlwe_fft_ks_dev: mode must be 1 (trlwe_keyswitch) or 2 (trlwe_priv_keyswitch_2)");
+  trlwe_fft_ks_dev(row_set, mode, (u64 *)d_out, (const u64 *)d_in, count, as_stream(stream));
+}
+void mb200_circuit_bootstrap_variant_dev(int variant, mb200_bsk_t bsk, mb200_gksk_t kska, mb200_bsk_t kska_fft,
+                                         mb200_gksk_t kskb, uint64_t *d_out_trgsw, const uint64_t *d_in, int l_out,
+                                         int Bg_bit_out, int count, void *stream) {
+  MB_REQUIRE(variant >= 1 && variant <= 3, "circuit bootstrap variant %d unknown", variant);
+  MB_REQUIRE(variant == 3 ? kska_fft != nullptr : kska != nullptr, "circuit bootstrap variant %d: private key switch key missing", variant);
+  if (count <= 0) return;
+  circuit_bootstrap_core(variant, bsk, variant == 3 ? nullptr : kska, variant == 3 ? kska_fft : nullptr, kskb,
+                         (u64 *)d_out_trgsw, (const u64 *)d_in, l_out, Bg_bit_out, count, as_stream(stream));
 }
 void mb200_register_generic_ks_key(Generic_KS_Key key) { (void)lookup_gksk(key); }
 void mb200_release_generic_ks_key(Generic_KS_Key key) {

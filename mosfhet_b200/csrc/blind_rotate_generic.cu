@@ -41,6 +41,7 @@ struct GenArgs {
   const int *dft_conj;
   const u64 *sub, *add;
   int sel_const;
+  int ks_mode;
 };
 
 // in-place radix-2 DIF, positive exponent, `nb` polynomials of M complex points; output bit-reversed
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
     const int p = c / N, i = c - p * N;
     u64 v = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
     if (sub) v -= sub[c];                            // CMUX operand in2 - in1 (trlwe_sub, vertical_packing.c:27)
+    if (A.ks_mode == 2 && p == k) v = 0ull - v;      // trlwe_priv_keyswitch_2 switches -b (keyswitch.c:55)
     acc[c] = v;
   }
   __syncthreads();
@@ -139,8 +141,10 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
 
     for (int c = threadIdx.x; c < polys * Mp; c += blockDim.x) { are[c] = 0.0; aim[c] = 0.0; }
 
-    for (int r0 = 0; r0 < rows; r0 += A.rows_batch) {
-      const int nb = min(A.rows_batch, rows - r0);
+    // trlwe_keyswitch decomposes the mask polynomials only (keyswitch.c:176-182): the rows of b are not swept
+    const int rows_used = A.ks_mode == 1 ? k * l : rows;
+    for (int r0 = 0; r0 < rows_used; r0 += A.rows_batch) {
+      const int nb = min(A.rows_batch, rows_used - r0);
       // -- rotate-minus-one, decompose, fold, twist -> FFT buffers
       for (int c = threadIdx.x; c < nb * M; c += blockDim.x) {
         const int rb = c / M, j = c - rb * M;
@@ -217,7 +221,13 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
   } else {
     u64 *o = A.out + (size_t)ct * polys * N;
     const u64 *add = A.add ? A.add + (size_t)ct * polys * N : nullptr;   // CMUX: + in1 (trlwe_add, :30)
-    for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = add ? acc[c] + add[c] : acc[c];
+    if (A.ks_mode == 1) {          // out = (0, in.b) - sum  (keyswitch.c:184-186)
+      for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = (c >= k * N ? tv[c] : 0ull) - acc[c];
+    } else if (A.ks_mode == 2) {   // both halves are (0, 0) - sum, added (keyswitch.c:56-61)
+      for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = 0ull - acc[c];
+    } else {
+      for (int c = threadIdx.x; c < polys * N; c += blockDim.x) o[c] = add ? acc[c] + add[c] : acc[c];
+    }
   }
 }
 
@@ -249,6 +259,7 @@ void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st) {
   g.N = p.N; g.k = p.k; g.l = p.l; g.Bg_bit = p.Bg_bit; g.rows_batch = rb;
   g.direct = a.direct; g.sel = a.sel; g.dft_out = a.dft_out; g.dft_perm = a.dft_perm; g.dft_conj = a.dft_conj;
   g.sub = a.sub; g.add = a.add; g.sel_const = a.direct ? a.sel_const : -1;
+  g.ks_mode = a.direct ? a.ks_mode : 0;
   int threads = p.N / 2;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;

@@ -94,6 +94,10 @@ struct BlindRotateLaunch {
   const u64 *sub;       // [count][(k+1)*N] or nullptr
   const u64 *add;       // [count][(k+1)*N] or nullptr (may alias `out`)
   int sel_const;        // >= 0: every ciphertext uses TRGSW number sel_const (no `sel` array)
+  // FFT-based TRLWE key switches, direct mode only (the key is held as a TRGSW-shaped row set, l = t, Bg_bit = base_bit):
+  //   1: trlwe_keyswitch (keyswitch.c:162-193)        out = (0, in.b) - sum over the mask rows only
+  //   2: trlwe_priv_keyswitch_2 (keyswitch.c:52-63)   out = -(rows (.) (in.a, -in.b))
+  int ks_mode;
 };
 
 void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);

@@ -502,3 +502,81 @@ void oracle_circuit_bootstrap_2(Torus *out_trgsw, const Torus *in_tlwe, const do
   }
   free(tv); free(acc); free(tl);
 }
+
+/* keyswitch.c:162-193 trlwe_keyswitch: out = (0, in.b) - sum_{i<k_in, j<t} FFT(Dec_j(in.a[i])) * KSK[i][j]
+ * ksk: natural-slot-order doubles [k_in][t][k_out+1][N]; in has k_in mask polynomials, out k_out. */
+void oracle_trlwe_keyswitch(Torus *out, const Torus *in, const double *ksk, int N, int k_in, int k_out, int t,
+                            int base_bit, int mode) {
+  int64_t *dec = (int64_t *)malloc(sizeof(int64_t) * N);
+  double *dec_dft = (double *)malloc(sizeof(double) * N);
+  double *acc = (double *)calloc((size_t)(k_out + 1) * N, sizeof(double));
+  Torus *as = (Torus *)malloc(sizeof(Torus) * (k_out + 1) * N);
+  Torus *b = (Torus *)malloc(sizeof(Torus) * N);
+  memcpy(b, in + (size_t)k_in * N, sizeof(Torus) * N);              /* in may alias out (keyswitch.c:57, 60) */
+  for (int i = 0; i < k_in; i++) {
+    for (int j = 0; j < t; j++) {
+      oracle_decompose_i(dec, in + (size_t)i * N, N, base_bit, t, j);
+      oracle_int_to_dft(dec_dft, dec, N);
+      const double *row = ksk + (size_t)(i * t + j) * (k_out + 1) * N;
+      for (int q = 0; q <= k_out; q++) dft_mul(acc + (size_t)q * N, row + (size_t)q * N, dec_dft, N, 1);
+    }
+  }
+  oracle_trlwe_from_dft(as, acc, N, k_out, mode);
+  for (int q = 0; q < k_out; q++)
+    for (int c = 0; c < N; c++) out[(size_t)q * N + c] = 0 - as[(size_t)q * N + c];
+  for (int c = 0; c < N; c++) out[(size_t)k_out * N + c] = b[c] - as[(size_t)k_out * N + c];
+  free(dec); free(dec_dft); free(acc); free(as); free(b);
+}
+
+/* keyswitch.c:52-63 trlwe_priv_keyswitch_2 (k = 1): ksk2 = [2][t][2][N], [0] switches a, [1] switches -b */
+void oracle_trlwe_priv_keyswitch_2(Torus *out, const Torus *in, const double *ksk2, int N, int t, int base_bit,
+                                   int mode) {
+  const size_t key_sz = (size_t)t * 2 * N;
+  Torus *tmp = (Torus *)calloc((size_t)2 * N, sizeof(Torus));
+  Torus *o = (Torus *)calloc((size_t)2 * N, sizeof(Torus));
+  for (int c = 0; c < N; c++) { tmp[c] = 0 - in[N + c]; o[c] = in[c]; }
+  oracle_trlwe_keyswitch(tmp, tmp, ksk2 + key_sz, N, 1, 1, t, base_bit, mode);
+  oracle_trlwe_keyswitch(o, o, ksk2, N, 1, 1, t, base_bit, mode);
+  for (int c = 0; c < 2 * N; c++) out[c] = o[c] + tmp[c];
+  free(tmp); free(o);
+}
+
+/* bootstrap.c:309-322 circuit_bootstrap: one functional bootstrap (torus_base 2, LUT {0, h_i}) per level */
+void oracle_circuit_bootstrap(Torus *out_trgsw, const Torus *in_tlwe, const double *bsk, const Torus *kska,
+                              const Torus *kskb, int n, int N, int k, int l, int Bg_bit, int l_out, int Bg_out,
+                              int t, int base_bit, int mode) {
+  const size_t W = (size_t)(k + 1) * N;
+  Torus *tv = (Torus *)calloc(W, sizeof(Torus));
+  Torus *tl = (Torus *)malloc(sizeof(Torus) * (k * N + 1));
+  for (int i = 0; i < l_out; i++) {
+    for (int c = 0; c < N; c++) tv[(size_t)k * N + c] = (c >= N / 2) ? (1ULL << (64 - (i + 1) * Bg_out)) : 0;
+    oracle_functional_bootstrap(tl, tv, in_tlwe, bsk, n, N, k, l, Bg_bit, 2, mode);
+    oracle_table_keyswitch_trlwe(out_trgsw + (size_t)i * W, tl, kska, k * N, 1, N, k, t, base_bit);
+    oracle_table_keyswitch_trlwe(out_trgsw + (size_t)(l_out + i) * W, tl, kskb, k * N, 0, N, k, t, base_bit);
+  }
+  free(tv); free(tl);
+}
+
+/* bootstrap.c:347-366 circuit_bootstrap_3 (k = 1): packing key switch, then the FFT-based private one */
+void oracle_circuit_bootstrap_3(Torus *out_trgsw, const Torus *in_tlwe, const double *bsk, const double *kska2,
+                                const Torus *kskb, int n, int N, int l, int Bg_bit, int Bg_out, int t_a,
+                                int base_bit_a, int t_b, int base_bit_b, int mode) {
+  const int k = 1;
+  const size_t W = (size_t)(k + 1) * N;
+  const int slot = N / (2 * l);
+  Torus *tv = (Torus *)calloc(W, sizeof(Torus));
+  Torus *acc = (Torus *)malloc(sizeof(Torus) * W);
+  Torus *tl = (Torus *)malloc(sizeof(Torus) * (k * N + 1));
+  for (int i = 0; i < N; i++) {
+    const int s = i / slot;
+    tv[(size_t)k * N + i] = (s >= l && s < 2 * l) ? (1ULL << (64 - (s - l + 1) * Bg_out)) : 0;
+  }
+  oracle_functional_bootstrap_wo_extract(acc, tv, in_tlwe, bsk, n, N, k, l, Bg_bit, 2 * l, mode);
+  for (int i = 0; i < l; i++) {
+    oracle_extract_tlwe(tl, acc, N, k, i * slot);
+    oracle_table_keyswitch_trlwe(out_trgsw + (size_t)(l + i) * W, tl, kskb, k * N, 0, N, k, t_b, base_bit_b);
+    oracle_trlwe_priv_keyswitch_2(out_trgsw + (size_t)i * W, out_trgsw + (size_t)(l + i) * W, kska2, N, t_a,
+                                  base_bit_a, mode);
+  }
+  free(tv); free(acc); free(tl);
+}

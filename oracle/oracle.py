@@ -64,6 +64,10 @@ def lib():
             "oracle_multivalue_phase2": (None, [_u64p, _i32p, _u64p, _int, _int, _int, _int]),
             "oracle_table_keyswitch_trlwe": (None, [_u64p, _u64p, _u64p] + [_int] * 6),
             "oracle_circuit_bootstrap_2": (None, [_u64p, _u64p, _f64p, _u64p, _u64p] + [_int] * 9),
+            "oracle_trlwe_keyswitch": (None, [_u64p, _u64p, _f64p] + [_int] * 6),
+            "oracle_trlwe_priv_keyswitch_2": (None, [_u64p, _u64p, _f64p] + [_int] * 4),
+            "oracle_circuit_bootstrap": (None, [_u64p, _u64p, _f64p, _u64p, _u64p] + [_int] * 10),
+            "oracle_circuit_bootstrap_3": (None, [_u64p, _u64p, _f64p, _f64p, _u64p] + [_int] * 10),
             "oracle_tlwe_keyswitch": (None, [_u64p, _u64p, _u64p, _int, _int, _int, _int]),
             "oracle_tlwe_phase": (C.c_uint64, [_u64p, _u64p, _int]),
             "oracle_trlwe_phase": (None, [_u64p, _u64p, _u64p, _int, _int]),
@@ -274,6 +278,50 @@ def circuit_bootstrap_2(tlwe_in, bsk, kska, kskb, l, Bg_bit, Bg_out, base_bit, m
     t, kp1, N = kskb.shape[1], kskb.shape[3], kskb.shape[4]
     out = np.empty((2 * l, kp1, N), np.uint64)
     lib().oracle_circuit_bootstrap_2(out, tlwe_in, bsk, kska, kskb, n, N, kp1 - 1, l, Bg_bit, Bg_out, t, base_bit, mode)
+    return out
+
+
+def trlwe_keyswitch(trlwe_in, ksk, base_bit, mode=0):
+    """ksk: natural-order doubles [k_in, t, k_out+1, N] (keyswitch.c:162-193)."""
+    trlwe_in = _c(trlwe_in, np.uint64)
+    ksk = _c(ksk, np.float64)
+    k_in, t, kp1, N = ksk.shape
+    assert trlwe_in.shape == (k_in + 1, N)
+    out = np.empty((kp1, N), np.uint64)
+    lib().oracle_trlwe_keyswitch(out, trlwe_in, ksk, N, k_in, kp1 - 1, t, base_bit, mode)
+    return out
+
+
+def trlwe_priv_keyswitch_2(trlwe_in, ksk2, base_bit, mode=0):
+    """ksk2: natural-order doubles [2, t, 2, N], the pair of trlwe_new_priv_KS_key (keyswitch.c:52-63)."""
+    trlwe_in = _c(trlwe_in, np.uint64)
+    ksk2 = _c(ksk2, np.float64)
+    _, t, _, N = ksk2.shape
+    out = np.empty((2, N), np.uint64)
+    lib().oracle_trlwe_priv_keyswitch_2(out, trlwe_in, ksk2, N, t, base_bit, mode)
+    return out
+
+
+def circuit_bootstrap(tlwe_in, bsk, kska, kskb, l, Bg_bit, l_out, Bg_out, base_bit, mode=0):
+    tlwe_in = _c(tlwe_in, np.uint64)
+    bsk = _c(bsk, np.float64)
+    kska, kskb = _c(kska, np.uint64), _c(kskb, np.uint64)
+    n = tlwe_in.shape[0] - 1
+    t, kp1, N = kskb.shape[1], kskb.shape[3], kskb.shape[4]
+    out = np.empty((2 * l_out, kp1, N), np.uint64)
+    lib().oracle_circuit_bootstrap(out, tlwe_in, bsk, kska, kskb, n, N, kp1 - 1, l, Bg_bit, l_out, Bg_out, t, base_bit, mode)
+    return out
+
+
+def circuit_bootstrap_3(tlwe_in, bsk, kska2, kskb, l, Bg_bit, Bg_out, base_bit_a, base_bit_b, mode=0):
+    tlwe_in = _c(tlwe_in, np.uint64)
+    bsk = _c(bsk, np.float64)
+    kska2, kskb = _c(kska2, np.float64), _c(kskb, np.uint64)
+    n = tlwe_in.shape[0] - 1
+    t_b, N = kskb.shape[1], kskb.shape[4]
+    out = np.empty((2 * l, 2, N), np.uint64)
+    lib().oracle_circuit_bootstrap_3(out, tlwe_in, bsk, kska2, kskb, n, N, l, Bg_bit, Bg_out, kska2.shape[1], base_bit_a,
+                                     t_b, base_bit_b, mode)
     return out
 
 

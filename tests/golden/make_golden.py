@@ -242,6 +242,11 @@ def gen_cb(variant):
         "trlwe_packing1_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
         "circuit_bootstrap_2": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
         "trgsw_alloc_new_sample": (abi.TRGSW, [C.c_int, C.c_int, C.c_int, C.c_int]),
+        "trlwe_new_priv_KS_key": (C.POINTER(abi.TRLWE_KS_Key), [abi.TRLWE_Key, abi.TRLWE_Key, C.c_int, C.c_int]),
+        "trlwe_keyswitch": (None, [abi.TRLWE, abi.TRLWE, abi.TRLWE_KS_Key]),
+        "trlwe_priv_keyswitch_2": (None, [abi.TRLWE, abi.TRLWE, C.POINTER(abi.TRLWE_KS_Key)]),
+        "circuit_bootstrap": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+        "circuit_bootstrap_3": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, C.POINTER(abi.TRLWE_KS_Key), abi.Generic_KS_Key]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(R.lib, name); fn.restype, fn.argtypes = res, args
@@ -261,7 +266,13 @@ def gen_cb(variant):
     out["bsk_host"] = abi.bootstrap_key_to_flat(bk)
     out["kska"] = abi.generic_ks_key_to_flat(kska)
     out["kskb"] = abi.generic_ks_key_to_flat(kskb)
+    # FFT-based private key switch (keyswitch.c:40-63) with its own decomposition (t2 digits of base_bit2 bits)
+    t2, base_bit2 = 10, 2
+    kska2 = R.lib.trlwe_new_priv_KS_key(key_rlwe, key_rlwe, t2, base_bit2)
+    out["kska2"] = np.stack([abi.trlwe_ks_key_to_flat(kska2[i])[0] for i in range(2)])      # [2, t2, 2, N]
+    out["params2"] = np.array([t2, base_bit2], np.int32)
     ins, cbs, pk, pv, tls = [], [], [], [], []
+    cb1, cb3, rk_in, rk_out, pv2_out = [], [], [], [], []
     for m in (0, 1, 0, 1):
         c = R.tlwe_new_sample(m << 62, key_lwe)            # LWE(m/4), as tests.c:980, 998
         ins.append(abi.tlwe_to_flat(c))
@@ -273,9 +284,21 @@ def gen_cb(variant):
         ht = abi.HostTLWE(tl)
         a = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_priv_keyswitch(a.handle, ht.handle, kska); pv.append(a.polys.copy())
         b = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_packing1_keyswitch(b.handle, ht.handle, kskb); pk.append(b.polys.copy())
+        o1 = R.lib.trgsw_alloc_new_sample(l, Bg_bit, k, N)
+        R.lib.circuit_bootstrap(o1, c, bk, kska, kskb)
+        cb1.append(abi.trgsw_to_flat(o1, k))
+        o3 = R.lib.trgsw_alloc_new_sample(l, Bg_bit, k, N)
+        R.lib.circuit_bootstrap_3(o3, c, bk, kska2, kskb)
+        cb3.append(abi.trgsw_to_flat(o3, k))
+        rin = abi.HostTRLWE(rand_u64(R, (k + 1) * N).reshape(k + 1, N))     # the FFT key switches alone
+        rk_in.append(rin.polys.copy())
+        ro = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_keyswitch(ro.handle, rin.handle, kska2[0]); rk_out.append(ro.polys.copy())
+        ro = abi.HostTRLWE.zeros(k, N); R.lib.trlwe_priv_keyswitch_2(ro.handle, rin.handle, kska2); pv2_out.append(ro.polys.copy())
     out["cb_in"] = np.stack(ins); out["cb_out"] = np.stack(cbs)
     out["ks_in"] = np.stack(tls); out["priv_out"] = np.stack(pv); out["pack_out"] = np.stack(pk)
     out["cb_msgs"] = np.array([0, 1, 0, 1], np.int32)
+    out["cb1_out"] = np.stack(cb1); out["cb3_out"] = np.stack(cb3)
+    out["rks_in"] = np.stack(rk_in); out["rks_out"] = np.stack(rk_out); out["priv2_out"] = np.stack(pv2_out)
     return out
 
 

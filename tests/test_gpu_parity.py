@@ -728,25 +728,50 @@ def _trlwe_encrypt(p, rlwe_key, seed):
     return np.stack([a, a_s + p])
 
 
+def _synth_priv_fft_key(rlwe_key, t, base_bit, seed):
+    """Torus-domain rows [2t, 2, N] of the trlwe_new_priv_KS_key pair (keyswitch.c:40-50, 12-37), noise-free:
+    rows 0..t-1 encrypt (-s*s) * 2^(64-(j+1)b), rows t..2t-1 encrypt (-s) * 2^(64-(j+1)b)."""
+    N = rlwe_key.shape[0]
+    zero = np.zeros(N, np.uint64)
+    s_sq = (np.uint64(0) - O.trlwe_phase(np.stack([rlwe_key, zero]), rlwe_key)).astype(np.uint64)      # s*s
+    rows = []
+    for which, key_in in enumerate(((np.uint64(0) - s_sq).astype(np.uint64), (np.uint64(0) - rlwe_key).astype(np.uint64))):
+        for j in range(t):
+            rows.append(_trlwe_encrypt(key_in << np.uint64(64 - (j + 1) * base_bit), rlwe_key, seed + 100 * which + j))
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("variant", [2, 1, 3])
 @pytest.mark.parametrize("N,l,Bg_bit,t,base_bit", [(1024, 4, 9, 7, 4), (2048, 4, 9, 7, 4), (512, 3, 10, 10, 3)])
-def test_circuit_bootstrap_full_size(N, l, Bg_bit, t, base_bit):
+def test_circuit_bootstrap_full_size(N, l, Bg_bit, t, base_bit, variant):
     """The reference's own check (tests.c:965-1007) at full ring sizes, batched and wholly on the device:
-    LWE(m/4) -> circuit bootstrap -> TRGSW(m); TRGSW(m) (.) TRLWE(p) must decrypt to m*p within 2^58."""
+    LWE(m/4) -> circuit bootstrap -> TRGSW(m); TRGSW(m) (.) TRLWE(p) must decrypt to m*p within 2^58.
+    variant 1/2/3 = circuit_bootstrap / _2 / _3."""
     import torch
+    if variant != 2 and N != 1024:
+        pytest.skip("variants 1 and 3 share everything but the composition; one ring size is enough")
     n, count = 632, 8
     P = Params(n, N, 1, l, Bg_bit, t, base_bit, 2.0 ** -30, 2.0 ** -55)
     lwe_key = syn.binary_key(n, 11)
     rlwe_key = syn.binary_key(N, 12)
     bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=N)
-    kska = api.GenericKSKey.synthesize(rlwe_key, rlwe_key, 1, t, base_bit, 2.0 ** -55, seed=21)
     kskb = api.GenericKSKey.synthesize(rlwe_key, rlwe_key, 0, t, base_bit, 2.0 ** -55, seed=22)
+    kska = kska_fft = None
+    if variant == 3:
+        t_a, bb_a = 13, 3          # 39 bits: the rounding of a is multiplied by s*s (norm ~2^13), keyswitch.c:43-45
+        rows = _synth_priv_fft_key(rlwe_key, t_a, bb_a, 500)
+        kska_fft = api.BootstrapKey.from_torus_dev(Params(1, N, 1, t_a, bb_a, t, base_bit, 0.0, 0.0), torch_dev(rows))
+    else:
+        kska = api.GenericKSKey.synthesize(rlwe_key, rlwe_key, 1, t, base_bit, 2.0 ** -55, seed=21)
     msgs = np.arange(count) % 2
     cts = syn.tlwe_encrypt((msgs.astype(np.uint64) << np.uint64(62)), lwe_key, P.lwe_sigma, seed=13)
     d_in = torch_dev(cts)
     d_trgsw = torch.empty((count, 2 * l, 2, N), dtype=torch.int64, device="cuda")
-    api.circuit_bootstrap_dev(bsk, kska, kskb, d_trgsw, d_in, Bg_bit, count)
+    if variant == 2:
+        api.circuit_bootstrap_dev(bsk, kska, kskb, d_trgsw, d_in, Bg_bit, count)
+    else:
+        api.circuit_bootstrap_variant_dev(variant, bsk, kska, kska_fft, kskb, d_trgsw, d_in, l, Bg_bit, count)
     api.synchronize()
-    assert api.last_blind_rotate_kernel().startswith("k1")
     trgsw = to_np(d_trgsw)
     # each TRGSW row decrypts to m * h_i on the right polynomial (trgsw.c:152-168)
     for c in range(count):
@@ -772,5 +797,77 @@ def test_circuit_bootstrap_full_size(N, l, Bg_bit, t, base_bit):
         ph = O.trlwe_phase(res[c], rlwe_key)
         want = polys[c] if msgs[c] else np.zeros(N, np.uint64)
         assert sdiff(ph, want).max() <= TOL_TEST, c
-    for h in (bsk, kska, kskb, tset):
-        h.free()
+    for h in (bsk, kska, kska_fft, kskb, tset):
+        if h is not None:
+            h.free()
+
+
+def test_trlwe_fft_keyswitches_dropin(golden_cb):
+    """trlwe_keyswitch (keyswitch.c:162-193) / trlwe_priv_keyswitch_2 (keyswitch.c:52-63) through the struct
+    entry points: raw coefficients within 2^24 of the reference (tolerance as in tests/test_oracle_golden.py)."""
+    g, P = golden_cb, golden_cb["P"]
+    N, k = P["N"], P["k"]
+    t2, bb2 = (int(x) for x in g["params2"])
+    api.set_host_fft_layout(g["layout"])
+    key0 = abi.HostTRLWEKSKey(g["kska2"][0][None], bb2)
+    pair = abi.HostTRLWEKSKeyPair(g["kska2"], bb2)
+    ins = [abi.HostTRLWE(x) for x in g["rks_in"]]
+    singles = []
+    for i, cin in enumerate(ins):
+        out = abi.HostTRLWE.zeros(k, N)
+        api.trlwe_keyswitch(out, cin, key0)
+        assert sdiff(out.polys, g["rks_out"][i]).max() <= (1 << 24)
+        alias = abi.HostTRLWE(g["rks_in"][i])
+        api.trlwe_keyswitch(alias, alias, key0)                   # in place, as keyswitch.c:57, 60 call it
+        assert np.array_equal(alias.polys, out.polys)
+        out2 = abi.HostTRLWE.zeros(k, N)
+        api.trlwe_priv_keyswitch_2(out2, cin, pair)
+        assert sdiff(out2.polys, g["priv2_out"][i]).max() <= (1 << 24)
+        singles.append((out.polys.copy(), out2.polys.copy()))
+    outs = [abi.HostTRLWE.zeros(k, N) for _ in ins]
+    api.trlwe_keyswitch_batch(outs, ins, key0)
+    assert all(np.array_equal(o.polys, s[0]) for o, s in zip(outs, singles))
+    outs = [abi.HostTRLWE.zeros(k, N) for _ in ins]
+    api.trlwe_priv_keyswitch_2_batch(outs, ins, pair)
+    assert all(np.array_equal(o.polys, s[1]) for o, s in zip(outs, singles))
+    api.release_trlwe_ks_key(key0)
+    api.release_trlwe_priv_ks_key(pair)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_circuit_bootstrap_1_and_3_dropin(golden_cb, variant):
+    """circuit_bootstrap (bootstrap.c:309-322) and circuit_bootstrap_3 (bootstrap.c:347-366) against the reference's
+    outputs, every TRGSW row in phase (tolerance: see test_circuit_bootstrap_dropin)."""
+    g, P = golden_cb, golden_cb["P"]
+    N, k, l, Bg_bit = P["N"], P["k"], P["l"], P["Bg_bit"]
+    t2, bb2 = (int(x) for x in g["params2"])
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, l, Bg_bit)
+    ka = abi.HostGenericKSKey(g["kska"], P["base_bit"], 1)
+    kb = abi.HostGenericKSKey(g["kskb"], P["base_bit"], 0)
+    pair = abi.HostTRLWEKSKeyPair(g["kska2"], bb2)
+    ins = [abi.HostTLWE(x) for x in g["cb_in"]]
+    want = g["cb1_out"] if variant == 1 else g["cb3_out"]
+    singles = []
+    for c, cin in enumerate(ins):
+        out = abi.HostTRGSW(np.zeros((2 * l, k + 1, N), np.uint64), l, Bg_bit)
+        if variant == 1:
+            api.circuit_bootstrap(out, cin, hbsk, ka, kb)
+        else:
+            api.circuit_bootstrap_3(out, cin, hbsk, pair, kb)
+        got = out.flat()
+        singles.append(got)
+        for r in range(2 * l):
+            d = sdiff(O.trlwe_phase(got[r], g["rlwe_key"]), O.trlwe_phase(want[c][r], g["rlwe_key"]))
+            assert d.max() <= (1 << 57), (c, r, int(d.max()))
+    outs = [abi.HostTRGSW(np.zeros((2 * l, k + 1, N), np.uint64), l, Bg_bit) for _ in ins]
+    if variant == 1:
+        api.circuit_bootstrap_batch(outs, ins, hbsk, ka, kb)
+    else:
+        api.circuit_bootstrap_3_batch(outs, ins, hbsk, pair, kb)
+    for o, s_ in zip(outs, singles):
+        assert np.array_equal(o.flat(), s_)
+    api.release_bootstrap_key(hbsk)
+    api.release_generic_ks_key(ka)
+    api.release_generic_ks_key(kb)
+    api.release_trlwe_priv_ks_key(pair)

@@ -187,3 +187,34 @@ def test_circuit_bootstrap_2(golden_cb):
             worst.append(int(np.abs(d).max()))
     # no digit moved in most rows: those agree to the rounding of the blind rotation itself
     assert sorted(worst)[len(worst) // 2] <= (1 << 40)
+
+
+def test_trlwe_fft_keyswitches(golden_cb):
+    """trlwe_keyswitch (keyswitch.c:162-193) and trlwe_priv_keyswitch_2 (keyswitch.c:52-63): raw coefficients
+    against the reference.  Same tolerance class as one external product: t digits of base_bit bits times
+    torus-sized key values, rounded in f64 (2^24 leaves a wide margin over the ~2^15 expected at N = 64)."""
+    g = golden_cb
+    t2, bb2 = (int(x) for x in g["params2"])
+    nat = O.permute_from_host(g["kska2"], g["layout"])
+    for i in range(g["rks_in"].shape[0]):
+        got = O.trlwe_keyswitch(g["rks_in"][i], nat[0][None], bb2)
+        assert np.abs(O.signed_diff(got, g["rks_out"][i])).max() <= (1 << 24)
+        got = O.trlwe_priv_keyswitch_2(g["rks_in"][i], nat, bb2)
+        assert np.abs(O.signed_diff(got, g["priv2_out"][i])).max() <= (1 << 24)
+
+
+def test_circuit_bootstrap_1_and_3(golden_cb):
+    """circuit_bootstrap (bootstrap.c:309-322) and circuit_bootstrap_3 (bootstrap.c:347-366), rows in phase."""
+    g, P = golden_cb, golden_cb["P"]
+    t2, bb2 = (int(x) for x in g["params2"])
+    nat = O.permute_from_host(g["bsk_host"], g["layout"])
+    nat2 = O.permute_from_host(g["kska2"], g["layout"])
+    for c in range(g["cb_in"].shape[0]):
+        got1 = O.circuit_bootstrap(g["cb_in"][c], nat, g["kska"], g["kskb"], P["l"], P["Bg_bit"], P["l"], P["Bg_bit"],
+                                   P["base_bit"])
+        got3 = O.circuit_bootstrap_3(g["cb_in"][c], nat, nat2, g["kskb"], P["l"], P["Bg_bit"], P["Bg_bit"], bb2,
+                                     P["base_bit"])
+        for got, want in ((got1, g["cb1_out"][c]), (got3, g["cb3_out"][c])):
+            for r in range(2 * P["l"]):
+                d = O.signed_diff(O.trlwe_phase(got[r], g["rlwe_key"]), O.trlwe_phase(want[r], g["rlwe_key"]))
+                assert np.abs(d).max() <= (1 << 57), (c, r, int(np.abs(d).max()))
