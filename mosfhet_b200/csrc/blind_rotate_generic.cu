@@ -27,6 +27,7 @@ struct GenArgs {
   int tv_count;
   const u64 *in;
   int in_stride;
+  int in_div;
   int size;
   u64 *out;
   int extract, init_rotate;
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(512, 1) blind_rotate_generic_kernel(GenArgs A)
   double *are = fim + A.rows_batch * Mp;                             // [polys][Mp]
   double *aim = are + polys * Mp;
 
-  const u64 *in = A.in ? A.in + (size_t)ct * A.in_stride : nullptr;
-  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct : 0) * polys * N;
+  const u64 *in = A.in ? A.in + (size_t)(ct / A.in_div) * A.in_stride : nullptr;
+  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * polys * N;
 
   // ---- initial accumulator -----------------------------------------------------------------
   int rot0 = 0;
@@ -253,7 +254,7 @@ void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st) {
   }
   GenArgs g;
   g.bsk = a.bsk->d; g.tw = twiddles_for(p.N);
-  g.tv = a.tv; g.tv_count = a.tv_count; g.in = a.in; g.in_stride = a.in_stride; g.size = a.size;
+  g.tv = a.tv; g.tv_count = a.tv_count; g.in = a.in; g.in_stride = a.in_stride; g.in_div = a.in_div > 0 ? a.in_div : 1; g.size = a.size;
   g.out = a.out; g.extract = a.extract; g.init_rotate = a.init_rotate; g.prec_offset = a.prec_offset;
   g.preprocess = a.preprocess; g.kappa = a.kappa; g.theta = a.theta;
   g.N = p.N; g.k = p.k; g.l = p.l; g.Bg_bit = p.Bg_bit; g.rows_batch = rb;
@@ -333,6 +334,28 @@ void launch_dft_to_torus(u64 *out, const double *in, int N, int count, const int
   if (smem > 48 * 1024) MB_CHECK(cudaFuncSetAttribute(dft_to_torus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int threads = M / 2 < 64 ? 64 : (M / 2 > 512 ? 512 : M / 2);
   dft_to_torus_kernel<<<count, threads, smem, st>>>(out, in, N, twiddles_for(N), perm, conj);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+// position order (torus_to_dft_kernel output) -> the host FFT backend's slot order; perm/conj are indexed by
+// the resident (tiled) index idx, whose position is 8*(idx % (M/8)) + idx / (M/8)  (keys.cu)
+__global__ void pos_to_host_order_kernel(double *out, const double *in, int N, size_t npolys, const int *perm,
+                                         const int *conj) {
+  const int M = N >> 1, C8 = M >> 3;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < npolys * M; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t poly = g / M;
+    const int idx = (int)(g - poly * M);
+    const int s = ((idx % C8) << 3) + idx / C8;
+    const int h = perm[idx];
+    out[poly * N + h] = in[poly * N + s];
+    out[poly * N + M + h] = conj[idx] ? -in[poly * N + M + s] : in[poly * N + M + s];
+  }
+}
+
+void launch_pos_to_host_order(double *out, const double *in, int N, size_t npolys, const int *perm, const int *conj,
+                              cudaStream_t st) {
+  pos_to_host_order_kernel<<<sm_count() * 4, 256, 0, st>>>(out, in, N, npolys, perm, conj);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }

@@ -39,8 +39,8 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
   const int log_N2 = LOGM + 2;
   const double2 *__restrict__ TA = A.tab;              // [8][S]
   const double2 *__restrict__ TB = A.tab + 8 * S;      // [R2][8]
-  const u64 *in = A.in + (size_t)ct * A.in_stride;
-  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct : 0) * 2 * N;
+  const u64 *in = A.in + (size_t)(ct / A.in_div) * A.in_stride;
+  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
   const int Bg_bit = A.Bg_bit;
 
   int rot0 = 0;
@@ -317,7 +317,7 @@ void launch_blind_rotate_k1h(const BlindRotateLaunch &b, cudaStream_t st) {
   upload_w64();
   K1Args a;
   a.bsk = b.bsk->d; a.tab = k1h_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
-  a.in_stride = b.in_stride; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
+  a.in_stride = b.in_stride; a.in_div = b.in_div > 0 ? b.in_div : 1; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   a.count = b.count;
   const int logm = ilog2i(p.N) - 1;

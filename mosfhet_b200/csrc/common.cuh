@@ -76,6 +76,7 @@ struct BlindRotateLaunch {
   int tv_count;
   const u64 *in;        // [count][in_stride]: a[0..size) (and b at index `size` when init_rotate)
   int in_stride;
+  int in_div;           // 0/1: one input per ciphertext; r > 1: ciphertext ct reads input ct / r (and tv ct % tv_count)
   int size;             // number of blind-rotation steps (= n for a bootstrap)
   u64 *out;             // mode 0: [count][(k+1)*N] accumulator; mode 1: [count][k*N+1] TLWE (extract idx 0)
   int extract;          // 0 / 1
@@ -101,6 +102,8 @@ struct BlindRotateLaunch {
 };
 
 void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);
+void launch_pos_to_host_order(double *out, const double *in, int N, size_t npolys, const int *perm, const int *conj,
+                              cudaStream_t st);
 bool k1_supported(const Params &p);
 void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1_variant_name(const Params &p);

@@ -84,6 +84,7 @@ struct K1Args {
   int tv_count;
   const u64 *in;
   int in_stride;
+  int in_div;          // ciphertexts per input TLWE (>= 1): ct uses input ct / in_div, test vector ct % tv_count
   int size;
   u64 *out;
   int extract, init_rotate;

@@ -580,3 +580,90 @@ void oracle_circuit_bootstrap_3(Torus *out_trgsw, const Torus *in_tlwe, const do
   }
   free(tv); free(acc); free(tl);
 }
+
+/* ---------- TRGSW-accumulator bootstrap (bootstrap.c:267-306) -------------------------------------- */
+
+/* functional_bootstrap_trgsw_phase1: every row of the trivial TRGSW(1) (trgsw.c:130-142) goes through the
+ * same blind rotation (blind_rotate_trgsw is blind_rotate row by row, trgsw.c:425-431).
+ * out_torus: [(k+1)*l_out][(k+1)][N] torus rows; out_dft: the same rows through polynomial_torus_to_DFT
+ * (natural slot order), either may be NULL. */
+void oracle_functional_bootstrap_trgsw_phase1(Torus *out_torus, double *out_dft, const Torus *in_tlwe,
+                                              const double *bsk, int n, int N, int k, int l, int Bg_bit, int l_out,
+                                              int Bg_out, int torus_base, int mode) {
+  const size_t W = (size_t)(k + 1) * N;
+  const int rows = (k + 1) * l_out, log_N2 = ilog2(2 * N);
+  const Torus prec_offset = oracle_double2torus(1.0 / (4 * torus_base));
+  const int rot0 = 2 * N - (int)oracle_torus2int(in_tlwe[n] + prec_offset, log_N2);
+  Torus *triv = (Torus *)malloc(sizeof(Torus) * W), *acc = (Torus *)malloc(sizeof(Torus) * W);
+  for (int r = 0; r < rows; r++) {
+    const int q = r / l_out, i = r - q * l_out;
+    memset(triv, 0, sizeof(Torus) * W);
+    triv[(size_t)q * N] = 1ULL << (64 - (i + 1) * Bg_out);
+    for (int p = 0; p <= k; p++) oracle_mul_by_xai(acc + (size_t)p * N, triv + (size_t)p * N, N, rot0);
+    oracle_blind_rotate(acc, in_tlwe, bsk, n, N, k, l, Bg_bit, mode);
+    if (out_torus) memcpy(out_torus + (size_t)r * W, acc, sizeof(Torus) * W);
+    if (out_dft)
+      for (int p = 0; p <= k; p++) oracle_torus_to_dft(out_dft + (size_t)r * W + (size_t)p * N, acc + (size_t)p * N, N);
+  }
+  free(triv); free(acc);
+}
+
+/* functional_bootstrap_trgsw_phase2 (bootstrap.c:298-306): out = extract_0(TRGSW (.) tv) */
+void oracle_functional_bootstrap_trgsw_phase2(Torus *out_tlwe, const double *trgsw_dft, const Torus *tv, int N, int k,
+                                              int l, int Bg_bit, int mode) {
+  double *tmp = (double *)malloc(sizeof(double) * (k + 1) * N);
+  Torus *res = (Torus *)malloc(sizeof(Torus) * (k + 1) * N);
+  oracle_trgsw_mul_trlwe_dft(tmp, tv, trgsw_dft, N, k, l, Bg_bit);
+  oracle_trlwe_from_dft(res, tmp, N, k, mode);
+  oracle_extract_tlwe(out_tlwe, res, N, k, 0);
+  free(tmp); free(res);
+}
+
+/* ---------- unfolded blind rotation (bootstrap.c:23-48 key layout, 124-148 loop) --------------------- */
+
+/* The TRGSW of one group of `unfolding` key bits: su[g*2^u + 0] + sum_{j>=1} X^{round(sum of selected a)} su[g*2^u + j]
+ * (exact integer arithmetic), in the torus domain.  su: [size/u * 2^u][(k+1)l][(k+1)][N]. */
+void oracle_unfold_group(Torus *xai, const Torus *a, const Torus *su, int group, int unfolding, int N, int k, int l) {
+  const int key_exp = 1 << unfolding, log_N2 = ilog2(2 * N);
+  const size_t T = (size_t)(k + 1) * l * (k + 1) * N, npoly = (size_t)(k + 1) * l * (k + 1);
+  const Torus *base = su + (size_t)group * key_exp * T;
+  Torus *rot = (Torus *)malloc(sizeof(Torus) * N);
+  memcpy(xai, base, sizeof(Torus) * T);
+  for (int j = 1; j < key_exp; j++) {
+    Torus a_i = 0;
+    for (int u = 0, j_ = j; u < unfolding; u++, j_ >>= 1)
+      if (j_ & 1) a_i += a[group * unfolding + u];
+    const int e = (int)oracle_torus2int(a_i, log_N2);
+    for (size_t p = 0; p < npoly; p++) {
+      oracle_mul_by_xai(rot, base + (size_t)j * T + p * N, N, e);
+      for (int c = 0; c < N; c++) xai[p * N + c] += rot[c];
+    }
+  }
+  free(rot);
+}
+
+void oracle_blind_rotate_unfolded(Torus *acc, const Torus *a, const Torus *su, int size, int unfolding, int N, int k,
+                                  int l, int Bg_bit, int mode) {
+  const size_t T = (size_t)(k + 1) * l * (k + 1) * N;
+  Torus *xai = (Torus *)malloc(sizeof(Torus) * T);
+  double *xai_dft = (double *)malloc(sizeof(double) * T);
+  double *tmp = (double *)malloc(sizeof(double) * (k + 1) * N);
+  for (int g = 0; g < size / unfolding; g++) {
+    oracle_unfold_group(xai, a, su, g, unfolding, N, k, l);
+    for (size_t p = 0; p < T / N; p++) oracle_torus_to_dft(xai_dft + p * N, xai + p * N, N);
+    oracle_trgsw_mul_trlwe_dft(tmp, acc, xai_dft, N, k, l, Bg_bit);
+    oracle_trlwe_from_dft(acc, tmp, N, k, mode);
+  }
+  free(xai); free(xai_dft); free(tmp);
+}
+
+/* functional_bootstrap_wo_extract with an unfolding > 1 key (bootstrap.c:192-198) */
+void oracle_functional_bootstrap_unfolded_wo_extract(Torus *out_trlwe, const Torus *tv, const Torus *in_tlwe,
+                                                     const Torus *su, int n, int unfolding, int N, int k, int l,
+                                                     int Bg_bit, int torus_base, int mode) {
+  const int log_N2 = ilog2(2 * N);
+  const Torus prec_offset = oracle_double2torus(1.0 / (4 * torus_base));
+  const int rot0 = 2 * N - (int)oracle_torus2int(in_tlwe[n] + prec_offset, log_N2);
+  for (int p = 0; p <= k; p++) oracle_mul_by_xai(out_trlwe + (size_t)p * N, tv + (size_t)p * N, N, rot0);
+  oracle_blind_rotate_unfolded(out_trlwe, in_tlwe, su, n, unfolding, N, k, l, Bg_bit, mode);
+}

@@ -64,6 +64,11 @@ def lib():
             "oracle_multivalue_phase2": (None, [_u64p, _i32p, _u64p, _int, _int, _int, _int]),
             "oracle_table_keyswitch_trlwe": (None, [_u64p, _u64p, _u64p] + [_int] * 6),
             "oracle_circuit_bootstrap_2": (None, [_u64p, _u64p, _f64p, _u64p, _u64p] + [_int] * 9),
+            "oracle_functional_bootstrap_trgsw_phase1": (None, [_u64p, _f64p, _u64p, _f64p] + [_int] * 9),
+            "oracle_functional_bootstrap_trgsw_phase2": (None, [_u64p, _f64p, _u64p] + [_int] * 5),
+            "oracle_unfold_group": (None, [_u64p, _u64p, _u64p] + [_int] * 5),
+            "oracle_blind_rotate_unfolded": (None, [_u64p, _u64p, _u64p] + [_int] * 7),
+            "oracle_functional_bootstrap_unfolded_wo_extract": (None, [_u64p, _u64p, _u64p, _u64p] + [_int] * 8),
             "oracle_trlwe_keyswitch": (None, [_u64p, _u64p, _f64p] + [_int] * 6),
             "oracle_trlwe_priv_keyswitch_2": (None, [_u64p, _u64p, _f64p] + [_int] * 4),
             "oracle_circuit_bootstrap": (None, [_u64p, _u64p, _f64p, _u64p, _u64p] + [_int] * 10),
@@ -322,6 +327,57 @@ def circuit_bootstrap_3(tlwe_in, bsk, kska2, kskb, l, Bg_bit, Bg_out, base_bit_a
     out = np.empty((2 * l, 2, N), np.uint64)
     lib().oracle_circuit_bootstrap_3(out, tlwe_in, bsk, kska2, kskb, n, N, l, Bg_bit, Bg_out, kska2.shape[1], base_bit_a,
                                      t_b, base_bit_b, mode)
+    return out
+
+
+def functional_bootstrap_trgsw_phase1(tlwe_in, bsk, l, Bg_bit, l_out, Bg_out, torus_base, mode=0):
+    """-> (torus rows [(k+1)l_out, k+1, N], natural-order DFT rows of the same shape)  (bootstrap.c:286-296)."""
+    tlwe_in = _c(tlwe_in, np.uint64)
+    bsk = _c(bsk, np.float64)
+    n, kp1, N = bsk.shape[0], bsk.shape[2], bsk.shape[3]
+    rows = kp1 * l_out
+    out_t, out_d = np.empty((rows, kp1, N), np.uint64), np.empty((rows, kp1, N), np.float64)
+    lib().oracle_functional_bootstrap_trgsw_phase1(out_t, out_d, tlwe_in, bsk, n, N, kp1 - 1, l, Bg_bit, l_out, Bg_out,
+                                                   torus_base, mode)
+    return out_t, out_d
+
+
+def functional_bootstrap_trgsw_phase2(trgsw_dft, tv, l, Bg_bit, mode=0):
+    trgsw_dft = _c(trgsw_dft, np.float64)
+    tv = _c(tv, np.uint64)
+    kp1, N = tv.shape
+    out = np.empty((kp1 - 1) * N + 1, np.uint64)
+    lib().oracle_functional_bootstrap_trgsw_phase2(out, trgsw_dft, tv, N, kp1 - 1, l, Bg_bit, mode)
+    return out
+
+
+def unfold_group(a, su, group, unfolding, l):
+    """su: torus [groups * 2^u, (k+1)l, k+1, N] -> the group's combined TRGSW [(k+1)l, k+1, N] (bootstrap.c:132-140)."""
+    a = _c(a, np.uint64)
+    su = _c(su, np.uint64)
+    kp1, N = su.shape[2], su.shape[3]
+    out = np.empty(su.shape[1:], np.uint64)
+    lib().oracle_unfold_group(out, a, su, group, unfolding, N, kp1 - 1, l)
+    return out
+
+
+def blind_rotate_unfolded(acc, a, su, size, unfolding, l, Bg_bit, mode=0):
+    acc = _c(acc, np.uint64).copy()
+    a = _c(a, np.uint64)
+    su = _c(su, np.uint64)
+    kp1, N = acc.shape
+    lib().oracle_blind_rotate_unfolded(acc, a, su, size, unfolding, N, kp1 - 1, l, Bg_bit, mode)
+    return acc
+
+
+def functional_bootstrap_unfolded_wo_extract(tv, tlwe_in, su, unfolding, l, Bg_bit, torus_base, mode=0):
+    tv = _c(tv, np.uint64)
+    tlwe_in = _c(tlwe_in, np.uint64)
+    su = _c(su, np.uint64)
+    kp1, N = tv.shape
+    out = np.empty((kp1, N), np.uint64)
+    lib().oracle_functional_bootstrap_unfolded_wo_extract(out, tv, tlwe_in, su, tlwe_in.shape[0] - 1, unfolding, N,
+                                                          kp1 - 1, l, Bg_bit, torus_base, mode)
     return out
 
 

@@ -41,5 +41,12 @@ def golden_cb():
 
 
 @pytest.fixture
+def golden_r4():
+    g = load_golden("tiny_r4_spqlios")
+    g["unfolding"] = int(g["unfolding"])
+    return g
+
+
+@pytest.fixture
 def golden_ffnt():
     return load_golden("tiny_k1_ffnt")

@@ -302,7 +302,83 @@ def gen_cb(variant):
     return out
 
 
+def gen_r4(variant):
+    """TRGSW-accumulator bootstrap (bootstrap.c:267-306) and the unfolded blind rotation (bootstrap.c:23-48,
+    124-190) with an unfolding = 2 key, recorded from the unmodified reference."""
+    R = reflib.load(variant)
+    sig = {
+        "functional_bootstrap_trgsw_phase1": (None, [abi.TRGSW_DFT, abi.TLWE, abi.Bootstrap_Key, C.c_int]),
+        "functional_bootstrap_trgsw_phase2": (None, [abi.TLWE, abi.TRGSW_DFT, abi.TRLWE]),
+        "blind_rotate_unfolded": (None, [abi.TRLWE, C.POINTER(C.c_uint64), C.POINTER(abi.TRGSW), C.c_int, C.c_int]),
+        "multivalue_bootstrap_UBR_phase1": (None, [C.POINTER(abi.TRGSW_DFT), abi.TLWE, abi.Bootstrap_Key]),
+        "multivalue_bootstrap_UBR_phase2": (None, [abi.TLWE, abi.TRLWE, abi.TLWE, C.POINTER(abi.TRGSW_DFT), abi.Bootstrap_Key, C.c_int]),
+        "trgsw_alloc_new_DFT_sample": (abi.TRGSW_DFT, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(R.lib, name); fn.restype, fn.argtypes = res, args
+    n, N, k, l, Bg_bit, t, base_bit = 12, 64, 1, 2, 10, 4, 2
+    unfolding = 2
+    R.init_fft(N)
+    out = dict(params=np.array([n, N, k, l, Bg_bit, t, base_bit], np.int32), layout=np.int32(R.layout),
+               unfolding=np.int32(unfolding))
+    key_lwe = R.tlwe_new_binary_key(n, 2.0 ** -30)
+    key_rlwe = R.trlwe_new_binary_key(N, k, 2.0 ** -45)
+    key_ext = R.tlwe_new_binary_key(k * N, 2.0 ** -45)
+    R.trlwe_extract_tlwe_key(key_ext, key_rlwe)
+    trgsw_key = R.trgsw_new_key(key_rlwe, l, Bg_bit)
+    bk = R.new_bootstrap_key(trgsw_key, key_lwe, 1)
+    bku = R.new_bootstrap_key(trgsw_key, key_lwe, unfolding)
+    out["lwe_key"] = key_words(key_lwe.contents.s, n)
+    out["rlwe_key"] = np.stack([key_words(key_rlwe.contents.s[i].contents.coeffs, N) for i in range(k)])
+    out["ext_key"] = key_words(key_ext.contents.s, k * N)
+    out["bsk_host"] = abi.bootstrap_key_to_flat(bk)
+    n_su = (n // unfolding) * (1 << unfolding)
+    out["su"] = np.stack([abi.trgsw_to_flat(bku.contents.su[i], k) for i in range(n_su)])
+    torus_base = 4
+    lut = rand_u64(R, torus_base)
+    tvh = abi.HostTRLWE(np.stack([np.zeros(N, np.uint64), np.repeat(lut, N // torus_base)]))
+    out["lut"] = lut; out["tv"] = tvh.polys.copy()
+    ins, p1, p2, fbu, bru, ubr1, ubr2, bru_in = [], [], [], [], [], [], [], []
+    for m in (0, 1, 2, 3):
+        c = R.tlwe_new_sample(m << 61, key_lwe)                                   # m/8 as tests.c:1753 (m = 1)
+        ins.append(abi.tlwe_to_flat(c))
+        g = R.lib.trgsw_alloc_new_DFT_sample(l, Bg_bit, k, N)
+        R.lib.functional_bootstrap_trgsw_phase1(g, c, bk, torus_base)
+        p1.append(abi.trgsw_dft_to_flat(g, k))
+        o = abi.HostTLWE.zeros(k * N)
+        R.lib.functional_bootstrap_trgsw_phase2(o.handle, g, tvh.handle)
+        p2.append(o.flat())
+        # functional_bootstrap_wo_extract through the unfolding = 2 key (bootstrap.c:197)
+        w = abi.HostTRLWE.zeros(k, N)
+        R.functional_bootstrap_wo_extract(w.handle, tvh.handle, c, bku, torus_base)
+        fbu.append(w.polys.copy())
+        acc = abi.HostTRLWE(rand_u64(R, (k + 1) * N).reshape(k + 1, N))            # blind_rotate_unfolded alone
+        bru_in.append(acc.polys.copy())
+        a_in = abi.tlwe_to_flat(c)[:n].copy()
+        R.lib.blind_rotate_unfolded(acc.handle, a_in.ctypes.data_as(C.POINTER(C.c_uint64)), bku.contents.su, n, unfolding)
+        bru.append(acc.polys.copy())
+        sa = [R.lib.trgsw_alloc_new_DFT_sample(l, Bg_bit, k, N) for _ in range(n // unfolding)]
+        sa_arr = (abi.TRGSW_DFT * len(sa))(*sa)
+        R.lib.multivalue_bootstrap_UBR_phase1(sa_arr, c, bku)
+        ubr1.append(np.stack([abi.trgsw_dft_to_flat(x, k) for x in sa]))
+        o = abi.HostTLWE.zeros(k * N)
+        R.lib.multivalue_bootstrap_UBR_phase2(o.handle, tvh.handle, c, sa_arr, bku, torus_base)
+        ubr2.append(o.flat())
+    out["bru_in"] = np.stack(bru_in)
+    out["r4_in"] = np.stack(ins); out["trgsw_p1"] = np.stack(p1); out["trgsw_p2"] = np.stack(p2)
+    out["fbu_out"] = np.stack(fbu); out["bru_out"] = np.stack(bru)
+    out["ubr_p1"] = np.stack(ubr1); out["ubr_p2"] = np.stack(ubr2)
+    out["msgs"] = np.arange(4, dtype=np.int32)
+    return out
+
+
 def main():
+    if "--r4-only" in sys.argv:
+        data = gen_r4("fma")
+        path = os.path.join(HERE, "tiny_r4_spqlios.npz")
+        np.savez_compressed(path, **data)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+        return
     if "--cb-only" in sys.argv:
         data = gen_cb("fma")
         path = os.path.join(HERE, "tiny_cb_spqlios.npz")

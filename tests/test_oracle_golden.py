@@ -218,3 +218,56 @@ def test_circuit_bootstrap_1_and_3(golden_cb):
             for r in range(2 * P["l"]):
                 d = O.signed_diff(O.trlwe_phase(got[r], g["rlwe_key"]), O.trlwe_phase(want[r], g["rlwe_key"]))
                 assert np.abs(d).max() <= (1 << 57), (c, r, int(np.abs(d).max()))
+
+
+def _dft_rows_to_torus(rows_nat):
+    """Natural-order Fourier rows [..., N] -> torus rows (polynomial_DFT_to_torus)."""
+    flat = rows_nat.reshape(-1, rows_nat.shape[-1])
+    return np.stack([O.dft_to_torus(r) for r in flat]).reshape(rows_nat.shape)
+
+
+def test_trgsw_accumulator_bootstrap(golden_r4):
+    """functional_bootstrap_trgsw_phase1 / phase2 (bootstrap.c:286-306).  Phase 1 is a blind rotation of every
+    row of the trivial TRGSW(1): rows compared in phase (the Fourier-domain output is brought back to the torus
+    first); phase 2 fed with the reference's own phase-1 output is one external product (<= 2^29 raw + extract)."""
+    g, P = golden_r4, golden_r4["P"]
+    nat = O.permute_from_host(g["bsk_host"], g["layout"])
+    tol = max(TOL_PHASE, 1 << (64 - P["l"] * P["Bg_bit"] + 7))
+    for c in range(g["r4_in"].shape[0]):
+        rows_t, rows_d = O.functional_bootstrap_trgsw_phase1(g["r4_in"][c], nat, P["l"], P["Bg_bit"], P["l"], P["Bg_bit"], 4)
+        ref_t = _dft_rows_to_torus(O.permute_from_host(g["trgsw_p1"][c], g["layout"]))
+        for r in range(rows_t.shape[0]):
+            d = O.signed_diff(O.trlwe_phase(rows_t[r], g["rlwe_key"]), O.trlwe_phase(ref_t[r], g["rlwe_key"]))
+            assert np.abs(d).max() <= tol, (c, r)
+        got = O.functional_bootstrap_trgsw_phase2(O.permute_from_host(g["trgsw_p1"][c], g["layout"]), g["tv"], P["l"], P["Bg_bit"])
+        assert np.abs(O.signed_diff(got, g["trgsw_p2"][c])).max() <= (1 << 29)
+        # end to end: decrypts to LUT[m] (tests.c:1764, tolerance 2^60)
+        out = O.functional_bootstrap_trgsw_phase2(rows_d, g["tv"], P["l"], P["Bg_bit"])
+        d = (O.tlwe_phase(out, g["ext_key"]) - int(g["lut"][g["msgs"][c]])) % 2**64
+        assert abs(int(np.int64(np.uint64(d)))) <= (1 << 60)
+
+
+def test_unfolded_blind_rotation(golden_r4):
+    """bootstrap.c:124-148 with the key layout of bootstrap.c:23-48.  The per-group TRGSW is exact integer work:
+    its Fourier image (multivalue_bootstrap_UBR_phase1, :151-172) is compared after the inverse transform
+    (<= 2^16 raw: 64-bit values lose 11 bits in f64, then two transforms); the rotation itself in phase."""
+    g, P = golden_r4, golden_r4["P"]
+    u, n = g["unfolding"], P["n"]
+    tol = max(TOL_PHASE, 1 << (64 - P["l"] * P["Bg_bit"] + 7))
+    for c in range(g["r4_in"].shape[0]):
+        a = g["r4_in"][c][:n]
+        for grp in range(n // u):
+            xai = O.unfold_group(a, g["su"], grp, u, P["l"])
+            ref = _dft_rows_to_torus(O.permute_from_host(g["ubr_p1"][c][grp], g["layout"]))
+            assert np.abs(O.signed_diff(xai, ref)).max() <= (1 << 16), (c, grp)
+        got = O.blind_rotate_unfolded(g["bru_in"][c], a, g["su"], n, u, P["l"], P["Bg_bit"])
+        d = O.signed_diff(O.trlwe_phase(got, g["rlwe_key"]), O.trlwe_phase(g["bru_out"][c], g["rlwe_key"]))
+        assert np.abs(d).max() <= tol, c
+        got = O.functional_bootstrap_unfolded_wo_extract(g["tv"], g["r4_in"][c], g["su"], u, P["l"], P["Bg_bit"], 4)
+        d = O.signed_diff(O.trlwe_phase(got, g["rlwe_key"]), O.trlwe_phase(g["fbu_out"][c], g["rlwe_key"]))
+        assert np.abs(d).max() <= tol, c
+        # multivalue_bootstrap_UBR_phase2 (:174-190) == the same rotation + extract
+        ph = O.tlwe_phase(O.extract_tlwe(got, 0), g["ext_key"])
+        ph_ref = O.tlwe_phase(g["ubr_p2"][c], g["ext_key"])
+        assert abs(int(np.int64(np.uint64((ph - ph_ref) % 2**64)))) <= tol
+        assert abs(int(np.int64(np.uint64((ph - int(g["lut"][g["msgs"][c]])) % 2**64)))) <= (1 << 58)
