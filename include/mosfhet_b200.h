@@ -63,7 +63,7 @@ typedef struct _TRLWE_KS_Key {                                               /* 
 
 typedef struct _Bootstrap_Key {                                              /* mosfhet.h:129 */
   TRGSW_DFT *s;           /* s[i], i < n: Fourier-domain TRGSW of LWE key bit i (unfolding==1) */
-  TRGSW     *su;          /* torus-domain keys for unfolding > 1 (not accelerated; rejected)   */
+  TRGSW     *su;          /* su[g*2^u + j]: torus-domain keys for unfolding u > 1 (bootstrap.c:23-48) */
   int n, k, N, Bg_bit, l, unfolding;
 } *Bootstrap_Key;
 
@@ -95,6 +95,14 @@ void circuit_bootstrap(TRGSW out, TLWE in, Bootstrap_Key key, Generic_KS_Key ksk
 void circuit_bootstrap_3(TRGSW out, TLWE in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb);  /* mosfhet.h:422, bootstrap.c:347 */
 void trlwe_keyswitch(TRLWE out, TRLWE in, TRLWE_KS_Key ks_key);                                           /* mosfhet.h:375, keyswitch.c:162 (out may alias in) */
 void trlwe_priv_keyswitch_2(TRLWE out, TRLWE in, TRLWE_KS_Key *ks_key);                                   /* mosfhet.h:399, keyswitch.c:52 */
+/* TRGSW-accumulator bootstrap and unfolded blind rotation.  functional_bootstrap and
+ * functional_bootstrap_wo_extract also accept unfolding > 1 keys (bootstrap.c:197). */
+void functional_bootstrap_trgsw_phase1(TRGSW_DFT out, TLWE in, Bootstrap_Key key, int torus_base);        /* mosfhet.h:415, bootstrap.c:286 */
+void functional_bootstrap_trgsw_phase2(TLWE out, TRGSW_DFT in, TRLWE tv);                                 /* mosfhet.h:416, bootstrap.c:298 */
+void blind_rotate_unfolded(TRLWE tv, Torus *a, TRGSW *s, int size, int unfolding);                        /* mosfhet.h:410, bootstrap.c:124 */
+void multivalue_bootstrap_UBR_phase1(TRGSW_DFT *out, TLWE in, Bootstrap_Key key);                         /* mosfhet.h:431, bootstrap.c:151 */
+void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa, Bootstrap_Key key,
+                                     int torus_base);                                                     /* mosfhet.h:432, bootstrap.c:174 */
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base);             /* mosfhet.h:413, bootstrap.c:232 */
 void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base,
                                  int log_torus_base);                                                 /* mosfhet.h:414, bootstrap.c:245 */
@@ -134,6 +142,9 @@ void circuit_bootstrap_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS
 void circuit_bootstrap_3_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb, int count);
 void trlwe_keyswitch_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key ks_key, int count);
 void trlwe_priv_keyswitch_2_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key *ks_key, int count);
+void functional_bootstrap_trgsw_phase1_batch(TRGSW_DFT *out, TLWE *in, Bootstrap_Key key, int torus_base, int count);
+void functional_bootstrap_trgsw_phase2_batch(TLWE *out, TRGSW_DFT *in, TRLWE *tv, int tv_count, int count);
+void blind_rotate_unfolded_batch(TRLWE *tv, Torus **a, TRGSW *s, int size, int unfolding, int count);
 void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count);
 void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLWE **rotated_tv,
                                        int torus_base, int log_torus_base, int count);
@@ -246,6 +257,11 @@ void mb200_trlwe_fft_ks_dev(mb200_bsk_t row_set, int mode, uint64_t *d_out /* [c
 void mb200_circuit_bootstrap_variant_dev(int variant, mb200_bsk_t bsk, mb200_gksk_t kska, mb200_bsk_t kska_fft,
                                          mb200_gksk_t kskb, uint64_t *d_out_trgsw, const uint64_t *d_in, int l_out,
                                          int Bg_bit_out, int count, void *stream);
+
+/* functional_bootstrap_trgsw_phase1 without the final trgsw_to_DFT: d_out_trgsw [count][(k+1)*l_out][(k+1)N] torus
+ * rows of TRGSW(X^-phase); feed mb200_bsk_from_torus_dev + mb200_extprod_dev + mb200_extract_dev for phase 2. */
+void mb200_bootstrap_trgsw_phase1_dev(mb200_bsk_t bsk, uint64_t *d_out_trgsw, const uint64_t *d_in /* [count][n+1] */,
+                                      int l_out, int Bg_bit_out, int torus_base, int count, void *stream);
 
 /* Device-resident batch ops (inputs/outputs already in HBM; asynchronous on `stream`). */
 void mb200_pbs_dev(mb200_bsk_t bsk, uint64_t *d_out_tlwe /* [count][k*N+1] */,

@@ -33,6 +33,15 @@ PROTOTYPES = {
     "trlwe_packing1_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
     "trlwe_priv_keyswitch": (None, [abi.TRLWE, abi.TLWE, abi.Generic_KS_Key]),
     "circuit_bootstrap_2": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
+    "functional_bootstrap_trgsw_phase1": (None, [abi.TRGSW_DFT, abi.TLWE, abi.Bootstrap_Key, C.c_int]),
+    "functional_bootstrap_trgsw_phase2": (None, [abi.TLWE, abi.TRGSW_DFT, abi.TRLWE]),
+    "blind_rotate_unfolded": (None, [abi.TRLWE, _u64p, _P(abi.TRGSW), C.c_int, C.c_int]),
+    "multivalue_bootstrap_UBR_phase1": (None, [_P(abi.TRGSW_DFT), abi.TLWE, abi.Bootstrap_Key]),
+    "multivalue_bootstrap_UBR_phase2": (None, [abi.TLWE, abi.TRLWE, abi.TLWE, _P(abi.TRGSW_DFT), abi.Bootstrap_Key, C.c_int]),
+    "functional_bootstrap_trgsw_phase1_batch": (None, [_P(abi.TRGSW_DFT), _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int]),
+    "functional_bootstrap_trgsw_phase2_batch": (None, [_P(abi.TLWE), _P(abi.TRGSW_DFT), _P(abi.TRLWE), C.c_int, C.c_int]),
+    "blind_rotate_unfolded_batch": (None, [_P(abi.TRLWE), _P(_u64p), _P(abi.TRGSW), C.c_int, C.c_int, C.c_int]),
+    "mb200_bootstrap_trgsw_phase1_dev": (None, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "circuit_bootstrap": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, abi.Generic_KS_Key, abi.Generic_KS_Key]),
     "circuit_bootstrap_3": (None, [abi.TRGSW, abi.TLWE, abi.Bootstrap_Key, _P(abi.TRLWE_KS_Key), abi.Generic_KS_Key]),
     "trlwe_keyswitch": (None, [abi.TRLWE, abi.TRLWE, abi.TRLWE_KS_Key]),

@@ -220,6 +220,20 @@ class HostBootstrapKey:
         self.handle = C.pointer(self.struct)
 
 
+class HostUnfoldedBootstrapKey:
+    """A ``Bootstrap_Key`` with ``unfolding`` > 1 over a torus ``[n/u * 2^u, (k+1)*l, (k+1), N]`` uint64 array
+    (``->su``, bootstrap.c:23-48)."""
+
+    def __init__(self, su: np.ndarray, n: int, unfolding: int, k: int, l: int, Bg_bit: int):
+        su = np.ascontiguousarray(su, dtype=np.uint64)
+        assert su.shape[0] == (n // unfolding) << unfolding
+        self.n, self.N = n, su.shape[3]
+        self.trgsw = [HostTRGSW(su[i], l, Bg_bit) for i in range(su.shape[0])]
+        self.su_array = (TRGSW * len(self.trgsw))(*[g.handle for g in self.trgsw])
+        self.struct = BootstrapKeyS(None, C.cast(self.su_array, C.POINTER(TRGSW)), n, k, self.N, Bg_bit, l, unfolding)
+        self.handle = C.pointer(self.struct)
+
+
 class HostKSKey:
     """A ``TLWE_KS_Key`` over a ``[N_in, t, 2^base_bit-1, n_out+1]`` uint64 array."""
 

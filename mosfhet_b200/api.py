@@ -106,6 +106,46 @@ def blind_rotate(tv, a, s, size: int) -> None:
     lib().blind_rotate(_h(tv), a, s, size)
 
 
+def blind_rotate_unfolded(tv, a, s, size: int, unfolding: int) -> None:
+    """In place on ``tv`` (bootstrap.c:124-148).  ``s``: array of torus-domain TRGSW (``Bootstrap_Key->su``)."""
+    if isinstance(a, np.ndarray):
+        a = a.ctypes.data_as(C.POINTER(C.c_uint64))
+    lib().blind_rotate_unfolded(_h(tv), a, s, size, unfolding)
+
+
+def functional_bootstrap_trgsw_phase1(out, in_, key, torus_base: int) -> None:
+    """TLWE -> TRGSW_DFT(X^-phase) (bootstrap.c:286-296)."""
+    lib().functional_bootstrap_trgsw_phase1(_h(out), _h(in_), _h(key), torus_base)
+
+
+def functional_bootstrap_trgsw_phase2(out, in_, tv) -> None:
+    lib().functional_bootstrap_trgsw_phase2(_h(out), _h(in_), _h(tv))
+
+
+def functional_bootstrap_trgsw_phase1_batch(outs, ins, key, torus_base: int) -> None:
+    lib().functional_bootstrap_trgsw_phase1_batch(abi.handle_array(outs, abi.TRGSW_DFT), abi.handle_array(ins, abi.TLWE),
+                                                  _h(key), torus_base, len(ins))
+
+
+def functional_bootstrap_trgsw_phase2_batch(outs, ins, tvs) -> None:
+    lib().functional_bootstrap_trgsw_phase2_batch(abi.handle_array(outs, abi.TLWE), abi.handle_array(ins, abi.TRGSW_DFT),
+                                                  abi.handle_array(tvs, abi.TRLWE), len(tvs), len(ins))
+
+
+def multivalue_bootstrap_UBR_phase1(outs, in_, key) -> None:
+    """outs: n/unfolding TRGSW_DFT handles (bootstrap.c:151-172)."""
+    lib().multivalue_bootstrap_UBR_phase1(abi.handle_array(outs, abi.TRGSW_DFT), _h(in_), _h(key))
+
+
+def multivalue_bootstrap_UBR_phase2(out, tv, in_, sa, key, torus_base: int) -> None:
+    lib().multivalue_bootstrap_UBR_phase2(_h(out), _h(tv), _h(in_), abi.handle_array(sa, abi.TRGSW_DFT), _h(key), torus_base)
+
+
+def bootstrap_trgsw_phase1_dev(bsk, d_out_trgsw, d_in, l_out, Bg_bit_out, torus_base, count, stream=None):
+    lib().mb200_bootstrap_trgsw_phase1_dev(bsk.handle, _ptr(d_out_trgsw), _ptr(d_in), l_out, Bg_bit_out, torus_base, count,
+                                           _ptr(stream))
+
+
 def trgsw_mul_trlwe_DFT(out, in1, in2) -> None:
     lib().trgsw_mul_trlwe_DFT(_h(out), _h(in1), _h(in2))
 

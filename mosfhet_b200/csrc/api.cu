@@ -40,6 +40,8 @@ struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; };
 struct mb200_gksk : GkskDev {};
 namespace {
 std::map<const void *, GkskDev *> g_gksk_cache;    // keyed by Generic_KS_Key->s
+struct UbskDev { u64 *d; mb::Params p; int unfolding; };   // torus-domain key of bootstrap.c:23-48, p.n = LWE dimension
+std::map<const void *, UbskDev *> g_ubsk_cache;    // keyed by Bootstrap_Key->su
 std::map<const void *, mb200_bsk *> g_rksk_cache;  // keyed by TRLWE_KS_Key->s, or by the TRLWE_KS_Key[2] array
 
 mb::Params to_params(const mb200_params *p) {
@@ -84,7 +86,7 @@ struct Scratch {
     h = d = nullptr; hcap = dcap = 0;
   }
 };
-enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_COUNT };
+enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_UX, S_UD, S_US, S_COUNT };
 thread_local Scratch t_scratch[S_COUNT];
 
 // ---- host FFT slot order ----------------------------------------------------------------------
@@ -379,6 +381,106 @@ void pbs_dev_impl(mb200_bsk_t bsk, u64 *d_out, int extract, const u64 *d_tv, int
   run_blind_rotate(a, st);
 }
 
+// ---- unfolded blind rotation (bootstrap.c:23-48, 124-148) -----------------------------------------------
+// Every group of `unfolding` key bits costs: one integer kernel that combines the 2^u torus-domain TRGSW
+// samples with the ciphertext's own monomial rotations (unfold.cu, exact), trgsw_to_DFT of the result
+// (it depends on the ciphertext, so nothing is shared across the batch) and one external product.  This is a
+// functional path for callers holding unfolding > 1 keys; the unfolding == 1 kernels are the fast ones.
+UbskDev *ubsk_upload(TRGSW *su, int n, int unfolding, int k, int N, int l, int Bg_bit) {
+  mb::ensure_init();
+  MB_REQUIRE(unfolding >= 2 && unfolding <= 8 && n % unfolding == 0,
+             "unfolded bootstrap key: n=%d must be a multiple of unfolding=%d (2..8)", n, unfolding);
+  UbskDev *U = new UbskDev();
+  U->p = mb::Params{}; U->p.n = n; U->p.N = N; U->p.k = k; U->p.l = l; U->p.Bg_bit = Bg_bit;
+  check_bsk_params(U->p);
+  U->unfolding = unfolding;
+  const size_t n_trgsw = (size_t)(n / unfolding) << unfolding, rows = (size_t)(k + 1) * l;
+  const size_t per = rows * (k + 1) * N;
+  std::vector<u64> flat(n_trgsw * per);
+  for (size_t i = 0; i < n_trgsw; ++i) {
+    MB_REQUIRE(su[i]->l == l && su[i]->Bg_bit == Bg_bit, "unfolded key: TRGSW %zu gadget mismatch", i);
+    for (size_t r = 0; r < rows; ++r) {
+      TRLWE row = su[i]->samples[r];
+      for (int q = 0; q <= k; ++q)
+        memcpy(&flat[i * per + (r * (k + 1) + q) * N], (q < k ? row->a[q] : row->b)->coeffs, sizeof(u64) * N);
+    }
+  }
+  cudaStream_t st = mb::default_stream();
+  MB_CHECK(cudaMalloc(&U->d, sizeof(u64) * flat.size()));
+  MB_CHECK(cudaMemcpyAsync(U->d, flat.data(), sizeof(u64) * flat.size(), cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  return U;
+}
+UbskDev *lookup_ubsk(Bootstrap_Key key) {
+  MB_REQUIRE(key != nullptr && key->su != nullptr, "Bootstrap_Key (unfolding > 1) has no torus-domain key");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ubsk_cache.find((const void *)key->su);
+    if (it != g_ubsk_cache.end()) return it->second;
+  }
+  UbskDev *U = ubsk_upload(key->su, key->n, key->unfolding, key->k, key->N, key->l, key->Bg_bit);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_ubsk_cache[(const void *)key->su] = U;
+  return U;
+}
+
+// d_acc [count][(k+1)N] in place; d_a [count][a_stride] holds the mask words
+void blind_rotate_unfolded_core(UbskDev *U, u64 *d_acc, const u64 *d_a, int a_stride, int size, int count, cudaStream_t st) {
+  const mb::Params &p = U->p;
+  const int u = U->unfolding;
+  MB_REQUIRE(size % u == 0 && size <= p.n, "blind_rotate_unfolded: size=%d must be a multiple of unfolding=%d and <= n=%d", size, u, p.n);
+  const int npoly = (p.k + 1) * p.l * (p.k + 1), groups = size / u;
+  const size_t W = (size_t)(p.k + 1) * p.N, per = (size_t)npoly * p.N;
+  const int chunk = count < 512 ? count : 512;                  // bounds the three scratch buffers (<= 3 x 134 MB at Level 2)
+  u64 *d_xai = (u64 *)t_scratch[S_UX].dev(sizeof(u64) * chunk * per);
+  double *d_dft = (double *)t_scratch[S_UD].dev(sizeof(double) * chunk * per);
+  double2 *d_set = (double2 *)t_scratch[S_US].dev(sizeof(double) * chunk * per);
+  int *h_sel = (int *)t_scratch[S_MISC2].host(sizeof(int) * chunk), *d_sel = (int *)t_scratch[S_MISC2].dev(sizeof(int) * chunk);
+  for (int i = 0; i < chunk; ++i) h_sel[i] = i;
+  MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * chunk, cudaMemcpyHostToDevice, st));
+  mb200_bsk tmp;
+  tmp.p = p; tmp.d = d_set; tmp.owned = false;
+  for (int c0 = 0; c0 < count; c0 += chunk) {
+    const int cc = count - c0 < chunk ? count - c0 : chunk;
+    tmp.p.n = cc;
+    for (int g = 0; g < groups; ++g) {
+      mb::launch_unfold(d_xai, U->d, d_a + (size_t)c0 * a_stride, a_stride, p.N, npoly, u, g, 1, cc, st);
+      mb::bsk_from_torus(&tmp, d_xai, d_dft, st);               // trgsw_to_DFT (bootstrap.c:141)
+      mb::BlindRotateLaunch a{};
+      a.bsk = &tmp; a.tv = d_acc + (size_t)c0 * W; a.tv_count = cc > 1 ? cc : 1; a.size = 1; a.out = d_acc + (size_t)c0 * W;
+      a.count = cc; a.direct = 1; a.sel = d_sel; a.sel_const = -1;
+      mb::launch_blind_rotate_generic(a, st);                   // trgsw_mul_trlwe_DFT + trlwe_from_DFT (:142-143)
+    }
+  }
+  g_last_kernel = "generic-unfolded";
+}
+
+// acc = tv * X^(2N - round((b + 1/(4*torus_base)) * 2N)) for every ciphertext: the generic kernel with zero steps
+void initial_rotation_dev(const mb::Params &p, u64 *d_acc, const u64 *d_tv, int tv_count, const u64 *d_in, int torus_base,
+                          int count, cudaStream_t st) {
+  mb200_bsk dummy;
+  dummy.p = p; dummy.d = nullptr; dummy.owned = false;
+  mb::BlindRotateLaunch a{};
+  a.bsk = &dummy; a.tv = d_tv; a.tv_count = tv_count; a.in = d_in + p.n; a.in_stride = p.n + 1; a.size = 0;
+  a.out = d_acc; a.extract = 0; a.init_rotate = 1; a.prec_offset = prec_offset_for(torus_base); a.count = count;
+  mb::launch_blind_rotate_generic(a, st);
+}
+
+// functional_bootstrap[_wo_extract] through an unfolding > 1 key (bootstrap.c:192-206)
+void pbs_unfolded_core(UbskDev *U, u64 *d_out, int extract, const u64 *d_tv, int tv_count, const u64 *d_in, int torus_base,
+                       int count, cudaStream_t st) {
+  const mb::Params &p = U->p;
+  const size_t W = (size_t)(p.k + 1) * p.N;
+  u64 *d_acc = extract ? (u64 *)t_scratch[S_MID].dev(sizeof(u64) * count * W) : d_out;
+  initial_rotation_dev(p, d_acc, d_tv, tv_count, d_in, torus_base, count, st);
+  blind_rotate_unfolded_core(U, d_acc, d_in, p.n + 1, p.n, count, st);
+  if (extract) {
+    int *d_idx = (int *)t_scratch[S_MISC].dev(sizeof(int));
+    MB_CHECK(cudaMemsetAsync(d_idx, 0, sizeof(int), st));
+    mb::launch_extract(d_out, d_acc, d_idx, 1, p.N, p.k, count, st);
+  }
+}
+
 // ---- handle-tree gather / scatter -----------------------------------------------------------------
 void gather_tlwe(u64 *dst, TLWE *in, int count, int n) {
   for (int i = 0; i < count; ++i) {
@@ -453,6 +555,8 @@ void mb200_shutdown(void) {
   g_gksk_cache.clear();
   for (auto &kv : g_rksk_cache) { if (kv.second->owned) cudaFree(kv.second->d); delete kv.second; }
   g_rksk_cache.clear();
+  for (auto &kv : g_ubsk_cache) { cudaFree(kv.second->d); delete kv.second; }
+  g_ubsk_cache.clear();
   for (auto &kv : g_dft_maps) cudaFree(kv.second.stored_to_host);
   g_dft_maps.clear();
   for (int i = 0; i < S_COUNT; ++i) t_scratch[i].release();
@@ -470,9 +574,20 @@ void mb200_host_slot_exponents(int layout, int N, int32_t *e_out) {
   memcpy(e_out, e.data(), sizeof(int32_t) * (N / 2));
 }
 
-void mb200_register_bootstrap_key(Bootstrap_Key key) { (void)lookup_bsk(key); }
+void mb200_register_bootstrap_key(Bootstrap_Key key) {
+  if (key && key->unfolding > 1) (void)lookup_ubsk(key);
+  else (void)lookup_bsk(key);
+}
 void mb200_release_bootstrap_key(Bootstrap_Key key) {
   std::lock_guard<std::mutex> lk(g_mu);
+  if (key->unfolding > 1) {
+    auto iu = g_ubsk_cache.find((const void *)key->su);
+    if (iu == g_ubsk_cache.end()) return;
+    cudaFree(iu->second->d);
+    delete iu->second;
+    g_ubsk_cache.erase(iu);
+    return;
+  }
   auto it = g_bsk_cache.find((const void *)key->s);
   if (it == g_bsk_cache.end()) return;
   if (it->second->owned) cudaFree(it->second->d);
@@ -695,13 +810,16 @@ void mb200_set_kernel_policy(int policy) { g_policy = policy; }
 void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
                                            int torus_base, int count) {
   if (count <= 0) return;
-  mb200_bsk *bsk = lookup_bsk(key);
-  const mb::Params &p = bsk->p;
+  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
+  UbskDev *U = key->unfolding > 1 ? lookup_ubsk(key) : nullptr;
+  mb200_bsk *bsk = U ? nullptr : lookup_bsk(key);
+  const mb::Params &p = U ? U->p : bsk->p;
   cudaStream_t st = mb::default_stream();
   PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
   const size_t out_b = sizeof(u64) * (size_t)count * (p.k + 1) * p.N;
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  pbs_dev_impl(bsk, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
+  if (U) pbs_unfolded_core(U, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
+  else pbs_dev_impl(bsk, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_trlwe(out, h_out, count, p.k, p.N);
@@ -710,13 +828,17 @@ void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, 
 static void fb_batch_impl(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int torus_base, int count,
                           int preprocess, int kappa, int theta) {
   if (count <= 0) return;
-  mb200_bsk *bsk = lookup_bsk(key);
-  const mb::Params &p = bsk->p;
+  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
+  MB_REQUIRE(key->unfolding == 1 || !preprocess, "programmable_bootstrap: unfolding > 1 keys are not supported");
+  UbskDev *U = key->unfolding > 1 ? lookup_ubsk(key) : nullptr;
+  mb200_bsk *bsk = U ? nullptr : lookup_bsk(key);
+  const mb::Params &p = U ? U->p : bsk->p;
   cudaStream_t st = mb::default_stream();
   PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
   const size_t out_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  pbs_dev_impl(bsk, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st, preprocess, kappa, theta);
+  if (U) pbs_unfolded_core(U, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st);
+  else pbs_dev_impl(bsk, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st, preprocess, kappa, theta);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_tlwe(out, h_out, count, p.k * p.N);
@@ -1176,6 +1298,201 @@ void circuit_bootstrap_2_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_
 }
 void circuit_bootstrap_3_batch(TRGSW *out, TLWE *in, Bootstrap_Key key, TRLWE_KS_Key *kska, Generic_KS_Key kskb, int count) {
   circuit_bootstrap_handles(3, out, in, key, nullptr, kska, kskb, count);
+}
+
+// ---- rank 4: unfolded blind rotation entry points (bootstrap.c:124-190) ------------------------------------
+void blind_rotate_unfolded_batch(TRLWE *tv, Torus **a, TRGSW *s, int size, int unfolding, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(tv && a && s && size > 0, "blind_rotate_unfolded: bad arguments");
+  const int k = tv[0]->k, N = tv[0]->b->N;
+  UbskDev *U = nullptr;
+  bool temporary = false;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ubsk_cache.find((const void *)s);
+    if (it != g_ubsk_cache.end()) U = it->second;
+  }
+  if (!U) { U = ubsk_upload(s, size, unfolding, k, N, s[0]->l, s[0]->Bg_bit); temporary = true; }
+  MB_REQUIRE(U->unfolding == unfolding && U->p.k == k && U->p.N == N, "blind_rotate_unfolded: key / accumulator shape mismatch");
+  cudaStream_t st = mb::default_stream();
+  const size_t a_b = sizeof(u64) * (size_t)count * size, acc_b = sizeof(u64) * (size_t)count * (k + 1) * N;
+  u64 *h_a = (u64 *)t_scratch[S_IN].host(a_b), *d_a = (u64 *)t_scratch[S_IN].dev(a_b);
+  u64 *h_acc = (u64 *)t_scratch[S_TV].host(acc_b), *d_acc = (u64 *)t_scratch[S_TV].dev(acc_b);
+  for (int i = 0; i < count; ++i) memcpy(h_a + (size_t)i * size, a[i], sizeof(u64) * size);
+  gather_trlwe(h_acc, tv, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_a, h_a, a_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_acc, h_acc, acc_b, cudaMemcpyHostToDevice, st));
+  blind_rotate_unfolded_core(U, d_acc, d_a, size, size, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_acc, d_acc, acc_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_trlwe(tv, h_acc, count, k, N);
+  if (temporary) { cudaFree(U->d); delete U; }
+}
+void blind_rotate_unfolded(TRLWE tv, Torus *a, TRGSW *s, int size, int unfolding) {
+  blind_rotate_unfolded_batch(&tv, &a, s, size, unfolding, 1);
+}
+
+// Fourier-domain rows on the device in position order -> the host's TRGSW_DFT handles (host slot order)
+static void dft_rows_to_handles(TRGSW_DFT *out, int n_trgsw, const u64 *d_rows_torus, const mb::Params &p, int rows,
+                                cudaStream_t st) {
+  const size_t npoly = (size_t)n_trgsw * rows * (p.k + 1), bytes = sizeof(double) * npoly * p.N;
+  DftMaps maps = dft_maps_for(p.N);
+  double *d_pos = (double *)t_scratch[S_UD].dev(bytes);
+  double *h_host = (double *)t_scratch[S_OUT].host(bytes), *d_host = (double *)t_scratch[S_OUT].dev(bytes);
+  mb::launch_torus_to_dft(d_pos, d_rows_torus, p.N, (int)npoly, st);
+  mb::launch_pos_to_host_order(d_host, d_pos, p.N, npoly, maps.pos_to_host, maps.pos_conj, st);
+  MB_CHECK(cudaMemcpyAsync(h_host, d_host, bytes, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n_trgsw; ++i)
+    for (int r = 0; r < rows; ++r) {
+      TRLWE_DFT row = out[i]->samples[r];
+      MB_REQUIRE(row->k == p.k && row->b->N == p.N, "output TRGSW_DFT %d shape mismatch", i);
+      for (int q = 0; q <= p.k; ++q)
+        memcpy((q < p.k ? row->a[q] : row->b)->coeffs, h_host + (((size_t)i * rows + r) * (p.k + 1) + q) * p.N,
+               sizeof(double) * p.N);
+    }
+}
+
+/* multivalue_bootstrap_UBR_phase1 (bootstrap.c:151-172): out[g] = trgsw_to_DFT of the g-th group's combined TRGSW */
+void multivalue_bootstrap_UBR_phase1(TRGSW_DFT *out, TLWE in, Bootstrap_Key key) {
+  MB_REQUIRE(key != nullptr && key->unfolding > 1, "multivalue_bootstrap_UBR_phase1 needs an unfolding > 1 key (bootstrap.c:156)");
+  UbskDev *U = lookup_ubsk(key);
+  const mb::Params &p = U->p;
+  MB_REQUIRE(in->n == p.n, "TLWE has dimension %d, expected %d", in->n, p.n);
+  cudaStream_t st = mb::default_stream();
+  const int groups = p.n / U->unfolding, rows = (p.k + 1) * p.l, npoly = rows * (p.k + 1);
+  u64 *h_a = (u64 *)t_scratch[S_IN].host(sizeof(u64) * p.n), *d_a = (u64 *)t_scratch[S_IN].dev(sizeof(u64) * p.n);
+  memcpy(h_a, in->a, sizeof(u64) * p.n);
+  MB_CHECK(cudaMemcpyAsync(d_a, h_a, sizeof(u64) * p.n, cudaMemcpyHostToDevice, st));
+  u64 *d_xai = (u64 *)t_scratch[S_UX].dev(sizeof(u64) * (size_t)groups * npoly * p.N);
+  mb::launch_unfold(d_xai, U->d, d_a, p.n, p.N, npoly, U->unfolding, 0, groups, 1, st);
+  dft_rows_to_handles(out, groups, d_xai, p, rows, st);
+}
+
+/* multivalue_bootstrap_UBR_phase2 (bootstrap.c:174-190): tv*X^(-b) through the n/u external products, extract */
+void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa, Bootstrap_Key key, int torus_base) {
+  MB_REQUIRE(key != nullptr && key->unfolding >= 1 && sa != nullptr, "multivalue_bootstrap_UBR_phase2: bad arguments");
+  const int k = tv->k, N = tv->b->N, groups = key->n / key->unfolding;
+  struct _Bootstrap_Key tmp;
+  tmp.s = sa; tmp.su = nullptr; tmp.n = groups; tmp.k = k; tmp.N = N; tmp.Bg_bit = sa[0]->Bg_bit; tmp.l = sa[0]->l; tmp.unfolding = 1;
+  bool cached;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cached = g_bsk_cache.count((const void *)sa) != 0;
+  }
+  mb200_bsk *set = lookup_bsk(&tmp);
+  mb::Params p = set->p;
+  p.n = key->n;
+  MB_REQUIRE(in->n == p.n, "TLWE has dimension %d, expected %d", in->n, p.n);
+  cudaStream_t st = mb::default_stream();
+  PbsStaged sg = stage_pbs_inputs(&tv, 1, &in, p, 1, st);
+  const size_t W = (size_t)(k + 1) * N;
+  u64 *d_acc = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * W);
+  initial_rotation_dev(p, d_acc, sg.d_tv, 1, sg.d_in, torus_base, 1, st);
+  for (int i = 0; i < groups; ++i) {
+    mb::BlindRotateLaunch a{};
+    a.bsk = set; a.tv = d_acc; a.tv_count = 1; a.size = 1; a.out = d_acc; a.count = 1; a.direct = 1; a.sel_const = i;
+    mb::launch_blind_rotate_generic(a, st);
+  }
+  g_last_kernel = "generic";
+  const size_t out_b = sizeof(u64) * (k * N + 1);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  int *d_idx = (int *)t_scratch[S_MISC].dev(sizeof(int));
+  MB_CHECK(cudaMemsetAsync(d_idx, 0, sizeof(int), st));
+  mb::launch_extract(d_out, d_acc, d_idx, 1, N, k, 1, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(&out, h_out, 1, k * N);
+  if (!cached) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_bsk_cache.erase((const void *)sa);
+    if (set->owned) cudaFree(set->d);
+    delete set;
+  }
+}
+
+// ---- rank 4: TRGSW-accumulator bootstrap (bootstrap.c:267-306) ------------------------------------------------
+// blind_rotate_trgsw is blind_rotate on each of the (k+1)*l_out rows with the same mask (trgsw.c:425-431): the rows
+// of all inputs form ONE batch for the blind-rotation kernel (row r of input c = ciphertext c*rows + r reads input c
+// and the r-th row of the trivial TRGSW(1) as its test vector).  d_out: [count][rows][(k+1)N] torus rows.
+static void trgsw_bootstrap_phase1_core(mb200_bsk *bsk, u64 *d_out, const u64 *d_in, int lo, int Bgo, int torus_base,
+                                        int count, cudaStream_t st) {
+  const mb::Params &p = bsk->p;
+  MB_REQUIRE(lo >= 1 && lo * Bgo < 64, "TRGSW bootstrap: output gadget l=%d Bg_bit=%d invalid", lo, Bgo);
+  const int rows = (p.k + 1) * lo;
+  const size_t W = (size_t)(p.k + 1) * p.N, tv_b = sizeof(u64) * rows * W;
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  memset(h_tv, 0, tv_b);
+  for (int i = 0; i < lo; ++i)                         // trgsw_noiseless_trivial_sample(1) (trgsw.c:130-142)
+    for (int q = 0; q <= p.k; ++q) h_tv[(size_t)(q * lo + i) * W + (size_t)q * p.N] = 1ull << (64 - (i + 1) * Bgo);
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  mb::BlindRotateLaunch a{};
+  a.bsk = bsk; a.tv = d_tv; a.tv_count = rows; a.in = d_in; a.in_stride = p.n + 1; a.in_div = rows; a.size = p.n;
+  a.out = d_out; a.extract = 0; a.init_rotate = 1; a.prec_offset = prec_offset_for(torus_base); a.count = count * rows;
+  run_blind_rotate(a, st);
+}
+void mb200_bootstrap_trgsw_phase1_dev(mb200_bsk_t bsk, uint64_t *d_out_trgsw, const uint64_t *d_in, int l_out,
+                                      int Bg_bit_out, int torus_base, int count, void *stream) {
+  if (count <= 0) return;
+  trgsw_bootstrap_phase1_core(bsk, (u64 *)d_out_trgsw, (const u64 *)d_in, l_out, Bg_bit_out, torus_base, count, as_stream(stream));
+}
+void functional_bootstrap_trgsw_phase1_batch(TRGSW_DFT *out, TLWE *in, Bootstrap_Key key, int torus_base, int count) {
+  if (count <= 0) return;
+  mb200_bsk *bsk = lookup_bsk(key);
+  const mb::Params &p = bsk->p;
+  const int lo = out[0]->l, Bgo = out[0]->Bg_bit, rows = (p.k + 1) * lo;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1);
+  u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
+  gather_tlwe(h_in, in, count, p.n);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  u64 *d_rows = (u64 *)t_scratch[S_UX].dev(sizeof(u64) * (size_t)count * rows * (p.k + 1) * p.N);
+  trgsw_bootstrap_phase1_core(bsk, d_rows, d_in, lo, Bgo, torus_base, count, st);
+  mb::Params po = p;
+  dft_rows_to_handles(out, count, d_rows, po, rows, st);        // trgsw_to_DFT (bootstrap.c:293)
+}
+void functional_bootstrap_trgsw_phase1(TRGSW_DFT out, TLWE in, Bootstrap_Key key, int torus_base) {
+  functional_bootstrap_trgsw_phase1_batch(&out, &in, key, torus_base, 1);
+}
+/* functional_bootstrap_trgsw_phase2 (bootstrap.c:298-306): out[c] = extract_0(in[c] (.) tv[c or 0]) */
+void functional_bootstrap_trgsw_phase2_batch(TLWE *out, TRGSW_DFT *in, TRLWE *tv, int tv_count, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(tv_count == 1 || tv_count == count, "functional_bootstrap_trgsw_phase2_batch: tv_count must be 1 or count");
+  const int k = tv[0]->k, N = tv[0]->b->N;
+  struct _Bootstrap_Key tmp;
+  tmp.s = in; tmp.su = nullptr; tmp.n = count; tmp.k = k; tmp.N = N; tmp.Bg_bit = in[0]->Bg_bit; tmp.l = in[0]->l; tmp.unfolding = 1;
+  bool cached;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cached = g_bsk_cache.count((const void *)in) != 0;
+  }
+  mb200_bsk *set = lookup_bsk(&tmp);
+  cudaStream_t st = mb::default_stream();
+  const size_t W = (size_t)(k + 1) * N, tv_b = sizeof(u64) * (size_t)tv_count * W, out_b = sizeof(u64) * (size_t)count * (k * N + 1);
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  int *h_sel = (int *)t_scratch[S_MISC].host(sizeof(int) * count), *d_sel = (int *)t_scratch[S_MISC].dev(sizeof(int) * count);
+  for (int i = 0; i < count; ++i) h_sel[i] = i;
+  gather_trlwe(h_tv, tv, tv_count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+  mb::BlindRotateLaunch a{};
+  a.bsk = set; a.tv = d_tv; a.tv_count = tv_count; a.size = 1; a.out = d_out; a.extract = 1; a.count = count; a.direct = 1;
+  a.sel = d_sel; a.sel_const = -1;
+  mb::launch_blind_rotate_generic(a, st);
+  g_last_kernel = "generic";
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, k * N);
+  if (!cached) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_bsk_cache.erase((const void *)in);
+    if (set->owned) cudaFree(set->d);
+    delete set;
+  }
+}
+void functional_bootstrap_trgsw_phase2(TLWE out, TRGSW_DFT in, TRLWE tv) {
+  functional_bootstrap_trgsw_phase2_batch(&out, &in, &tv, 1, 1);
 }
 
 mb200_gksk_t mb200_gksk_from_host(const uint64_t *h_rows, int n_in, int include_b, int N, int t, int base_bit) {

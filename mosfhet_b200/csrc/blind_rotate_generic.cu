@@ -338,18 +338,17 @@ void launch_dft_to_torus(u64 *out, const double *in, int N, int count, const int
   count_launch();
 }
 
-// position order (torus_to_dft_kernel output) -> the host FFT backend's slot order; perm/conj are indexed by
-// the resident (tiled) index idx, whose position is 8*(idx % (M/8)) + idx / (M/8)  (keys.cu)
+// position order (torus_to_dft_kernel output) -> the host FFT backend's slot order; perm[s] / conj[s] give the
+// host slot fed by position s (the same maps dft_to_torus_kernel reads the other way)
 __global__ void pos_to_host_order_kernel(double *out, const double *in, int N, size_t npolys, const int *perm,
                                          const int *conj) {
-  const int M = N >> 1, C8 = M >> 3;
+  const int M = N >> 1;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < npolys * M; g += (size_t)gridDim.x * blockDim.x) {
     const size_t poly = g / M;
-    const int idx = (int)(g - poly * M);
-    const int s = ((idx % C8) << 3) + idx / C8;
-    const int h = perm[idx];
+    const int s = (int)(g - poly * M);
+    const int h = perm[s];
     out[poly * N + h] = in[poly * N + s];
-    out[poly * N + M + h] = conj[idx] ? -in[poly * N + M + s] : in[poly * N + M + s];
+    out[poly * N + M + h] = conj[s] ? -in[poly * N + M + s] : in[poly * N + M + s];
   }
 }
 

@@ -1,0 +1,56 @@
+// unfold.cu -- the per-group TRGSW of the unfolded blind rotation (reference bootstrap.c:132-140):
+//     xai = su[g*2^u + 0] + sum_{j = 1}^{2^u - 1} X^{round(2N * sum_{bits of j} a[g*u + bit])} * su[g*2^u + j]
+// where su[g*2^u + j] = TRGSW(prod_bits s^bit (1-s)^(1-bit)) is the key layout of bootstrap.c:23-48.
+// Exact u64 wrap-around arithmetic (rotation = index shift + sign), so bit-exact with the reference whatever
+// the summation order.  One CTA per (polynomial, group, ciphertext); HBM bound: 2^u polynomial reads per
+// polynomial written.
+#include "common.cuh"
+#include "device_math.cuh"
+
+namespace mb {
+
+struct UnfoldArgs {
+  u64 *out;           // [count][n_groups][npoly][N]
+  const u64 *su;      // [groups_total * 2^u][npoly][N]
+  const u64 *a;       // [count][a_stride]
+  int a_stride;
+  int N, npoly, unfolding, group0, n_groups;
+};
+
+__global__ void __launch_bounds__(256) unfold_kernel(UnfoldArgs A) {
+  __shared__ int e[256];
+  const int poly = blockIdx.x, gi = blockIdx.y, ct = blockIdx.z;
+  const int g = A.group0 + gi, N = A.N, u = A.unfolding, key_exp = 1 << u;
+  const int log_N2 = 31 - __clz(2 * N);
+  const size_t T = (size_t)A.npoly * N;
+  const u64 *base = A.su + (size_t)g * key_exp * T + (size_t)poly * N;
+  const u64 *a = A.a + (size_t)ct * A.a_stride + (size_t)g * u;
+  for (int j = threadIdx.x; j < key_exp; j += blockDim.x) {
+    u64 sum = 0;
+    for (int b = 0; b < u; ++b)
+      if ((j >> b) & 1) sum += a[b];
+    e[j] = (int)torus2int(sum, log_N2) & (2 * N - 1);          // bootstrap.c:135-139
+  }
+  __syncthreads();
+  u64 *o = A.out + (((size_t)ct * A.n_groups + gi) * A.npoly + poly) * N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    u64 v = base[c];
+    for (int j = 1; j < key_exp; ++j) v += rotated_coeff(base + (size_t)j * T, c, e[j], N);   // trgsw_mul_by_xai_addto
+    o[c] = v;
+  }
+}
+
+void launch_unfold(u64 *out, const u64 *su, const u64 *a, int a_stride, int N, int npoly, int unfolding, int group0,
+                   int n_groups, int count, cudaStream_t st) {
+  MB_REQUIRE(unfolding >= 1 && unfolding <= 8, "unfolding=%d unsupported (1..8)", unfolding);
+  MB_REQUIRE(n_groups <= 65535 && count <= 65535, "unfold: grid too large (%d groups x %d ciphertexts)", n_groups, count);
+  if (count <= 0 || n_groups <= 0) return;
+  UnfoldArgs A;
+  A.out = out; A.su = su; A.a = a; A.a_stride = a_stride; A.N = N; A.npoly = npoly; A.unfolding = unfolding;
+  A.group0 = group0; A.n_groups = n_groups;
+  unfold_kernel<<<dim3(npoly, n_groups, count), 256, 0, st>>>(A);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace mb

@@ -871,3 +871,162 @@ def test_circuit_bootstrap_1_and_3_dropin(golden_cb, variant):
     api.release_generic_ks_key(ka)
     api.release_generic_ks_key(kb)
     api.release_trlwe_priv_ks_key(pair)
+
+
+# ------------------------------------------------------------------------------------------------
+# TRGSW-accumulator bootstrap and unfolded blind rotation
+# ------------------------------------------------------------------------------------------------
+def _host_dft_rows_to_torus(rows_host, layout):
+    nat = O.permute_from_host(rows_host, layout)
+    flat = nat.reshape(-1, nat.shape[-1])
+    return np.stack([O.dft_to_torus(r) for r in flat]).reshape(nat.shape)
+
+
+def _trgsw_dft_handle(rows, l, Bg_bit):
+    return abi.HostTRGSWDFT(np.ascontiguousarray(rows, np.float64), l, Bg_bit)
+
+
+def _trgsw_dft_flat(h):
+    return np.stack([r.polys for r in h.rows])
+
+
+def test_trgsw_accumulator_bootstrap_dropin(golden_r4):
+    """functional_bootstrap_trgsw_phase1 / phase2 (bootstrap.c:286-306) against the reference's outputs."""
+    g, P = golden_r4, golden_r4["P"]
+    N, k, l, Bg_bit = P["N"], P["k"], P["l"], P["Bg_bit"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, l, Bg_bit)
+    tv = abi.HostTRLWE(g["tv"])
+    ins = [abi.HostTLWE(x) for x in g["r4_in"]]
+    tol = phase_tol(l, Bg_bit)
+    singles = []
+    for c, cin in enumerate(ins):
+        out = _trgsw_dft_handle(np.zeros((2 * l, k + 1, N)), l, Bg_bit)
+        api.functional_bootstrap_trgsw_phase1(out, cin, hbsk, 4)
+        got_t = _host_dft_rows_to_torus(_trgsw_dft_flat(out), g["layout"])
+        ref_t = _host_dft_rows_to_torus(g["trgsw_p1"][c], g["layout"])
+        for r in range(2 * l):
+            d = sdiff(O.trlwe_phase(got_t[r], g["rlwe_key"]), O.trlwe_phase(ref_t[r], g["rlwe_key"]))
+            assert d.max() <= tol, (c, r)
+        # phase 2 on the reference's own phase-1 output: one external product + extraction
+        o2 = abi.HostTLWE.zeros(k * N)
+        api.functional_bootstrap_trgsw_phase2(o2, _trgsw_dft_handle(g["trgsw_p1"][c], l, Bg_bit), tv)
+        assert sdiff(o2.flat(), g["trgsw_p2"][c]).max() <= TOL_EXTPROD_RAW
+        # end to end through our own phase 1 (tests.c:1761-1764, tolerance 2^60)
+        o3 = abi.HostTLWE.zeros(k * N)
+        api.functional_bootstrap_trgsw_phase2(o3, out, tv)
+        ph = O.tlwe_phase(o3.flat(), g["ext_key"])
+        assert sdiff(np.uint64(ph), g["lut"][g["msgs"][c]]) <= (1 << 60)
+        singles.append((_trgsw_dft_flat(out).copy(), o3.flat().copy()))
+    outs = [_trgsw_dft_handle(np.zeros((2 * l, k + 1, N)), l, Bg_bit) for _ in ins]
+    api.functional_bootstrap_trgsw_phase1_batch(outs, ins, hbsk, 4)
+    for o, s_ in zip(outs, singles):
+        assert np.array_equal(_trgsw_dft_flat(o), s_[0])
+    o_tl = [abi.HostTLWE.zeros(k * N) for _ in ins]
+    api.functional_bootstrap_trgsw_phase2_batch(o_tl, outs, [tv])
+    for o, s_ in zip(o_tl, singles):
+        assert np.array_equal(o.flat(), s_[1])
+    api.release_bootstrap_key(hbsk)
+
+
+def test_trgsw_accumulator_bootstrap_full_size():
+    """tests.c:1738-1764 at the default parameters (N = 2048, n = 632, 36-bit gadget: the rows' noise is amplified
+    by Bg/2 * sqrt(2lN) in phase 2, which the 18-bit Level-1 gadget cannot afford), batched and on the device:
+    TLWE(m/8) -> TRGSW(X^-phase) -> (.) LUT -> extract decrypts to LUT[m]."""
+    import torch
+    P = LEVEL2
+    count, l, Bg_bit = 8, P.l, P.Bg_bit
+    lwe_key, rlwe_key = syn.binary_key(P.n, 31), syn.binary_key(P.N, 32)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=33)
+    msgs = np.arange(count) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, P.lwe_sigma, seed=34)
+    lut = np.random.default_rng(5).integers(0, 1 << 63, size=4, dtype=np.uint64) << np.uint64(1)
+    tvs = np.tile(syn.test_vector(lut, P.N, 1), (count, 1, 1))
+    rows = 2 * l
+    d_trgsw = torch.empty((count, rows, 2, P.N), dtype=torch.int64, device="cuda")
+    api.bootstrap_trgsw_phase1_dev(bsk, d_trgsw, torch_dev(cts), l, Bg_bit, 4, count)
+    api.synchronize()
+    assert api.last_blind_rotate_kernel().startswith("k1")
+    tset = api.BootstrapKey.from_torus_dev(Params(count, P.N, 1, l, Bg_bit, P.t, P.base_bit), d_trgsw)
+    d_tv = torch_dev(tvs)
+    d_o = torch.empty_like(d_tv)
+    api.extprod_dev(tset, np.arange(count, dtype=np.int32), d_o, d_tv, count)
+    api.synchronize()
+    res = to_np(d_o)
+    for c in range(count):
+        ph = O.tlwe_phase(O.extract_tlwe(res[c], 0), rlwe_key)
+        assert sdiff(np.uint64(ph), lut[msgs[c]]) <= (1 << 60), c
+    bsk.free()
+    tset.free()
+
+
+def test_unfolded_blind_rotation_dropin(golden_r4):
+    """blind_rotate_unfolded, functional_bootstrap[_wo_extract] with an unfolding = 2 key, and
+    multivalue_bootstrap_UBR_phase1/2 (bootstrap.c:124-198) against the reference's outputs."""
+    g, P = golden_r4, golden_r4["P"]
+    n, N, k, l, Bg_bit, u = P["n"], P["N"], P["k"], P["l"], P["Bg_bit"], golden_r4["unfolding"]
+    api.set_host_fft_layout(g["layout"])
+    key = abi.HostUnfoldedBootstrapKey(g["su"], n, u, k, l, Bg_bit)
+    tv = abi.HostTRLWE(g["tv"])
+    tol = phase_tol(l, Bg_bit)
+    for c in range(g["r4_in"].shape[0]):
+        cin = abi.HostTLWE(g["r4_in"][c])
+        a = g["r4_in"][c][:n].copy()
+        # the group TRGSWs: exact integer combination, then trgsw_to_DFT (compare after the inverse transform)
+        sa = [_trgsw_dft_handle(np.zeros((2 * l, k + 1, N)), l, Bg_bit) for _ in range(n // u)]
+        api.multivalue_bootstrap_UBR_phase1(sa, cin, key)
+        for grp in range(n // u):
+            got_t = _host_dft_rows_to_torus(_trgsw_dft_flat(sa[grp]), g["layout"])
+            assert sdiff(got_t, O.unfold_group(a, g["su"], grp, u, l)).max() <= (1 << 16), (c, grp)
+        acc = abi.HostTRLWE(g["bru_in"][c])
+        api.blind_rotate_unfolded(acc, a, key.su_array, n, u)
+        d = sdiff(O.trlwe_phase(acc.polys, g["rlwe_key"]), O.trlwe_phase(g["bru_out"][c], g["rlwe_key"]))
+        assert d.max() <= tol, c
+        wo = abi.HostTRLWE.zeros(k, N)
+        api.functional_bootstrap_wo_extract(wo, tv, cin, key, 4)
+        d = sdiff(O.trlwe_phase(wo.polys, g["rlwe_key"]), O.trlwe_phase(g["fbu_out"][c], g["rlwe_key"]))
+        assert d.max() <= tol, c
+        out = abi.HostTLWE.zeros(k * N)
+        api.functional_bootstrap(out, tv, cin, key, 4)
+        ph = O.tlwe_phase(out.flat(), g["ext_key"])
+        assert sdiff(np.uint64(ph), g["lut"][g["msgs"][c]]) <= TOL_TEST
+        # UBR phase 2 on the reference's own phase-1 output
+        sa_ref = [_trgsw_dft_handle(g["ubr_p1"][c][grp], l, Bg_bit) for grp in range(n // u)]
+        o2 = abi.HostTLWE.zeros(k * N)
+        api.multivalue_bootstrap_UBR_phase2(o2, tv, cin, sa_ref, key, 4)
+        ph2, ph_ref = O.tlwe_phase(o2.flat(), g["ext_key"]), O.tlwe_phase(g["ubr_p2"][c], g["ext_key"])
+        assert sdiff(np.uint64(ph2), np.uint64(ph_ref)) <= tol
+    api.release_bootstrap_key(key)
+
+
+def test_unfolded_bootstrap_full_size():
+    """functional_bootstrap_batch through an unfolding = 2 key at N = 1024 (n = 64 keeps the host-side key
+    generation of the test short): every output decrypts to LUT[m]."""
+    N, n, l, Bg_bit, u, count = 1024, 64, 3, 8, 2, 6
+    lwe_key, rlwe_key = syn.binary_key(n, 41), syn.binary_key(N, 42)
+    su = np.zeros(((n // u) << u, 2 * l, 2, N), np.uint64)
+    seed = 1000
+    for grp in range(n // u):
+        for j in range(1 << u):
+            bit = 1
+            for b in range(u):
+                s_b = int(lwe_key[grp * u + b])
+                bit *= s_b if (j >> b) & 1 else 1 - s_b             # bootstrap.c:38-44
+            for r in range(2 * l):
+                row = _trlwe_encrypt(np.zeros(N, np.uint64), rlwe_key, seed)
+                seed += 1
+                row[r // l, 0] += np.uint64(bit << (64 - (r % l + 1) * Bg_bit))     # trgsw_monomial_sample (trgsw.c:152-168)
+                su[(grp << u) + j, r] = row
+    key = abi.HostUnfoldedBootstrapKey(su, n, u, 1, l, Bg_bit)
+    msgs = np.arange(count) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, 2.0 ** -30, seed=43)
+    lut = syn.encode((3 * np.arange(4) + 1) % 4, 4)
+    tv = abi.HostTRLWE(syn.test_vector(lut, N, 1))
+    ins = [abi.HostTLWE(x) for x in cts]
+    outs = [abi.HostTLWE.zeros(N) for _ in ins]
+    api.functional_bootstrap_batch(outs, [tv], ins, key, 4)
+    assert api.last_blind_rotate_kernel() == "generic-unfolded"
+    for c, o in enumerate(outs):
+        ph = O.tlwe_phase(o.flat(), rlwe_key)
+        assert sdiff(np.uint64(ph), lut[msgs[c]]) <= TOL_TEST, c
+    api.release_bootstrap_key(key)
