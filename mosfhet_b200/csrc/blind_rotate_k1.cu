@@ -37,8 +37,13 @@ namespace mb {
 // are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
 // CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
 // G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
+#ifdef MB200_K1_MAXNREG
+#define MB200_K1_BOUNDS __maxnreg__(MB200_K1_MAXNREG)       // experiment: explicit register cap (build-wide)
+#else
+#define MB200_K1_BOUNDS __launch_bounds__(G * (1 << LOGM) / 8, MINB)
+#endif
 template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G>
-__global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_kernel(K1Args A) {
+__global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
   constexpr int LOGR2 = clog2(R2);
   constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;    // ROWS_B: shared-memory row buffers (largest batch)
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(G * (1 << LOGM) / 8, MINB) blind_rotate_k1_ker
     };
     // measured: no faster than the two unrolled copies (47.2-47.8 ms vs 46.5-48.0 ms at level 1) -> opt-in
 #ifdef MB200_ROLLED_BATCH
-    constexpr bool ROLLED = (L % LB != 0) && PF == 0 && G == 1;
+    constexpr bool ROLLED = (LB < L) && PF == 0 && G == 1;
 #else
     constexpr bool ROLLED = false;
 #endif
@@ -557,6 +562,7 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
 #ifdef MB200_K1_EXPERIMENTS
   MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 3, 3, 1, 0)
   MB_K1_CASE(9, 3, 2, 1, 2) MB_K1_CASE(9, 3, 3, 1, 2) MB_K1_CASE(10, 4, 2, 1, 2)
+  MB_K1_CASE(9, 3, 1, 4, 0) MB_K1_CASE(9, 3, 1, 5, 0) MB_K1_CASE(9, 3, 1, 6, 0) MB_K1_CASE(10, 4, 1, 3, 0)
 #endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
