@@ -364,6 +364,18 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   }
 }
 
+// one external product per ciphertext (direct mode): the k = 1 kernel when it has the shape, else the generic one
+void run_direct(const mb::BlindRotateLaunch &a, cudaStream_t st) {
+  if (a.count <= 0) return;
+  if (g_policy != 1 && mb::k1_direct_supported(a)) {
+    mb::launch_extprod_k1(a, st);
+    g_last_kernel = "k1-direct";
+  } else {
+    mb::launch_blind_rotate_generic(a, st);
+    g_last_kernel = "generic";
+  }
+}
+
 u64 prec_offset_for(int torus_base) {
   // double2torus(1./(4*torus_base)), misc.c:13-15 / bootstrap.c:194
   return (u64)((int64_t)(18446744073709551616.0 * (1.0 / (4.0 * torus_base))));
@@ -449,10 +461,10 @@ void blind_rotate_unfolded_core(UbskDev *U, u64 *d_acc, const u64 *d_a, int a_st
       mb::BlindRotateLaunch a{};
       a.bsk = &tmp; a.tv = d_acc + (size_t)c0 * W; a.tv_count = cc > 1 ? cc : 1; a.size = 1; a.out = d_acc + (size_t)c0 * W;
       a.count = cc; a.direct = 1; a.sel = d_sel; a.sel_const = -1;
-      mb::launch_blind_rotate_generic(a, st);                   // trgsw_mul_trlwe_DFT + trlwe_from_DFT (:142-143)
+      run_direct(a, st);                                        // trgsw_mul_trlwe_DFT + trlwe_from_DFT (:142-143)
     }
   }
-  g_last_kernel = "generic-unfolded";
+  g_last_kernel = "unfolded";
 }
 
 // acc = tv * X^(2N - round((b + 1/(4*torus_base)) * 2N)) for every ciphertext: the generic kernel with zero steps
@@ -716,8 +728,7 @@ void mb200_extprod_dev(mb200_bsk_t set, const int *h_sel, uint64_t *d_out, const
   a.bsk = set; a.tv = (const u64 *)d_in; a.tv_count = count; a.size = 1; a.out = (u64 *)d_out; a.count = count;
   a.direct = 1; a.sel = d_sel; a.sel_const = -1;
   if (count == 1) a.tv_count = 1;
-  mb::launch_blind_rotate_generic(a, st);
-  g_last_kernel = "generic";
+  run_direct(a, st);
 }
 
 /* CMUX: out[c] = in1[c] + TRGSW[sel] (.) (in2[c] - in1[c])  (vertical_packing.c:24-33); out may alias in1 */
@@ -728,8 +739,7 @@ void mb200_cmux_dev(mb200_bsk_t trgsw_set, int sel, uint64_t *d_out, const uint6
   mb::BlindRotateLaunch a{};
   a.bsk = trgsw_set; a.tv = (const u64 *)d_in2; a.tv_count = count > 1 ? count : 1; a.size = 1; a.out = (u64 *)d_out;
   a.count = count; a.direct = 1; a.sel_const = sel; a.sub = (const u64 *)d_in1; a.add = (const u64 *)d_in1;
-  mb::launch_blind_rotate_generic(a, as_stream(stream));
-  g_last_kernel = "generic";
+  run_direct(a, as_stream(stream));
 }
 
 /* CGGI vertical packing (vertical_packing.c:36-52): `bits` holds TRGSW(bit i) for i < size; the n_luts =
@@ -1182,8 +1192,7 @@ static void trlwe_fft_ks_dev(mb200_bsk *set, int mode, u64 *d_out, const u64 *d_
   mb::BlindRotateLaunch a{};
   a.bsk = set; a.tv = d_in; a.tv_count = count > 1 ? count : 1; a.size = 1; a.out = d_out; a.count = count;
   a.direct = 1; a.sel_const = 0; a.ks_mode = mode;
-  mb::launch_blind_rotate_generic(a, st);
-  g_last_kernel = "generic";
+  run_direct(a, st);
 }
 static void trlwe_fft_ks_batch(TRLWE *out, TRLWE *in, mb200_bsk *set, int mode, int count) {
   if (count <= 0) return;
@@ -1392,9 +1401,8 @@ void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa,
   for (int i = 0; i < groups; ++i) {
     mb::BlindRotateLaunch a{};
     a.bsk = set; a.tv = d_acc; a.tv_count = 1; a.size = 1; a.out = d_acc; a.count = 1; a.direct = 1; a.sel_const = i;
-    mb::launch_blind_rotate_generic(a, st);
+    run_direct(a, st);
   }
-  g_last_kernel = "generic";
   const size_t out_b = sizeof(u64) * (k * N + 1);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
   int *d_idx = (int *)t_scratch[S_MISC].dev(sizeof(int));
@@ -1479,8 +1487,7 @@ void functional_bootstrap_trgsw_phase2_batch(TLWE *out, TRGSW_DFT *in, TRLWE *tv
   mb::BlindRotateLaunch a{};
   a.bsk = set; a.tv = d_tv; a.tv_count = tv_count; a.size = 1; a.out = d_out; a.extract = 1; a.count = count; a.direct = 1;
   a.sel = d_sel; a.sel_const = -1;
-  mb::launch_blind_rotate_generic(a, st);
-  g_last_kernel = "generic";
+  run_direct(a, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_tlwe(out, h_out, count, k * N);

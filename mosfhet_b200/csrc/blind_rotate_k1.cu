@@ -25,401 +25,11 @@
 // trlwe.c:437, and the prologue/epilogue bootstrap.c:192-206 + trlwe.c:540-552.
 #include <map>
 #include <mutex>
-#include <type_traits>
 #include <vector>
 
-#include "k1_common.cuh"
+#include "k1_kernel.cuh"
 
 namespace mb {
-
-// G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
-// memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
-// are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
-// CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
-// G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
-#ifdef MB200_K1_MAXNREG
-#define MB200_K1_BOUNDS __maxnreg__(MB200_K1_MAXNREG)       // experiment: explicit register cap (build-wide)
-#else
-#define MB200_K1_BOUNDS __launch_bounds__(G * (1 << LOGM) / 8, MINB)
-#endif
-template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G>
-__global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
-  constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
-  constexpr int LOGR2 = clog2(R2);
-  constexpr int ROWS = 2 * L, ROWS_B = 2 * LB;    // ROWS_B: shared-memory row buffers (largest batch)
-  constexpr int PKL = PKALL ? L : LB;                 // gadget levels packed into one 32-bit word per coefficient
-#ifdef MB200_PB_FULL
-  constexpr int PB_UNROLL = 16;
-#elif defined(MB200_PB_UNROLL)
-  constexpr int PB_UNROLL = MB200_PB_UNROLL;
-#else
-  // independent pass-B butterflies in flight per thread; 4 measured 3 % slower than 2 at N = 1024 (code size:
-  // profiles/r1k_k1_occupancy.log)
-  constexpr int PB_UNROLL = 2;
-#endif
-#ifndef MB200_PA_UNROLL
-#define MB200_PA_UNROLL 1
-#endif
-#ifndef MB200_PC_UNROLL
-#define MB200_PC_UNROLL 2
-#endif
-  constexpr int PC_UNROLL = MB200_PC_UNROLL;          // pass-C rows unrolled together when keys are not double buffered
-  constexpr int PA_UNROLL = MB200_PA_UNROLL;          // gadget levels of pass A unrolled together
-  static_assert(LB >= 1 && LB <= L, "levels per batch");
-  static_assert(R2 >= 2 && R2 <= 16, "supported N: 512..4096");
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int grp = (G > 1) ? threadIdx.x / T : 0;
-  const int tid = (G > 1) ? threadIdx.x - grp * T : threadIdx.x;
-  const int ct_raw = blockIdx.x * G + grp;
-  const bool live = ct_raw < A.count;
-  const int ct = live ? ct_raw : A.count - 1;        // surplus groups of the last CTA shadow a real ciphertext
-  const size_t region = (size_t)2 * N * 8 + (size_t)ROWS_B * M * 16 + (((size_t)A.size * 2 + 15) & ~(size_t)15);
-  u64 *acc = reinterpret_cast<u64 *>(smem_raw + grp * region);       // [2][N]
-  double2 *buf = reinterpret_cast<double2 *>(acc + 2 * N);           // [ROWS_B][M]
-  unsigned short *rot = reinterpret_cast<unsigned short *>(buf + ROWS_B * M);   // [size] rotation amounts
-
-  const int log_N2 = LOGM + 2;
-  const double2 *__restrict__ TA = A.tab;
-  const double2 *__restrict__ TB = A.tab + 16 * S;
-  const u64 *in = A.in + (size_t)(ct / A.in_div) * A.in_stride;
-  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
-  const int Bg_bit = A.Bg_bit;
-
-  // ---- initial accumulator: tv * X^(2N - round((b + 1/(4*torus_base)) * 2N))  (bootstrap.c:194-195)
-  int rot0 = 0;
-  if (A.init_rotate) {
-    u64 b = in[A.size];
-    if (A.preprocess) b = pb_preprocess(b, A.kappa, A.theta, log_N2);
-    rot0 = (2 * N - (int)torus2int(b + A.prec_offset, log_N2)) & (2 * N - 1);
-  }
-  for (int c = tid; c < 2 * N; c += T) {
-    const int p = c / N, i = c - p * N;
-    acc[c] = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
-  }
-  // all rotation amounts up front: round(a_i * 2N / 2^64) (bootstrap.c:113), one 16-bit word per step
-  for (int i = tid; i < A.size; i += T) {
-    u64 av = in[i];
-    if (A.preprocess) av = pb_preprocess(av, A.kappa, A.theta, log_N2);
-    rot[i] = (unsigned short)(torus2int(av, log_N2) & (2 * N - 1));
-  }
-  __syncthreads();
-
-  const u64 off = decomp_offset(Bg_bit, L);
-  const unsigned dmask = (1u << Bg_bit) - 1u;
-  // digit u in [0, Bg) -> double(u - Bg/2) = hiloint2double(0x43300000, u) - (2^52 + Bg/2), exact
-  const double dbias = 4503599627370496.0 + (double)(1 << (Bg_bit - 1));
-  const double inv_M = 1.0 / (double)M;
-  const int pA = tid / S, qA = tid - pA * S;          // pass A / A' ownership
-  const int qpB = tid & 7;                            // pass B twiddle column (T is a multiple of 8)
-  // Swizzled addresses spelled out so that they are (thread constant) + (compile-time constant):
-  //   swz(s) = s ^ ((s >> 3) & 7) only permutes the low 3 bits, by a mask that depends on s >> 3.
-  // pass A / A': element pos*S + qA -> mask ((pos*(S/8)) + (qA>>3)) & 7: NVA distinct masks
-  constexpr int S8 = S / 8, NVA = (S8 >= 8) ? 1 : 8 / S8;
-  int qsw[NVA];
-#pragma unroll
-  for (int v = 0; v < NVA; ++v) qsw[v] = qA ^ ((v * S8 + (qA >> 3)) & 7);
-  // pass B / B': element b*S + 8m + qp with b = (tid>>3) + it*(T/8): mask ((tid>>3)*S8 + m) & 7 (it drops out)
-  int qx[R2];
-#pragma unroll
-  for (int m = 0; m < R2; ++m) qx[m] = qpB ^ ((((tid >> 3) * S8) + m) & 7);
-  const int bB0 = (tid >> 3) * S;                     // first element of this thread's pass-B block
-
-  for (int step = 0; step < A.size; ++step) {
-    const int a_i = rot[step];
-    // bootstrap.c:114 skips a_i == 0.  With several ciphertexts in lockstep the step is executed
-    // instead: (X^0 - 1)*acc = 0 decomposes into all-zero digits, so the accumulator is unchanged.
-    if (G == 1 && a_i == 0) continue;
-    const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M;
-
-    double2 fa[2][8];                                 // Fourier accumulators: positions 8*tid .. 8*tid+7
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) fa[pp][i] = make_double2(0.0, 0.0);
-
-    unsigned pk0[16], pk1[16];
-    // (X^a - 1)*acc + rounding offset, top PKL*Bg_bit bits (= PKL signed digits) per coefficient
-    auto pack_digits = [&](int lev_end) {
-      const u64 *ap = acc + pA * N;
-      const int pk_shift = 64 - lev_end * Bg_bit;
-      const int base = (qA - a_i) & (2 * N - 1);       // index of coefficient qA in acc * X^a (sign in bit log2 N)
-#pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const int j = qA + m * S;
-        const int s0 = (base + m * S) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
-        const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
-        const u64 t0 = off - ap[j], t1 = off - ap[j + M];
-        const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
-        const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
-        pk0[m] = (unsigned)(v0 >> pk_shift);
-        pk1[m] = (unsigned)(v1 >> pk_shift);
-      }
-    };
-    if (PKALL) pack_digits(L);
-
-    // One batch = NB gadget levels of both input polynomials (2*NB rows of shared-memory buffers).
-    auto batch = [&](auto nb_tag, const int lev0) {
-      constexpr int NB = decltype(nb_tag)::value, ROWS_B = 2 * NB;
-      // ------------------------------- pass A -------------------------------------------------
-      if (!PKALL) pack_digits(lev0 + NB);
-      // pass-A twiddles w^q * W_M^(q*k1): the same 16 values for every level of the batch -- loaded once
-      // (the L1/shared-memory data pipe, not FP64, is the busiest unit of this kernel: ncu r1e)
-      constexpr bool HOIST_TW = (LOGM <= 9);          // N = 2048+: registers are needed elsewhere (pass C key buffers)
-      double2 twA[HOIST_TW ? 16 : 1];
-      if (HOIST_TW) {
-#pragma unroll
-        for (int pos = 0; pos < 16; ++pos) twA[HOIST_TW ? pos : 0] = __ldg(&TA[brev(pos, 4) * S + qA]);
-      }
-#pragma unroll(PA_UNROLL)
-      for (int lb = 0; lb < NB; ++lb) {
-        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (NB - 1 - lb)) * Bg_bit;
-        double2 x[16];
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
-          const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
-          // fold z = d0 + i*d1 and the constant part of the twist, w^(m*M/16) = W_64^m
-          x[m] = mul_w64(make_double2(d0, d1), m, false);
-        }
-        reg_dif<16>(x);
-        double2 *row = buf + (pA * NB + lb) * M;
-#pragma unroll
-        for (int pos = 0; pos < 16; ++pos) {
-          const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
-          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
-        }
-      }
-      __syncthreads();
-      // key rows of this batch: row index of buffer rb
-      auto key_row = [&](int rb) {
-        const int p = rb / NB, lev = lev0 + (rb - p * NB);
-        return key + (size_t)((p * L + lev) * 2) * M + tid;            // TRGSW row order of trgsw.c:394-419
-      };
-      double2 kv[PF == 1 ? 2 : 1][16];
-      auto load_keys = [&](double2 (&dst)[16], int rb) {
-        const double2 *__restrict__ k0 = key_row(rb);
-#pragma unroll
-#ifdef MB200_ABL_NOKEY
-        for (int i = 0; i < 8; ++i) { dst[i] = make_double2(1.0 + i, 0.5 * rb); dst[8 + i] = make_double2(0.25 * i, 2.0 + rb); }
-        (void)k0;
-#else
-        for (int i = 0; i < 8; ++i) {
-          if (G > 1 || PF == 2) { dst[i] = __ldg(k0 + i * C8); dst[8 + i] = __ldg(k0 + M + i * C8); }   // L1-allocating
-          else { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }          // streaming
-        }
-#endif
-      };
-      // PF == 2: no register double buffer; the next row is pulled into L1 (one lane per 128-byte line) while
-      // the current one computes, so the demand loads hit L1 instead of waiting for L2
-      auto prefetch_keys = [&](int rb) {
-        if ((tid & 7) == 0) {
-          const double2 *__restrict__ k0 = key_row(rb);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(k0 + i * C8));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(k0 + M + i * C8));
-          }
-        }
-      };
-      if (PF == 1) load_keys(kv[0], 0);                                 // in flight across pass B
-      if (PF == 2) prefetch_keys(0);
-      // ------------------------------- pass B -------------------------------------------------
-      constexpr int TASKS_B = ROWS_B * 128 / T;
-      static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
-#ifdef MB200_ABL_NOPASSB
-      if (a_i < 0)
-#endif
-#pragma unroll(PB_UNROLL)
-      for (int it = 0; it < TASKS_B; ++it) {
-        // task = tid + it*T: row = task >> 7, block b = (task & 127) >> 3 = (tid >> 3) + it*(T/8) (mod 16)
-        double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
-        double2 x[R2];
-#pragma unroll
-        for (int m = 0; m < R2; ++m) x[m] = blk[8 * m + qx[m]];
-        reg_dif<R2>(x);
-#pragma unroll
-        for (int pos = 0; pos < R2; ++pos) {
-          const int k = brev(pos, LOGR2);
-          const double2 y = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
-          blk[8 * pos + qx[pos]] = y;
-        }
-      }
-      __syncthreads();
-      // ------------------------------- pass C + MAC ----------------------------------------------
-      if (PF == 1) {
-        // fully unrolled on purpose: a 2-row ping-pong loop (smaller code) measured 10 % slower
-#pragma unroll
-        for (int rb = 0; rb < ROWS_B; ++rb) {
-          if (rb + 1 < ROWS_B) load_keys(kv[(rb + 1) & 1], rb + 1);     // next row's keys while this row computes
-          const double2 *row = buf + rb * M;
-          double2 x[8];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
-          reg_dif<8>(x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[rb & 1][i]); cfma(fa[1][i], x[i], kv[rb & 1][8 + i]); }
-        }
-      } else {
-#pragma unroll(PC_UNROLL)
-        for (int rb = 0; rb < ROWS_B; ++rb) {
-          load_keys(kv[0], rb);
-          if (PF == 2 && rb + 1 < ROWS_B) prefetch_keys(rb + 1);
-          const double2 *row = buf + rb * M;
-          double2 x[8];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
-          reg_dif<8>(x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[0][i]); cfma(fa[1][i], x[i], kv[0][8 + i]); }
-        }
-      }
-      __syncthreads();
-    };
-    // The same batch with the number of levels as a run-time value: ONE copy of the pass A/B/C code for the
-    // full and the ragged batch (the kernel is instruction-cache sensitive: ncu shows 64-72 % GCC instruction
-    // requests and 12 % no_instruction stalls in pass A).  Used when the batches are ragged and the keys are
-    // not double buffered in registers (that path needs compile-time buffer indices).
-    auto batch_rt = [&](const int nb, const int lev0) {
-      if (!PKALL) pack_digits(lev0 + nb);
-      constexpr bool HOIST_TW = (LOGM <= 9);
-      double2 twA[HOIST_TW ? 16 : 1];
-      if (HOIST_TW) {
-#pragma unroll
-        for (int pos = 0; pos < 16; ++pos) twA[HOIST_TW ? pos : 0] = __ldg(&TA[brev(pos, 4) * S + qA]);
-      }
-#pragma unroll 1
-      for (int lb = 0; lb < nb; ++lb) {
-        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (nb - 1 - lb)) * Bg_bit;
-        double2 x[16];
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const double d0 = __hiloint2double(0x43300000, (int)((pk0[m] >> sh) & dmask)) - dbias;
-          const double d1 = __hiloint2double(0x43300000, (int)((pk1[m] >> sh) & dmask)) - dbias;
-          x[m] = mul_w64(make_double2(d0, d1), m, false);
-        }
-        reg_dif<16>(x);
-        double2 *row = buf + (pA * nb + lb) * M;
-#pragma unroll
-        for (int pos = 0; pos < 16; ++pos) {
-          const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
-          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
-        }
-      }
-      __syncthreads();
-      const int tasks_b = 2 * nb * 128 / T;
-#pragma unroll(PB_UNROLL)
-      for (int it = 0; it < tasks_b; ++it) {
-        double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
-        double2 x[R2];
-#pragma unroll
-        for (int m = 0; m < R2; ++m) x[m] = blk[8 * m + qx[m]];
-        reg_dif<R2>(x);
-#pragma unroll
-        for (int pos = 0; pos < R2; ++pos) {
-          const int k = brev(pos, LOGR2);
-          const double2 y = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
-          blk[8 * pos + qx[pos]] = y;
-        }
-      }
-      __syncthreads();
-#pragma unroll 1
-      for (int p = 0; p < 2; ++p) {
-#pragma unroll(PC_UNROLL)
-        for (int lv = 0; lv < nb; ++lv) {
-          const double2 *__restrict__ k0 = key + (size_t)((p * L + lev0 + lv) * 2) * M + tid;
-          double2 kv[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { kv[i] = ldg_key(k0 + i * C8); kv[8 + i] = ldg_key(k0 + M + i * C8); }
-          const double2 *row = buf + (p * nb + lv) * M;
-          double2 x[8];
-#pragma unroll
-          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
-          reg_dif<8>(x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[i]); cfma(fa[1][i], x[i], kv[8 + i]); }
-        }
-      }
-      __syncthreads();
-    };
-    // measured: no faster than the two unrolled copies (47.2-47.8 ms vs 46.5-48.0 ms at level 1) -> opt-in
-#ifdef MB200_ROLLED_BATCH
-    constexpr bool ROLLED = (LB < L) && PF == 0 && G == 1;
-#else
-    constexpr bool ROLLED = false;
-#endif
-    if constexpr (ROLLED) {
-#pragma unroll 1
-      for (int lev0 = 0; lev0 < L; lev0 += LB) batch_rt(min(LB, L - lev0), lev0);
-    } else {
-      // full batches of LB levels, then the ragged remainder (compile-time structure: constant shifts and rows)
-#pragma unroll
-      for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
-      if constexpr (L % LB != 0) batch(std::integral_constant<int, L % LB>{}, L - L % LB);
-    }
-
-    // ---------------------------------- inverse: C' ------------------------------------------------
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
-      reg_dit_inv<8>(fa[pp]);
-      double2 *row = buf + pp * M;
-#pragma unroll
-      for (int m = 0; m < 8; ++m) row[8 * tid + (m ^ (tid & 7))] = fa[pp][m];
-    }
-    __syncthreads();
-    // ---------------------------------- B' ---------------------------------------------------------
-    constexpr int TASKS_BI = 2 * 128 / T > 0 ? 2 * 128 / T : 1;
-#ifdef MB200_ABL_NOPASSB
-    if (a_i < 0)
-#endif
-#pragma unroll
-    for (int it = 0; it < TASKS_BI; ++it) {
-      double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
-      double2 x[R2];
-#pragma unroll
-      for (int pos = 0; pos < R2; ++pos) {
-        const int k = brev(pos, LOGR2);
-        const double2 y = blk[8 * pos + qx[pos]];
-        x[pos] = k == 0 ? y : cmul_conj(y, __ldg(&TB[k * 8 + qpB]));
-      }
-      reg_dit_inv<R2>(x);
-#pragma unroll
-      for (int m = 0; m < R2; ++m) blk[8 * m + qx[m]] = x[m];
-    }
-    __syncthreads();
-    // ---------------------------------- A' + accumulate --------------------------------------------
-    {
-      const double2 *row = buf + pA * M;
-      double2 x[16];
-#pragma unroll
-      for (int pos = 0; pos < 16; ++pos) {
-        const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);
-        x[pos] = cmul_conj(row[pos * S + qsw[pos & (NVA - 1)]], t);
-      }
-      reg_dit_inv<16>(x);
-      u64 *ap = acc + pA * N;
-#pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const double2 z = mul_w64(x[m], m, true);
-        const int j = qA + m * S;
-        ap[j] += f64_to_torus_fast(z.x * inv_M);       // trlwe_from_DFT + trlwe_addto
-        ap[j + M] += f64_to_torus_fast(z.y * inv_M);
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- epilogue: sample extraction at index 0 (trlwe.c:540-552) or the raw accumulator -------------
-  if (!live) return;
-  if (A.extract) {
-    u64 *o = A.out + (size_t)ct * (N + 1);
-    for (int c = tid; c < N; c += T) o[c] = (c == 0) ? acc[0] : (0ull - acc[N - c]);
-    if (tid == 0) o[N] = acc[N];
-  } else {
-    u64 *o = A.out + (size_t)ct * 2 * N;
-    for (int c = tid; c < 2 * N; c += T) o[c] = acc[c];
-  }
-}
 
 // ---- per-N tables ------------------------------------------------------------------------------
 static std::mutex g_k1_mu;
@@ -534,6 +144,7 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   a.in_stride = b.in_stride; a.in_div = b.in_div > 0 ? b.in_div : 1; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   a.count = b.count;
+  a.sel = nullptr; a.sel_const = -1; a.sub = nullptr; a.add = nullptr;
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");

@@ -107,6 +107,8 @@ void launch_unfold(u64 *out, const u64 *su, const u64 *a, int a_stride, int N, i
 void launch_pos_to_host_order(double *out, const double *in, int N, size_t npolys, const int *perm, const int *conj,
                               cudaStream_t st);
 bool k1_supported(const Params &p);
+bool k1_direct_supported(const BlindRotateLaunch &a);     // one external product / CMUX on the k = 1 kernel
+void launch_extprod_k1(const BlindRotateLaunch &a, cudaStream_t st);
 void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1_variant_name(const Params &p);
 bool k1h_supported(const Params &p);

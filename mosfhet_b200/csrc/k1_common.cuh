@@ -92,6 +92,10 @@ struct K1Args {
   int preprocess, kappa, theta;
   int Bg_bit;
   int count;              // ciphertexts in the launch (kernels with several ciphertexts per CTA)
+  // DIRECT instantiations only (one external product / CMUX):
+  const int *sel;         // [count] TRGSW index per ciphertext, used when sel_const < 0
+  int sel_const;
+  const u64 *sub, *add;   // operand = tv - sub, result = add + product (either may be null)
 };
 
 // f64 -> u64 mod 2^64, round to nearest (AVX-512 path of the reference, fft_processor_spqlios.c:158-164)

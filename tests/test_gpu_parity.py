@@ -1025,7 +1025,7 @@ def test_unfolded_bootstrap_full_size():
     ins = [abi.HostTLWE(x) for x in cts]
     outs = [abi.HostTLWE.zeros(N) for _ in ins]
     api.functional_bootstrap_batch(outs, [tv], ins, key, 4)
-    assert api.last_blind_rotate_kernel() == "generic-unfolded"
+    assert api.last_blind_rotate_kernel() == "unfolded"
     for c, o in enumerate(outs):
         ph = O.tlwe_phase(o.flat(), rlwe_key)
         assert sdiff(np.uint64(ph), lut[msgs[c]]) <= TOL_TEST, c
