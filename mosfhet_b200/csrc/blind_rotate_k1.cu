@@ -144,7 +144,6 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   a.in_stride = b.in_stride; a.in_div = b.in_div > 0 ? b.in_div : 1; a.size = b.size; a.out = b.out; a.extract = b.extract; a.init_rotate = b.init_rotate;
   a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta; a.Bg_bit = p.Bg_bit;
   a.count = b.count;
-  a.sel = nullptr; a.sel_const = -1; a.sub = nullptr; a.add = nullptr;
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");

@@ -1,7 +1,7 @@
 // blind_rotate_k1_direct.cu -- ONE external product per ciphertext on the specialised k = 1 kernel
 // (DIRECT instantiations of k1_kernel.cuh): trgsw_mul_trlwe_DFT + trlwe_from_DFT (trgsw.c:385-423,
 // trlwe.c:629-634) and the CMUX of the leveled LUT (vertical_packing.c:24-33) as one launch
-//     out[c] = add[c] + TRGSW[sel] (.) (tv[c] - sub[c])
+//     out[c] = in1[c] + TRGSW[sel] (.) (tv[c] - in1[c])        (in1 = null: the plain external product)
 // These are what the compositions of SURVEY 8(f) spend their time in (CMUX tree, TRGSW-accumulator phase 2,
 // unfolded rotation, circuit-bootstrap consumers).  One step of the bootstrap kernel costs ~9 us per CTA, so a
 // batch is bound by moving its operands: 3 x 2N words per ciphertext through HBM.
@@ -12,7 +12,7 @@ namespace mb {
 bool k1_supported(const Params &p);
 
 bool k1_direct_supported(const BlindRotateLaunch &b) {
-  return b.direct && !b.dft_out && b.ks_mode == 0 && b.size == 1 && k1_supported(b.bsk->p);
+  return b.direct && !b.dft_out && b.ks_mode == 0 && b.size == 1 && b.sub == b.add && k1_supported(b.bsk->p);
 }
 
 template <int LOGM, int L, int LB, bool PKALL>
@@ -34,9 +34,9 @@ void launch_extprod_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   const Params &p = b.bsk->p;
   upload_w64();
   K1Args a{};
-  a.bsk = b.bsk->d; a.tab = k1_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = nullptr; a.in_stride = 0;
-  a.in_div = 1; a.size = 1; a.out = b.out; a.extract = b.extract; a.init_rotate = 0; a.prec_offset = 0; a.preprocess = 0;
-  a.Bg_bit = p.Bg_bit; a.count = b.count; a.sel = b.sel; a.sel_const = b.sel_const; a.sub = b.sub; a.add = b.add;
+  a.bsk = b.bsk->d; a.tab = k1_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count;
+  a.in_div = 1; a.size = 1; a.out = b.out; a.extract = b.extract; a.init_rotate = 0; a.preprocess = 0;
+  a.Bg_bit = p.Bg_bit; a.count = b.count; a.sel = b.sel; a.sel_const = b.sel_const; a.in1 = b.add;   // b.sub == b.add
   MB_REQUIRE(a.sel_const >= 0 || a.sel != nullptr, "external product: no TRGSW selector");
   const int logm = ilog2i(p.N) - 1;
   // levels per shared-memory batch: 2 (1 at N = 4096 or when two digits exceed the 32-bit packed word)

@@ -82,21 +82,21 @@ struct K1Args {
   const double2 *tab;     // TA[16][S] then TB[R2][8]
   const u64 *tv;
   int tv_count;
-  const u64 *in;
-  int in_stride;
+  // DIRECT instantiations (one external product / CMUX) reuse three bootstrap-only slots through anonymous unions.
+  // The struct must keep its size and layout: the Level-2 kernel sits on the 255-register cliff and ptxas' allocation
+  // depends on the parameter block (32 more bytes of parameters: 176 B of spills and 141 -> 200 ms per 4096).
+  union { const u64 *in; const int *sel; };          // sel: [count] TRGSW index per ciphertext (when sel_const < 0)
+  union { int in_stride; int sel_const; };
   int in_div;          // ciphertexts per input TLWE (>= 1): ct uses input ct / in_div, test vector ct % tv_count
   int size;
   u64 *out;
   int extract, init_rotate;
-  u64 prec_offset;
+  union { u64 prec_offset; const u64 *in1; };        // in1: CMUX operand, product of (tv - in1) and result in1 + product
   int preprocess, kappa, theta;
   int Bg_bit;
   int count;              // ciphertexts in the launch (kernels with several ciphertexts per CTA)
-  // DIRECT instantiations only (one external product / CMUX):
-  const int *sel;         // [count] TRGSW index per ciphertext, used when sel_const < 0
-  int sel_const;
-  const u64 *sub, *add;   // operand = tv - sub, result = add + product (either may be null)
 };
+static_assert(sizeof(K1Args) == 104, "K1Args layout is performance critical, see above");
 
 // f64 -> u64 mod 2^64, round to nearest (AVX-512 path of the reference, fft_processor_spqlios.c:158-164)
 // done on the FP64 pipe + one F2I instead of ~25 integer instructions: r = rint(x / 2^64) by the

@@ -20,8 +20,8 @@ namespace mb {
 #endif
 // DIRECT: one external product instead of the rotation loop (trgsw_mul_trlwe_DFT + trlwe_from_DFT, trgsw.c:385 /
 // trlwe.c:629, or the CMUX of vertical_packing.c:24-33): the shared-memory accumulator starts as the OPERAND
-// tv - sub, its digits are taken as they are (no X^a - 1), the TRGSW is number sel_const / sel[ct] of the
-// resident set, and the result is add + product.
+// tv - in1, its digits are taken as they are (no X^a - 1), the TRGSW is number sel_const / sel[ct] of the
+// resident set, and the result is in1 + product (in1 may be null: plain external product).
 template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G, bool DIRECT = false>
 __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   constexpr int M = 1 << LOGM, N = 2 * M, S = M / 16, R2 = M / 128, T = M / 8, C8 = M / 8;
@@ -62,7 +62,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   const int log_N2 = LOGM + 2;
   const double2 *__restrict__ TA = A.tab;
   const double2 *__restrict__ TB = A.tab + 16 * S;
-  const u64 *in = A.in + (size_t)(ct / A.in_div) * A.in_stride;
+  const u64 *in = DIRECT ? nullptr : A.in + (size_t)(ct / A.in_div) * A.in_stride;
   const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
   const int Bg_bit = A.Bg_bit;
 
@@ -74,7 +74,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
     rot0 = (2 * N - (int)torus2int(b + A.prec_offset, log_N2)) & (2 * N - 1);
   }
   if (DIRECT) {
-    const u64 *sub = A.sub ? A.sub + (size_t)ct * 2 * N : nullptr;
+    const u64 *sub = A.in1 ? A.in1 + (size_t)ct * 2 * N : nullptr;
     for (int c = tid; c < 2 * N; c += T) acc[c] = sub ? tv[c] - sub[c] : tv[c];
   } else {
     for (int c = tid; c < 2 * N; c += T) {
@@ -389,7 +389,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       }
       reg_dit_inv<16>(x);
       u64 *ap = acc + pA * N;
-      const u64 *addp = (DIRECT && A.add) ? A.add + (size_t)ct * 2 * N + pA * N : nullptr;
+      const u64 *addp = (DIRECT && A.in1) ? A.in1 + (size_t)ct * 2 * N + pA * N : nullptr;
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const double2 z = mul_w64(x[m], m, true);

@@ -1,0 +1,42 @@
+"""Code-generation guard (CPU, no GPU needed): the two benchmark kernels sit on the 255-register cliff and ptxas'
+allocation has flipped into spilling for reasons as remote as the size of the kernel parameter struct (141 -> 200 ms
+per 4096 Level-2 bootstraps).  This pins the resource usage of the default instantiations in the built objects."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "mosfhet_b200", "build")
+
+
+def _usage(obj):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) and not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(obj):
+        pytest.skip(f"{obj} not built in this checkout (python mosfhet_b200/build.py)")
+    out = subprocess.run([exe, "-res-usage", obj], capture_output=True, text=True).stdout
+    res = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        res[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    return res
+
+
+def test_default_bootstrap_kernels_do_not_spill():
+    res = _usage(os.path.join(BUILD, "blind_rotate_k1.o"))
+    # <LOGM, L, LB, MINB, PKALL, PF, G, DIRECT>: Level 1 (N=1024, l=3, batches of 2+1 levels) and Level 2 (N=2048, l=4)
+    level1 = [v for k, v in res.items() if "Li9ELi3ELi2ELi1ELb1ELi0ELi1ELb0E" in k]
+    level2 = [v for k, v in res.items() if "Li10ELi4ELi2ELi1ELb0ELi0ELi1ELb0E" in k]
+    assert level1 and level2, "default instantiations missing from blind_rotate_k1.o"
+    assert level1[0][1] == 0, f"Level-1 kernel spills: REG/STACK = {level1[0]}"
+    assert level2[0][1] <= 16, f"Level-2 kernel spills more than its 16-byte baseline: REG/STACK = {level2[0]}"
+
+
+def test_keyswitch_kernel_register_budget():
+    res = _usage(os.path.join(BUILD, "keyswitch.o"))
+    ks = [v for k, v in res.items() if "keyswitch_warp_kernelILi10ELb0E" in k]
+    assert ks, "TLWE key-switch instantiation (640-word rows) missing"
+    assert ks[0][0] <= 72, f"28 warps per SM need <= 72 registers, got {ks[0]}"
