@@ -306,7 +306,8 @@ void mb200_ks_host(mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_in, int c
 uint64_t    mb200_launch_count(void);
 void        mb200_reset_launch_count(void);
 const char *mb200_last_blind_rotate_kernel(void);
-/* Force the generic (any k, l, N) kernel instead of the specialised k=1 one: 0 = auto, 1 = generic */
+/* Kernel choice for the blind rotation: 0 = auto (by batch size and shape), 1 = generic (any k, l, N), 2 = k1 (one CTA
+ * per ciphertext, throughput), 3 = k1h (T = M/4 threads), 4 = k1c (one ciphertext per 2-CTA cluster, latency) */
 void        mb200_set_kernel_policy(int policy);
 /* Measured FP64 FMA throughput (TFLOP/s) of the current device: the roofline denominator of the
  * FP64-bound blind-rotation kernel (MEASURED_PEAKS.json has no FP64 entry). */

@@ -352,7 +352,17 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   const char *eh = getenv("MB200_K1H");
   bool want_h = g_policy == 3 || (g_policy == 0 && a.count <= 2 * mb::sm_count() && a.bsk->p.N <= 1024);
   if (g_policy == 0 && eh) want_h = eh[0] == '1';
-  if ((g_policy == 0 || g_policy == 3) && !a.direct && want_h && mb::k1h_supported(a.bsk->p)) {
+  // policy 4 / small batches: one ciphertext per 2-CTA cluster (two SMs per bootstrap) while the batch leaves at
+  // least half the SMs idle otherwise
+  const char *ec = getenv("MB200_K1C");
+  // (measured, profiles/r1o_latency.log: at N = 2048 4.9 ms instead of 8.6 ms per bootstrap; at N <= 1024 the T = M/4
+  // kernel below is faster still, 2.7 ms against 3.3 ms)
+  bool want_c = g_policy == 4 || (g_policy == 0 && 2 * a.count <= mb::sm_count() && a.bsk->p.N > 1024);
+  if (g_policy == 0 && ec) want_c = ec[0] == '1';
+  if ((g_policy == 0 || g_policy == 4) && !a.direct && want_c && mb::k1c_supported(a.bsk->p)) {
+    mb::launch_blind_rotate_k1c(a, st);
+    g_last_kernel = mb::k1c_variant_name(a.bsk->p);
+  } else if ((g_policy == 0 || g_policy == 3) && !a.direct && want_h && mb::k1h_supported(a.bsk->p)) {
     mb::launch_blind_rotate_k1h(a, st);
     g_last_kernel = mb::k1h_variant_name(a.bsk->p);
   } else if (can_k1 || (g_policy == 2 && !a.direct && mb::k1_supported(a.bsk->p))) {

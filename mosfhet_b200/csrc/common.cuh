@@ -112,6 +112,9 @@ void launch_extprod_k1(const BlindRotateLaunch &a, cudaStream_t st);
 void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1_variant_name(const Params &p);
 bool k1h_supported(const Params &p);
+bool k1c_supported(const Params &p);                      // one ciphertext per 2-CTA cluster (latency)
+void launch_blind_rotate_k1c(const BlindRotateLaunch &a, cudaStream_t st);
+const char *k1c_variant_name(const Params &p);
 void launch_blind_rotate_k1h(const BlindRotateLaunch &a, cudaStream_t st);
 const char *k1h_variant_name(const Params &p);
 

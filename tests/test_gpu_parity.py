@@ -430,16 +430,18 @@ def test_k1_instantiations_vs_generic(N, l, Bg_bit):
     lut = syn.splitmix64_stream(N + 17, 4)
     tv = syn.test_vector(lut, P.N, 1)
     outs = {}
-    for name, policy in (("generic", 1), ("k1", 2), ("k1h", 3)):
+    for name, policy in (("generic", 1), ("k1", 2), ("k1h", 3), ("k1c", 4)):
         api.set_kernel_policy(policy)
         outs[name] = api.pbs_host(bsk, tv, cts, 4).copy()
         outs[name + "_kernel"] = api.last_blind_rotate_kernel()
     api.set_kernel_policy(0)
     assert outs["generic_kernel"] == "generic"
     assert outs["k1_kernel"].startswith("k1<"), outs["k1_kernel"]
+    if N in (1024, 2048) and (l == 1 or 2 * Bg_bit <= 32):
+        assert outs["k1c_kernel"].startswith("k1c<"), outs["k1c_kernel"]      # the 2-CTA cluster kernel
     tol = phase_tol(l, Bg_bit)
     ph_g = syn.tlwe_phase(outs["generic"], rlwe_key)
-    for name in ("k1", "k1h"):
+    for name in ("k1", "k1h", "k1c"):
         ph = syn.tlwe_phase(outs[name], rlwe_key)
         assert syn.torus_distance(ph, ph_g).max() <= tol, (name, outs[name + "_kernel"])
     # the oracle on the first ciphertext (keys read back from the resident layout)
