@@ -171,6 +171,14 @@ void launch_table_keyswitch(const u64 *table, int row_stride, int n_entries, int
     nv = 8;
   }
   MB_REQUIRE(nv <= 16, "keyswitch: row stride %d unsupported (above 1024 words it must be a multiple of 512)", row_stride);
+  // latency mode: a batch that cannot occupy the GPU even with its sweep sliced over 32-coefficient groups is also
+  // split by 64-word output columns (one 128-bit load per lane and row): nv times more warps in flight
+  const int max_slices = (n_entries + 31) / 32;
+  if ((long long)count * A.chunks * max_slices < 2LL * sm_count()) {
+    A.chunks = row_stride / 64;
+    launch_ks_nv<1, true>(A, st);
+    return;
+  }
   if (A.chunks > 1) { launch_ks_nv<8, true>(A, st); return; }
   switch (nv) {
 #define MB_KS_CASE(NV_) case NV_: launch_ks_nv<NV_, false>(A, st); break;

@@ -404,6 +404,9 @@ def test_full_size_round_trip(P, count):
     ks_only = api.ks_host(ksk, mid)
     # PBS is deterministic for a given kernel, so fused == separate bit for bit
     assert np.array_equal(ks_only, out)
+    # the small-batch key switch (sweep sliced over warps, output columns chunked, integer atomics) is the same sum
+    for small in (1, 3, 9, 40):
+        assert np.array_equal(api.ks_host(ksk, mid[:small]), out[:small]), small
     # a second bootstrap of the key-switched output still decrypts (chained caller pattern, integer.c:94-96)
     out2 = api.pbs_ks_host(bsk, ksk, tv, out, torus_base)
     dec2 = ((syn.tlwe_phase(out2, lwe_key) + (np.uint64(1) << np.uint64(60))) >> np.uint64(61)).astype(np.int64)
