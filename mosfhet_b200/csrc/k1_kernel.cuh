@@ -213,7 +213,15 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
           }
         }
       };
-      if (PF == 1) load_keys(kv[0], 0);                                 // in flight across pass B
+      // PF == 3: single register buffer, software pipelined by halves: the first row is requested before pass B,
+      // and inside pass C the q = 0 (q = 1) half of the NEXT row is requested as soon as the MACs of that half are
+      // done, so the loads fly under the next row's shared-memory reads and radix-8 butterflies
+      auto load_keys_half = [&](double2 (&dst)[16], int rb, int q) {
+        const double2 *__restrict__ k0 = key_row(rb) + q * M;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[8 * q + i] = ldg_key(k0 + i * C8);
+      };
+      if (PF == 1 || PF == 3) load_keys(kv[0], 0);                      // in flight across pass B
       if (PF == 2) prefetch_keys(0);
       // ------------------------------- pass B -------------------------------------------------
       constexpr int TASKS_B = ROWS_B * 128 / T;
@@ -250,6 +258,21 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
           reg_dif<8>(x);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[rb & 1][i]); cfma(fa[1][i], x[i], kv[rb & 1][8 + i]); }
+        }
+      } else if (PF == 3) {
+#pragma unroll(PC_UNROLL)
+        for (int rb = 0; rb < ROWS_B; ++rb) {
+          const double2 *row = buf + rb * M;
+          double2 x[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
+          reg_dif<8>(x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cfma(fa[0][i], x[i], kv[0][i]);
+          if (rb + 1 < ROWS_B) load_keys_half(kv[0], rb + 1, 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cfma(fa[1][i], x[i], kv[0][8 + i]);
+          if (rb + 1 < ROWS_B) load_keys_half(kv[0], rb + 1, 1);
         }
       } else {
 #pragma unroll(PC_UNROLL)
