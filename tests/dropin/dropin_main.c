@@ -32,9 +32,20 @@ TLWE tlwe_alloc_sample(int n);
 Torus tlwe_phase(TLWE c, TLWE_Key key);
 TRLWE trlwe_alloc_new_sample(int k, int N);
 void trlwe_torus_packing(TRLWE out, Torus *in, int size);
+Generic_KS_Key trlwe_new_priv_SK_KS_key_N2(TRLWE_Key out_key, TLWE_Key in_key, int t, int base_bit);   /* keyswitch.c:611 */
+Generic_KS_Key trlwe_new_packing1_KS_key(TRLWE_Key out_key, TLWE_Key in_key, int t, int base_bit);     /* keyswitch.c:368 */
+TRGSW trgsw_alloc_new_sample(int l, int Bg_bit, int k, int N);
 
 typedef void (*fb_t)(TLWE, TRLWE, TLWE, Bootstrap_Key, int);
 typedef void (*ks_t)(TLWE, TLWE, TLWE_KS_Key);
+typedef void (*gks_t)(TRLWE, TLWE, Generic_KS_Key);
+typedef void (*cb_t)(TRGSW, TLWE, Bootstrap_Key, Generic_KS_Key, Generic_KS_Key);
+
+static int trlwe_equal(TRLWE a, TRLWE b, int k, int N) {
+  for (int q = 0; q < k; q++)
+    if (memcmp(a->a[q]->coeffs, b->a[q]->coeffs, sizeof(Torus) * N)) return 0;
+  return !memcmp(a->b->coeffs, b->b->coeffs, sizeof(Torus) * N);
+}
 
 static long long sdist(Torus a, Torus b) { long long d = (long long)(a - b); return d < 0 ? -d : d; }
 
@@ -80,6 +91,37 @@ int main(int argc, char **argv) {
     if (ko->b != ko_ref->b || memcmp(ko->a, ko_ref->a, sizeof(Torus) * n)) { printf("KS %d: not bit-exact\n", i); bad++; }
     const Torus dec = (tlwe_phase(ko, key_lwe) + (1ULL << 60)) >> 61;
     if ((int)(dec & 7) != (3 * m + 1) % 4) { printf("KS %d: decrypts to %d, want %d\n", i, (int)(dec & 7), (3 * m + 1) % 4); bad++; }
+  }
+  /* ---- circuit bootstrap keys as the DEFAULT reference build makes them: seed-compressed TRLWE rows under a
+   * process-global AES key (keyswitch.c:231-241, rnd/aes_rng.c:88-93).  The CUDA library expands them at upload
+   * through this process's own trlwe_compressed_subto.  The oracle here is the reference function in THIS namespace
+   * (dlsym RTLD_NEXT: the definition after the preloaded library) -- the private dlmopen copy has another AES key. */
+  {
+    const int t2 = 4, bb2 = 2;
+    Generic_KS_Key kska = trlwe_new_priv_SK_KS_key_N2(key_rlwe, key_ext, t2, bb2);
+    Generic_KS_Key kskb = trlwe_new_packing1_KS_key(key_rlwe, key_ext, t2, bb2);
+    gks_t next_priv = (gks_t)dlsym(RTLD_NEXT, "trlwe_priv_keyswitch");
+    gks_t next_pack = (gks_t)dlsym(RTLD_NEXT, "trlwe_packing1_keyswitch");
+    cb_t next_cb2 = (cb_t)dlsym(RTLD_NEXT, "circuit_bootstrap_2");
+    if (!next_priv || !next_pack || !next_cb2) { fprintf(stderr, "RTLD_NEXT lookup failed\n"); return 4; }
+    for (int i = 0; i < 3; i++) {
+      TLWE c = tlwe_new_sample((Torus)(i % 2) << 62, key_lwe);
+      TLWE tl = tlwe_alloc_sample(k * N);
+      ref_fb(tl, lut, c, bk, torus_base);                       /* some TLWE of dimension k*N */
+      TRLWE a = trlwe_alloc_new_sample(k, N), a_ref = trlwe_alloc_new_sample(k, N);
+      trlwe_priv_keyswitch(a, tl, kska);                         /* CUDA (interposed) */
+      next_priv(a_ref, tl, kska);                                /* reference CPU, same AES state */
+      if (!trlwe_equal(a, a_ref, k, N)) { printf("priv KS %d: not bit-exact\n", i); bad++; }
+      trlwe_packing1_keyswitch(a, tl, kskb);
+      next_pack(a_ref, tl, kskb);
+      if (!trlwe_equal(a, a_ref, k, N)) { printf("packing KS %d: not bit-exact\n", i); bad++; }
+      /* the reference's composed caller running on the interposed primitives == the fused CUDA composition */
+      TRGSW g = trgsw_alloc_new_sample(l, Bg_bit, k, N), g_ref = trgsw_alloc_new_sample(l, Bg_bit, k, N);
+      circuit_bootstrap_2(g, c, bk, kska, kskb);
+      next_cb2(g_ref, c, bk, kska, kskb);
+      for (int r = 0; r < 2 * l; r++)
+        if (!trlwe_equal(g->samples[r], g_ref->samples[r], k, N)) { printf("circuit bootstrap %d row %d differs\n", i, r); bad++; }
+    }
   }
   printf(bad ? "DROPIN FAILED (%d)\n" : "DROPIN OK\n", bad);
   return bad ? 1 : 0;
