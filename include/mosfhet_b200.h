@@ -289,6 +289,9 @@ void mb200_cmux_dev(mb200_bsk_t trgsw_set, int sel, uint64_t *d_out, const uint6
 /* CGGI vertical packing (vertical_packing.c:36-52): bits = TRGSW(bit i), i < size; d_luts holds
  * 2^(size - log2 N) TRLWE LUTs (consumed); d_out_tlwe receives the TLWE (dimension k*N) of LUT[input]. */
 void mb200_vertical_packing_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_out_tlwe, int size, void *stream);
+/* E independent evaluations at once (BASELINE config 5: leveled LUT over batched ciphertexts): evaluation e's TRGSW(bit i)
+ * is sample e*size + i of `bits`; d_luts is LUT-major [2^(size - log2 N)][E][(k+1)N] (consumed); d_out_tlwe [E][k*N+1] */
+void mb200_vertical_packing_batch_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_out_tlwe, int size, int E, void *stream);
 /* Negacyclic transforms in the library's internal slot order (bit-reversed, e = 1+4*bitrev(s)). */
 void mb200_torus_to_dft_dev(double *d_out /* [count][N] Re|Im */, const uint64_t *d_in, int N, int count, void *stream);
 void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int count, void *stream);

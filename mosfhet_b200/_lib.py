@@ -119,6 +119,7 @@ PROTOTYPES = {
     "mb200_extprod_dev": (None, [_vp, _P(C.c_int), _vp, _vp, C.c_int, _vp]),
     "mb200_cmux_dev": (None, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "mb200_vertical_packing_dev": (None, [_vp, _vp, _vp, C.c_int, _vp]),
+    "mb200_vertical_packing_batch_dev": (None, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_torus_to_dft_dev": (None, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_dft_to_torus_dev": (None, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "mb200_pbs_ks_host": (None, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]),

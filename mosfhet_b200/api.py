@@ -570,6 +570,11 @@ def cmux_dev(trgsw_set, sel: int, d_out, d_in1, d_in2, count, stream=None):
     lib().mb200_cmux_dev(trgsw_set.handle, sel, _ptr(d_out), _ptr(d_in1), _ptr(d_in2), count, _ptr(stream))
 
 
+def vertical_packing_batch_dev(bits, d_luts, d_out_tlwe, size: int, E: int, stream=None):
+    """E evaluations in lockstep; bits: E*size TRGSWs (evaluation-major), d_luts LUT-major [n_luts][E][2N] (consumed)."""
+    lib().mb200_vertical_packing_batch_dev(bits.handle, _ptr(d_luts), _ptr(d_out_tlwe), size, E, _ptr(stream))
+
+
 def vertical_packing_dev(bits, d_luts, d_out_tlwe, size: int, stream=None):
     """CGGI vertical packing over resident TRGSW bit encryptions; consumes d_luts (vertical_packing.c:36-52)."""
     lib().mb200_vertical_packing_dev(bits.handle, _ptr(d_luts), _ptr(d_out_tlwe), size, _ptr(stream))

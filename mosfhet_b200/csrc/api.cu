@@ -774,6 +774,42 @@ void mb200_vertical_packing_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_
   const int idx0 = 0;
   mb200_extract_dev(d_out_tlwe, d_luts, &idx0, 1, p.N, p.k, 1, st);
 }
+/* The same over E independent evaluations in lockstep: evaluation e's TRGSW(bit i) is set[e*size + i]; the LUTs are
+ * LUT-major, d_luts[j][e] (so that in1 / in2 of every CMUX level are two contiguous ranges); one CMUX launch per
+ * tree level over half*E ciphertexts, then log2 N rotate + CMUX pairs (the blind rotation of :50 with per-evaluation
+ * keys: acc + TRGSW (.) (X^a*acc - acc)), one extraction. */
+void mb200_vertical_packing_batch_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64_t *d_out_tlwe, int size, int E, void *stream) {
+  const mb::Params &p = bits->p;
+  cudaStream_t st = as_stream(stream);
+  if (E <= 0) return;
+  const int log_N = mb::ilog2i(p.N);
+  MB_REQUIRE(size >= 1 && size <= 30 && (long long)size * E <= p.n,
+             "vertical packing: %d evaluations x %d input bits but %d TRGSW samples", E, size, p.n);
+  const size_t W = (size_t)(p.k + 1) * p.N;
+  const int n_max = size > log_N ? (1 << (size - log_N - 1)) * E : E;
+  int *d_sel = (int *)t_scratch[S_MISC2].dev(sizeof(int) * n_max);
+  for (int i = 0; i < size - log_N; ++i) {
+    const int half = 1 << (size - log_N - i - 1), count = half * E;
+    mb::launch_fill_sel(d_sel, E, size, size - i - 1, count, st);
+    mb::BlindRotateLaunch a{};
+    a.bsk = bits; a.tv = (const u64 *)d_luts + (size_t)count * W; a.tv_count = count > 1 ? count : 1; a.size = 1;
+    a.out = (u64 *)d_luts; a.count = count; a.direct = 1; a.sel = d_sel; a.sel_const = -1;
+    a.sub = (const u64 *)d_luts; a.add = (const u64 *)d_luts;
+    run_direct(a, st);
+  }
+  const int rot_bits = size > log_N ? log_N : size;
+  u64 *d_rot = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * (size_t)E * W);
+  for (int i = 0; i < rot_bits; ++i) {
+    mb::launch_rotate_trlwe(d_rot, (const u64 *)d_luts, 2 * p.N - (1 << i), p.N, p.k + 1, E, st);
+    mb::launch_fill_sel(d_sel, E, size, i, E, st);
+    mb::BlindRotateLaunch a{};
+    a.bsk = bits; a.tv = d_rot; a.tv_count = E > 1 ? E : 1; a.size = 1; a.out = (u64 *)d_luts; a.count = E; a.direct = 1;
+    a.sel = d_sel; a.sel_const = -1; a.sub = (const u64 *)d_luts; a.add = (const u64 *)d_luts;
+    run_direct(a, st);
+  }
+  const int idx0 = 0;
+  mb200_extract_dev(d_out_tlwe, d_luts, &idx0, 1, p.N, p.k, E, st);
+}
 void mb200_torus_to_dft_dev(double *d_out, const uint64_t *d_in, int N, int count, void *stream) {
   mb::launch_torus_to_dft(d_out, (const u64 *)d_in, N, count, as_stream(stream));
 }

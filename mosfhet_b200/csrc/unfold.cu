@@ -53,4 +53,29 @@ void launch_unfold(u64 *out, const u64 *su, const u64 *a, int a_stride, int N, i
   count_launch();
 }
 
+// ---- helpers of the batched leveled LUT (vertical_packing.c:36-52 over E independent evaluations) ---------------
+// selector of CMUX c of a level: evaluation c % E uses its own TRGSW(bit) = set[(c % E) * size + bit]
+__global__ void fill_sel_kernel(int *sel, int E, int size, int bit, int count) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < count; c += gridDim.x * blockDim.x) sel[c] = (c % E) * size + bit;
+}
+void launch_fill_sel(int *sel, int E, int size, int bit, int count, cudaStream_t st) {
+  fill_sel_kernel<<<(count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024, 256, 0, st>>>(sel, E, size, bit, count);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+// out = in * X^amount for `count` TRLWE samples of `polys` polynomials (trlwe_mul_by_xai, trlwe.c:507-513)
+__global__ void rotate_trlwe_kernel(u64 *out, const u64 *in, int amount, int N, size_t total) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t poly = g / N;
+    const int i = (int)(g - poly * N);
+    out[g] = rotated_coeff(in + poly * N, i, amount, N);
+  }
+}
+void launch_rotate_trlwe(u64 *out, const u64 *in, int amount, int N, int polys, int count, cudaStream_t st) {
+  const size_t total = (size_t)count * polys * N;
+  rotate_trlwe_kernel<<<sm_count() * 8, 256, 0, st>>>(out, in, amount & (2 * N - 1), N, total);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
 }  // namespace mb

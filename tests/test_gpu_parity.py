@@ -1035,3 +1035,40 @@ def test_unfolded_bootstrap_full_size():
         ph = O.tlwe_phase(o.flat(), rlwe_key)
         assert sdiff(np.uint64(ph), lut[msgs[c]]) <= TOL_TEST, c
     api.release_bootstrap_key(key)
+
+
+@pytest.mark.parametrize("N,l,Bg_bit", [(512, 2, 10), (1024, 2, 10)])
+def test_vertical_packing_batch(N, l, Bg_bit):
+    """BASELINE config 5 (applications/leveled_lut over batched ciphertexts): E independent LUT evaluations in lockstep,
+    each with its own TRGSW bit encryptions; every output decrypts to LUT[value_e], and evaluation 0 agrees in phase
+    with the single-evaluation entry point on the same TRGSW samples."""
+    import torch
+    log_N = N.bit_length() - 1
+    size, E = log_N + 3, 5
+    out_prec = 10
+    rng = np.random.default_rng(N + 1)
+    values = rng.integers(0, 1 << size, size=E)
+    bits = np.array([[(int(v) >> i) & 1 for i in range(size)] for v in values], np.uint64).reshape(-1)   # [E*size]
+    P = Params(E * size, N, 1, l, Bg_bit, 3, 2, 2.0 ** -30, 2.0 ** -55)
+    rlwe_key = syn.binary_key(N, 78)
+    trgsw_bits = api.BootstrapKey.synthesize(P, bits, rlwe_key, seed=N + 9)
+    lut = rng.integers(0, 1 << out_prec, size=(8, N), dtype=np.uint64)
+    luts = np.zeros((8, 2, N), np.uint64)
+    luts[:, 1, :] = lut << np.uint64(64 - out_prec)
+    d_luts = torch_dev(np.repeat(luts[:, None], E, axis=1))            # LUT-major [8][E][2][N]
+    d_res = torch.empty((E, N + 1), dtype=torch.int64, device="cuda")
+    api.vertical_packing_batch_dev(trgsw_bits, d_luts, d_res, size, E)
+    api.synchronize()
+    assert api.last_blind_rotate_kernel() == "k1-direct"
+    res = to_np(d_res)
+    for e in range(E):
+        ph = O.tlwe_phase(res[e], rlwe_key)
+        assert O.torus2int(ph, out_prec) % (1 << out_prec) == int(lut.reshape(-1)[values[e]]), e
+    # evaluation 0 through the single-evaluation entry point (its TRGSW samples are the first `size` of the set)
+    d_one = torch_dev(luts)
+    d_r1 = torch.empty(N + 1, dtype=torch.int64, device="cuda")
+    api.vertical_packing_dev(trgsw_bits, d_one, d_r1, size)
+    api.synchronize()
+    ph1 = O.tlwe_phase(to_np(d_r1), rlwe_key)
+    assert sdiff(np.uint64(O.tlwe_phase(res[0], rlwe_key)), np.uint64(ph1)) <= phase_tol(l, Bg_bit)
+    trgsw_bits.free()
