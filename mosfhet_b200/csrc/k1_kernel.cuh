@@ -8,6 +8,35 @@
 
 namespace mb {
 
+// ---- tensor memory as a per-thread constant store (disable with MB200_NO_TMEM_TW) -----------------------------------------------
+// The 16 pass-A / A' twiddles of a thread are thread constants that do not fit the register budget, so they were
+// re-read from global memory (through the L1 data pipe, the busiest unit of this kernel) three times per step.
+// Blackwell's tensor memory is private per lane and has its own datapath: each thread parks its 64 words there once
+// (tcgen05.st) and fetches them 16 words at a time (tcgen05.ld.32x32b.x16) when needed.
+__device__ __forceinline__ void tmem_st4(unsigned taddr, const double2 (&v)[4]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)),
+      "r"(__double2hiint(v[0].y)), "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)), "r"(__double2loint(v[1].y)),
+      "r"(__double2hiint(v[1].y)), "r"(__double2loint(v[2].x)), "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)),
+      "r"(__double2hiint(v[2].y)), "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)),
+      "r"(__double2hiint(v[3].y))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
+  int w[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    v[i] = make_double2(__hiloint2double(w[4 * i + 1], w[4 * i]), __hiloint2double(w[4 * i + 3], w[4 * i + 2]));
+}
+
 // G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
 // memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
 // are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
@@ -66,6 +95,46 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
   const int Bg_bit = A.Bg_bit;
 
+#ifndef MB200_NO_TMEM_TW
+  constexpr bool TMEM_TW = (T <= 128) && (G == 1);    // one lane per thread: warps 0..3 of the CTA own TMEM lanes 32w..32w+31
+#else
+  constexpr bool TMEM_TW = false;
+#endif
+  // pass-B / B' twiddles too when they fill whole 16-word groups (R2 = 4, 8): columns 64 .. 64 + 4*R2
+  constexpr bool TMEM_TB = TMEM_TW && (R2 == 4 || R2 == 8);
+  constexpr int TMEM_COLS = TMEM_TB ? 128 : 64;
+  __shared__ unsigned tmem_base_s;
+  unsigned tw_taddr = 0;
+  if (TMEM_TW) {
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n\t"
+                   "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+                   ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tw_taddr = tmem_base_s + ((unsigned)(tid >> 5) << 21);            // lane field (bits 31:16) = 32 * warp
+    const int qA0 = tid % (M / 16);
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      double2 tw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tw[i] = __ldg(&A.tab[brev(4 * g4 + i, 4) * (M / 16) + qA0]);
+      tmem_st4(tw_taddr + 16 * g4, tw);
+    }
+    if (TMEM_TB) {
+#pragma unroll
+      for (int g4 = 0; g4 < R2 / 4; ++g4) {
+        double2 tw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tw[i] = __ldg(&A.tab[16 * (M / 16) + (4 * g4 + i) * 8 + (tid & 7)]);   // TB[k*8 + qpB]
+        tmem_st4(tw_taddr + 64 + 16 * g4, tw);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+
   // ---- initial accumulator: tv * X^(2N - round((b + 1/(4*torus_base)) * 2N))  (bootstrap.c:194-195)
   int rot0 = 0;
   if (A.init_rotate) {
@@ -109,6 +178,21 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
 #pragma unroll
   for (int m = 0; m < R2; ++m) qx[m] = qpB ^ ((((tid >> 3) * S8) + m) & 7);
   const int bB0 = (tid >> 3) * S;                     // first element of this thread's pass-B block
+  // pass-B twiddles W_S^(qp*k), k < R2: from tensor memory (TMEM_TB) or global memory
+  auto load_tb = [&](double2 (&tb)[R2]) {
+    if (TMEM_TB) {
+#pragma unroll
+      for (int g4 = 0; g4 < R2 / 4; ++g4) {
+        double2 tw[4];
+        tmem_ld4(tw, tw_taddr + 64 + 16 * g4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tb[(4 * g4 + i) & (R2 - 1)] = tw[i];
+      }
+    } else {
+#pragma unroll
+      for (int k = 1; k < R2; ++k) tb[k] = __ldg(&TB[k * 8 + qpB]);
+    }
+  };
 
   for (int step = 0; step < (DIRECT ? 1 : A.size); ++step) {
     const int a_i = DIRECT ? 0 : rot[step];
@@ -156,7 +240,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       if (!PKALL) pack_digits(lev0 + NB);
       // pass-A twiddles w^q * W_M^(q*k1): the same 16 values for every level of the batch -- loaded once
       // (the L1/shared-memory data pipe, not FP64, is the busiest unit of this kernel: ncu r1e)
-      constexpr bool HOIST_TW = (LOGM <= 9);          // N = 2048+: registers are needed elsewhere (pass C key buffers)
+      constexpr bool HOIST_TW = (LOGM <= 9) && !TMEM_TW;   // N = 2048+: registers are needed elsewhere (pass C key buffers)
       double2 twA[HOIST_TW ? 16 : 1];
       if (HOIST_TW) {
 #pragma unroll
@@ -175,10 +259,20 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         }
         reg_dif<16>(x);
         double2 *row = buf + (pA * NB + lb) * M;
+        if (TMEM_TW) {
 #pragma unroll
-        for (int pos = 0; pos < 16; ++pos) {
-          const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
-          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
+          for (int g4 = 0; g4 < 4; ++g4) {
+            double2 tw[4];
+            tmem_ld4(tw, tw_taddr + 16 * g4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[(4 * g4 + i) * S + qsw[(4 * g4 + i) & (NVA - 1)]] = cmul(x[4 * g4 + i], tw[i]);
+          }
+        } else {
+#pragma unroll
+          for (int pos = 0; pos < 16; ++pos) {
+            const double2 t = HOIST_TW ? twA[HOIST_TW ? pos : 0] : __ldg(&TA[brev(pos, 4) * S + qA]);
+            row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], t);
+          }
         }
       }
       __syncthreads();
@@ -226,6 +320,8 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       // ------------------------------- pass B -------------------------------------------------
       constexpr int TASKS_B = ROWS_B * 128 / T;
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
+      double2 tb[R2];
+      load_tb(tb);
 #ifdef MB200_ABL_NOPASSB
       if (a_i < 0)
 #endif
@@ -240,7 +336,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
 #pragma unroll
         for (int pos = 0; pos < R2; ++pos) {
           const int k = brev(pos, LOGR2);
-          const double2 y = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
+          const double2 y = k == 0 ? x[pos] : cmul(x[pos], tb[k]);
           blk[8 * pos + qx[pos]] = y;
         }
       }
@@ -383,6 +479,8 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
     __syncthreads();
     // ---------------------------------- B' ---------------------------------------------------------
     constexpr int TASKS_BI = 2 * 128 / T > 0 ? 2 * 128 / T : 1;
+    double2 tbi[R2];
+    load_tb(tbi);
 #ifdef MB200_ABL_NOPASSB
     if (a_i < 0)
 #endif
@@ -394,7 +492,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       for (int pos = 0; pos < R2; ++pos) {
         const int k = brev(pos, LOGR2);
         const double2 y = blk[8 * pos + qx[pos]];
-        x[pos] = k == 0 ? y : cmul_conj(y, __ldg(&TB[k * 8 + qpB]));
+        x[pos] = k == 0 ? y : cmul_conj(y, tbi[k]);
       }
       reg_dit_inv<R2>(x);
 #pragma unroll
@@ -405,10 +503,20 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
     {
       const double2 *row = buf + pA * M;
       double2 x[16];
+      if (TMEM_TW) {
 #pragma unroll
-      for (int pos = 0; pos < 16; ++pos) {
-        const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);
-        x[pos] = cmul_conj(row[pos * S + qsw[pos & (NVA - 1)]], t);
+        for (int g4 = 0; g4 < 4; ++g4) {
+          double2 tw[4];
+          tmem_ld4(tw, tw_taddr + 16 * g4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[4 * g4 + i] = cmul_conj(row[(4 * g4 + i) * S + qsw[(4 * g4 + i) & (NVA - 1)]], tw[i]);
+        }
+      } else {
+#pragma unroll
+        for (int pos = 0; pos < 16; ++pos) {
+          const double2 t = __ldg(&TA[brev(pos, 4) * S + qA]);
+          x[pos] = cmul_conj(row[pos * S + qsw[pos & (NVA - 1)]], t);
+        }
       }
       reg_dit_inv<16>(x);
       u64 *ap = acc + pA * N;
@@ -429,6 +537,9 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
     __syncthreads();
   }
 
+  if (TMEM_TW) {                                       // every thread is past its last tcgen05.ld (block barrier above)
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(TMEM_COLS) : "memory");
+  }
   // ---- epilogue: sample extraction at index 0 (trlwe.c:540-552) or the raw accumulator -------------
   if (!live) return;
   if (A.extract) {
