@@ -23,6 +23,28 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const double2 (&v)[4]) 
       "r"(__double2hiint(v[3].y))
       : "memory");
 }
+// 16 raw words: 4 x (acc[j], acc[j + M]) as u64 pairs
+__device__ __forceinline__ void tmem_st_u64x8(unsigned taddr, const u64 (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"((unsigned)v[0]), "r"((unsigned)(v[0] >> 32)), "r"((unsigned)v[1]), "r"((unsigned)(v[1] >> 32)),
+      "r"((unsigned)v[2]), "r"((unsigned)(v[2] >> 32)), "r"((unsigned)v[3]), "r"((unsigned)(v[3] >> 32)),
+      "r"((unsigned)v[4]), "r"((unsigned)(v[4] >> 32)), "r"((unsigned)v[5]), "r"((unsigned)(v[5] >> 32)),
+      "r"((unsigned)v[6]), "r"((unsigned)(v[6] >> 32)), "r"((unsigned)v[7]), "r"((unsigned)(v[7] >> 32))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_u64x8(u64 (&v)[8], unsigned taddr) {
+  unsigned w[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ((u64)w[2 * i + 1] << 32) | (u64)w[2 * i];
+}
 __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
   int w[16];
   asm volatile(
@@ -101,8 +123,16 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   constexpr bool TMEM_TW = false;
 #endif
   // pass-B / B' twiddles too when they fill whole 16-word groups (R2 = 4, 8): columns 64 .. 64 + 4*R2
-  constexpr bool TMEM_TB = TMEM_TW && (R2 == 4 || R2 == 8);
-  constexpr int TMEM_COLS = TMEM_TB ? 128 : 64;
+  // ... and the 32 accumulator words a thread owns (columns 64..127), so that only the ROTATED reads of pass A go to
+  // shared memory; N >= 1024 only (at N = 512 up to 8 CTAs share the SM's 512 columns)
+#ifndef MB200_NO_TMEM_ACC
+  constexpr bool TMEM_ACC = TMEM_TW && !DIRECT && LOGM >= 9;
+#else
+  constexpr bool TMEM_ACC = false;
+#endif
+  constexpr int COL_ACC = 64, COL_TB = TMEM_ACC ? 128 : 64;
+  constexpr bool TMEM_TB = TMEM_TW && (R2 == 8 || (R2 == 4 && !TMEM_ACC));   // 4 CTAs x 128 columns at N = 1024
+  constexpr int TMEM_COLS = TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
   __shared__ unsigned tmem_base_s;
   unsigned tw_taddr = 0;
   if (TMEM_TW) {
@@ -129,7 +159,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         double2 tw[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) tw[i] = __ldg(&A.tab[16 * (M / 16) + (4 * g4 + i) * 8 + (tid & 7)]);   // TB[k*8 + qpB]
-        tmem_st4(tw_taddr + 64 + 16 * g4, tw);
+        tmem_st4(tw_taddr + COL_TB + 16 * g4, tw);
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -158,6 +188,18 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
     rot[i] = (unsigned short)(torus2int(av, log_N2) & (2 * N - 1));
   }
   __syncthreads();
+  if (TMEM_ACC) {                                     // park the accumulator words this thread owns (pass A / A' ownership)
+    const int pA0 = tid / (M / 16), qA0 = tid - pA0 * (M / 16);
+    const u64 *ap0 = acc + pA0 * N;
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      u64 v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = ap0[qA0 + (4 * g4 + i) * (M / 16)]; v[2 * i + 1] = ap0[qA0 + (4 * g4 + i) * (M / 16) + M]; }
+      tmem_st_u64x8(tw_taddr + COL_ACC + 16 * g4, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
 
   const u64 off = decomp_offset(Bg_bit, L);
   const unsigned dmask = (1u << Bg_bit) - 1u;
@@ -184,7 +226,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
 #pragma unroll
       for (int g4 = 0; g4 < R2 / 4; ++g4) {
         double2 tw[4];
-        tmem_ld4(tw, tw_taddr + 64 + 16 * g4);
+        tmem_ld4(tw, tw_taddr + COL_TB + 16 * g4);
 #pragma unroll
         for (int i = 0; i < 4; ++i) tb[(4 * g4 + i) & (R2 - 1)] = tw[i];
       }
@@ -214,6 +256,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       const u64 *ap = acc + pA * N;
       const int pk_shift = 64 - lev_end * Bg_bit;
       const int base = (qA - a_i) & (2 * N - 1);       // index of coefficient qA in acc * X^a (sign in bit log2 N)
+      u64 own[8];                                      // TMEM_ACC: acc[j], acc[j + M] of 4 consecutive m
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int j = qA + m * S;
@@ -224,7 +267,8 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         }
         const int s0 = (base + m * S) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
         const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
-        const u64 t0 = off - ap[j], t1 = off - ap[j + M];
+        if (TMEM_ACC && (m & 3) == 0) tmem_ld_u64x8(own, tw_taddr + COL_ACC + 4 * m);
+        const u64 t0 = off - (TMEM_ACC ? own[2 * (m & 3)] : ap[j]), t1 = off - (TMEM_ACC ? own[2 * (m & 3) + 1] : ap[j + M]);
         const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
         const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
         pk0[m] = (unsigned)(v0 >> pk_shift);
@@ -521,6 +565,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       reg_dit_inv<16>(x);
       u64 *ap = acc + pA * N;
       const u64 *addp = (DIRECT && A.in1) ? A.in1 + (size_t)ct * 2 * N + pA * N : nullptr;
+      u64 ownA[8];
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const double2 z = mul_w64(x[m], m, true);
@@ -528,11 +573,20 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         if (DIRECT) {                                  // trlwe_from_DFT (+ in1 for a CMUX, vertical_packing.c:30)
           ap[j] = f64_to_torus_fast(z.x * inv_M) + (addp ? addp[j] : 0ull);
           ap[j + M] = f64_to_torus_fast(z.y * inv_M) + (addp ? addp[j + M] : 0ull);
+        } else if (TMEM_ACC) {
+          if ((m & 3) == 0) tmem_ld_u64x8(ownA, tw_taddr + COL_ACC + 4 * m);
+          const u64 n0 = ownA[2 * (m & 3)] + f64_to_torus_fast(z.x * inv_M);
+          const u64 n1 = ownA[2 * (m & 3) + 1] + f64_to_torus_fast(z.y * inv_M);
+          ownA[2 * (m & 3)] = n0; ownA[2 * (m & 3) + 1] = n1;
+          ap[j] = n0;                                  // shared copy: read (rotated) by other threads in the next step
+          ap[j + M] = n1;
+          if ((m & 3) == 3) tmem_st_u64x8(tw_taddr + COL_ACC + 4 * (m - 3), ownA);
         } else {
           ap[j] += f64_to_torus_fast(z.x * inv_M);     // trlwe_from_DFT + trlwe_addto
           ap[j + M] += f64_to_torus_fast(z.y * inv_M);
         }
       }
+      if (TMEM_ACC) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     __syncthreads();
   }
