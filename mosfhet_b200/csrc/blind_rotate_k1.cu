@@ -173,6 +173,7 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 3, 3, 1, 0)
   MB_K1_CASE(9, 3, 2, 1, 2) MB_K1_CASE(9, 3, 3, 1, 2) MB_K1_CASE(10, 4, 2, 1, 2)
   MB_K1_CASE(9, 3, 2, 1, 3) MB_K1_CASE(9, 3, 3, 1, 3) MB_K1_CASE(10, 4, 2, 1, 3)
+  MB_K1_CASE(9, 3, 1, 5, 0) MB_K1_CASE(9, 3, 1, 6, 0) MB_K1_CASE(9, 3, 1, 5, 3) MB_K1_CASE(9, 3, 1, 6, 3) MB_K1_CASE(9, 3, 1, 1, 3)
 #endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
