@@ -369,6 +369,39 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
 #ifdef MB200_ABL_NOPASSB
       if (a_i < 0)
 #endif
+#ifdef MB200_PB_PIPE
+      constexpr bool PB_PIPE = (TASKS_B % 2 == 0);
+#else
+      constexpr bool PB_PIPE = false;
+#endif
+      if constexpr (PB_PIPE) {
+        // software pipeline: the loads of task it+1 are issued before the butterflies of task it (tasks touch
+        // disjoint blocks, so in-place is safe); pass B is shared-memory latency bound (ncu: 41-49 % short scoreboard)
+        auto blk_of = [&](int it) { return buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0; };
+        auto ld = [&](double2 (&x)[R2], int it) {
+          const double2 *blk = blk_of(it);
+#pragma unroll
+          for (int m = 0; m < R2; ++m) x[m] = blk[8 * m + qx[m]];
+        };
+        auto fin = [&](double2 (&x)[R2], int it) {
+          double2 *blk = blk_of(it);
+          reg_dif<R2>(x);
+#pragma unroll
+          for (int pos = 0; pos < R2; ++pos) {
+            const int k = brev(pos, LOGR2);
+            blk[8 * pos + qx[pos]] = k == 0 ? x[pos] : cmul(x[pos], tb[k]);
+          }
+        };
+        double2 xa[R2], xb[R2];
+        ld(xa, 0);
+#pragma unroll 1
+        for (int it = 0; it < TASKS_B; it += 2) {
+          ld(xb, it + 1);
+          fin(xa, it);
+          if (it + 2 < TASKS_B) ld(xa, it + 2);
+          fin(xb, it + 1);
+        }
+      } else {
 #pragma unroll(PB_UNROLL)
       for (int it = 0; it < TASKS_B; ++it) {
         // task = tid + it*T: row = task >> 7, block b = (task & 127) >> 3 = (tid >> 3) + it*(T/8) (mod 16)
@@ -383,6 +416,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
           const double2 y = k == 0 ? x[pos] : cmul(x[pos], tb[k]);
           blk[8 * pos + qx[pos]] = y;
         }
+      }
       }
       __syncthreads();
       // ------------------------------- pass C + MAC ----------------------------------------------
