@@ -45,6 +45,41 @@ __device__ __forceinline__ void tmem_ld_u64x8(u64 (&v)[8], unsigned taddr) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = ((u64)w[2 * i + 1] << 32) | (u64)w[2 * i];
 }
+// tcgen05.ld.16x256b.x1 (measured mapping, profiles/r1r_tmem_shapes.log): thread t receives the 64-bit word at columns
+// 2(t%4), 2(t%4)+1 of lane L0 + t/4 and of lane L0 + 8 + t/4 (L0 = lane field of taddr, 0 or 16 inside the warp's window)
+__device__ __forceinline__ void tmem_ld_16x256(double &lo_lane, double &hi_lane, unsigned taddr) {
+  int w0, w1, w2, w3;
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(taddr) : "memory");
+  lo_lane = __hiloint2double(w1, w0);
+  hi_lane = __hiloint2double(w3, w2);
+}
+// .x4: four consecutive 256-bit windows (32 columns); registers 4i..4i+3 belong to window i with the same pattern
+__device__ __forceinline__ void tmem_ld_16x256_x4(double (&lo)[4], double (&hi)[4], unsigned taddr) {
+  int w[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lo[i] = __hiloint2double(w[4 * i + 1], w[4 * i]);
+    hi[i] = __hiloint2double(w[4 * i + 3], w[4 * i + 2]);
+  }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_f64x8(unsigned taddr, double a0, double a1, double a2, double a3, double a4,
+                                              double a5, double a6, double a7) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__double2loint(a0)), "r"(__double2hiint(a0)), "r"(__double2loint(a1)), "r"(__double2hiint(a1)),
+      "r"(__double2loint(a2)), "r"(__double2hiint(a2)), "r"(__double2loint(a3)), "r"(__double2hiint(a3)),
+      "r"(__double2loint(a4)), "r"(__double2hiint(a4)), "r"(__double2loint(a5)), "r"(__double2hiint(a5)),
+      "r"(__double2loint(a6)), "r"(__double2hiint(a6)), "r"(__double2loint(a7)), "r"(__double2hiint(a7))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
   int w[16];
   asm volatile(
@@ -125,14 +160,24 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   // pass-B / B' twiddles too when they fill whole 16-word groups (R2 = 4, 8): columns 64 .. 64 + 4*R2
   // ... and the 32 accumulator words a thread owns (columns 64..127), so that only the ROTATED reads of pass A go to
   // shared memory; N >= 1024 only (at N = 512 up to 8 CTAs share the SM's 512 columns)
+  // ... and, at N = 1024 where a row's pass-A threads are exactly one warp, the pass A -> pass B exchange itself: the
+  // warp parks its 16 x 32 transformed values (real / imaginary parts in separate column groups) and reads them back
+  // with the 16x256b shape, which hands thread t the stride-8 lanes t/4 + 8m of a radix-4 group.  That takes the
+  // pass-A stores and the pass-B loads (a third of the kernel's L1 wavefronts) and one block barrier out of the batch.
+#ifdef MB200_TMEM_XB
+  constexpr bool TMEM_XB = TMEM_TW && LOGM == 9;
+#else
+  constexpr bool TMEM_XB = false;
+#endif
 #ifndef MB200_NO_TMEM_ACC
-  constexpr bool TMEM_ACC = TMEM_TW && !DIRECT && LOGM >= 9;
+  constexpr bool TMEM_ACC = TMEM_TW && !DIRECT && LOGM >= 9 && !TMEM_XB;     // the column budget goes to the exchange
 #else
   constexpr bool TMEM_ACC = false;
 #endif
+  constexpr int COL_X = 64;
   constexpr int COL_ACC = 64, COL_TB = TMEM_ACC ? 128 : 64;
-  constexpr bool TMEM_TB = TMEM_TW && (R2 == 8 || (R2 == 4 && !TMEM_ACC));   // 4 CTAs x 128 columns at N = 1024
-  constexpr int TMEM_COLS = TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
+  constexpr bool TMEM_TB = TMEM_TW && !TMEM_XB && (R2 == 8 || (R2 == 4 && !TMEM_ACC));   // 4 CTAs x 128 columns at N = 1024
+  constexpr int TMEM_COLS = TMEM_XB ? 128 : TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
   __shared__ unsigned tmem_base_s;
   unsigned tw_taddr = 0;
   if (TMEM_TW) {
@@ -303,7 +348,52 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         }
         reg_dif<16>(x);
         double2 *row = buf + (pA * NB + lb) * M;
-        if (TMEM_TW) {
+        if constexpr (TMEM_XB) {
+          // twiddle, park in tensor memory: column COL_X + 2*pos = Re, COL_X + 32 + 2*pos = Im of element (block pos, lane qA)
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            double2 tw[4];
+            tmem_ld4(tw, tw_taddr + 16 * g4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[4 * g4 + i] = cmul(x[4 * g4 + i], tw[i]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_st_f64x8(tw_taddr + COL_X + 16 * h, x[8 * h].x, x[8 * h + 1].x, x[8 * h + 2].x, x[8 * h + 3].x,
+                          x[8 * h + 4].x, x[8 * h + 5].x, x[8 * h + 6].x, x[8 * h + 7].x);
+            tmem_st_f64x8(tw_taddr + COL_X + 32 + 16 * h, x[8 * h].y, x[8 * h + 1].y, x[8 * h + 2].y, x[8 * h + 3].y,
+                          x[8 * h + 4].y, x[8 * h + 5].y, x[8 * h + 6].y, x[8 * h + 7].y);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          // pass B of this row by the same warp: thread (qB, cB) = (lane / 4, lane % 4) takes the radix-4 groups
+          // (block p0 + cB, lanes qB + 8m), p0 = 0, 4, 8, 12, and writes the row buffer pass C reads
+          const int lane = tid & 31, qB = lane >> 2, cB = lane & 3;
+          double2 tbx[4];
+#pragma unroll
+          for (int k = 1; k < 4; ++k) tbx[k] = __ldg(&TB[k * 8 + qB]);
+          {
+            // all four groups of the thread at once: 4 x (16x256b.x4) = the whole 32-column Re / Im group groups of lanes
+            // qB, qB + 8 (address lane 0) and qB + 16, qB + 24 (address lane 16); window i holds block 4i + cB
+            double r0[4], r1[4], r2[4], r3[4], i0[4], i1[4], i2[4], i3[4];
+            tmem_ld_16x256_x4(r0, r1, tw_taddr + COL_X);
+            tmem_ld_16x256_x4(r2, r3, tw_taddr + (16u << 16) + COL_X);
+            tmem_ld_16x256_x4(i0, i1, tw_taddr + COL_X + 32);
+            tmem_ld_16x256_x4(i2, i3, tw_taddr + (16u << 16) + COL_X + 32);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              double2 y[4] = {make_double2(r0[g], i0[g]), make_double2(r1[g], i1[g]), make_double2(r2[g], i2[g]),
+                              make_double2(r3[g], i3[g])};
+              reg_dif<4>(y);
+              const int b = 4 * g + cB;
+#pragma unroll
+              for (int pos = 0; pos < 4; ++pos) {
+                const int k = brev(pos, 2);
+                row[b * S + 8 * pos + (qB ^ ((4 * b + pos) & 7))] = k == 0 ? y[pos] : cmul(y[pos], tbx[k]);
+              }
+            }
+          }
+        } else if (TMEM_TW) {
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             double2 tw[4];
@@ -319,7 +409,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
           }
         }
       }
-      __syncthreads();
+      if constexpr (!TMEM_XB) __syncthreads();
       // key rows of this batch: row index of buffer rb
       auto key_row = [&](int rb) {
         const int p = rb / NB, lev = lev0 + (rb - p * NB);
@@ -365,10 +455,11 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       constexpr int TASKS_B = ROWS_B * 128 / T;
       static_assert(TASKS_B * T == ROWS_B * 128, "pass B tasks must tile the CTA");
       double2 tb[R2];
-      load_tb(tb);
+      if constexpr (!TMEM_XB) load_tb(tb);
 #ifdef MB200_ABL_NOPASSB
       if (a_i < 0)
 #endif
+      if constexpr (!TMEM_XB) {
 #ifdef MB200_PB_PIPE
       constexpr bool PB_PIPE = (TASKS_B % 2 == 0);
 #else
@@ -418,6 +509,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         }
       }
       }
+      }   // !TMEM_XB
       __syncthreads();
       // ------------------------------- pass C + MAC ----------------------------------------------
       if (PF == 1) {
