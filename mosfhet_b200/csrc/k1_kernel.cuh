@@ -80,6 +80,22 @@ __device__ __forceinline__ void tmem_st_f64x8(unsigned taddr, double a0, double 
       "r"(__double2loint(a6)), "r"(__double2hiint(a6)), "r"(__double2loint(a7)), "r"(__double2hiint(a7))
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_u32x16(unsigned taddr, const unsigned (&w)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+      "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_u32x16(unsigned (&w)[16], unsigned taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
   int w[16];
   asm volatile(
@@ -175,9 +191,19 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
   constexpr bool TMEM_ACC = false;
 #endif
   constexpr int COL_X = 64;
+  // ... and, when the l levels do not fit one 32-bit word per coefficient (PKALL = false) but the levels after the first
+  // batch do, the low digit word of every coefficient: the digits are then extracted ONCE per step (one pass over the
+  // accumulator, rotated reads included) instead of once per batch.  Needs 32 spare columns: N >= 2048 (256 per CTA).
+#ifndef MB200_NO_TMEM_PK
+  constexpr bool TMEM_PK = TMEM_TW && !PKALL && !DIRECT && LOGM >= 10 && (L - LB) <= LB && (L - LB) >= 1;
+#else
+  constexpr bool TMEM_PK = false;
+#endif
+  constexpr int COL_PK = 160;
   constexpr int COL_ACC = 64, COL_TB = TMEM_ACC ? 128 : 64;
   constexpr bool TMEM_TB = TMEM_TW && !TMEM_XB && (R2 == 8 || (R2 == 4 && !TMEM_ACC));   // 4 CTAs x 128 columns at N = 1024
-  constexpr int TMEM_COLS = TMEM_XB ? 128 : TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
+  constexpr int TMEM_COLS = TMEM_PK ? 256 : TMEM_XB ? 128 : TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
+  static_assert(!TMEM_PK || (COL_TB + 32 <= COL_PK), "tensor-memory column layout");
   __shared__ unsigned tmem_base_s;
   unsigned tw_taddr = 0;
   if (TMEM_TW) {
@@ -302,6 +328,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       const int pk_shift = 64 - lev_end * Bg_bit;
       const int base = (qA - a_i) & (2 * N - 1);       // index of coefficient qA in acc * X^a (sign in bit log2 N)
       u64 own[8];                                      // TMEM_ACC: acc[j], acc[j + M] of 4 consecutive m
+      unsigned plo[16];                                // TMEM_PK: low digit words of 8 consecutive m
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int j = qA + m * S;
@@ -316,17 +343,38 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
         const u64 t0 = off - (TMEM_ACC ? own[2 * (m & 3)] : ap[j]), t1 = off - (TMEM_ACC ? own[2 * (m & 3) + 1] : ap[j + M]);
         const u64 v0 = (s0 & N) ? t0 - r0 : t0 + r0;
         const u64 v1 = (s1 & N) ? t1 - r1 : t1 + r1;
-        pk0[m] = (unsigned)(v0 >> pk_shift);
-        pk1[m] = (unsigned)(v1 >> pk_shift);
+        if (TMEM_PK) {
+          // w = top L*Bg_bit bits; registers keep the first batch's levels, tensor memory the remaining ones
+          const int lo_bits = (L - LB) * Bg_bit;
+          const u64 w0 = v0 >> pk_shift, w1 = v1 >> pk_shift;
+          pk0[m] = (unsigned)(w0 >> lo_bits);
+          pk1[m] = (unsigned)(w1 >> lo_bits);
+          plo[2 * (m & 7)] = (unsigned)w0 & ((1u << lo_bits) - 1u);
+          plo[2 * (m & 7) + 1] = (unsigned)w1 & ((1u << lo_bits) - 1u);
+          if ((m & 7) == 7) tmem_st_u32x16(tw_taddr + COL_PK + 2 * (m - 7), plo);
+        } else {
+          pk0[m] = (unsigned)(v0 >> pk_shift);
+          pk1[m] = (unsigned)(v1 >> pk_shift);
+        }
       }
+      if (TMEM_PK) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     };
-    if (PKALL) pack_digits(L);
+    if (PKALL || TMEM_PK) pack_digits(L);
 
     // One batch = NB gadget levels of both input polynomials (2*NB rows of shared-memory buffers).
     auto batch = [&](auto nb_tag, const int lev0) {
       constexpr int NB = decltype(nb_tag)::value, ROWS_B = 2 * NB;
       // ------------------------------- pass A -------------------------------------------------
-      if (!PKALL) pack_digits(lev0 + NB);
+      if (!PKALL && !TMEM_PK) pack_digits(lev0 + NB);
+      if (TMEM_PK && lev0 > 0) {                        // the remaining levels' digit words, parked by pack_digits(L)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned w[16];
+          tmem_ld_u32x16(w, tw_taddr + COL_PK + 16 * h);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { pk0[8 * h + i] = w[2 * i]; pk1[8 * h + i] = w[2 * i + 1]; }
+        }
+      }
       // pass-A twiddles w^q * W_M^(q*k1): the same 16 values for every level of the batch -- loaded once
       // (the L1/shared-memory data pipe, not FP64, is the busiest unit of this kernel: ncu r1e)
       constexpr bool HOIST_TW = (LOGM <= 9) && !TMEM_TW;   // N = 2048+: registers are needed elsewhere (pass C key buffers)
@@ -337,7 +385,7 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
       }
 #pragma unroll(PA_UNROLL)
       for (int lb = 0; lb < NB; ++lb) {
-        const int sh = (PKALL ? (L - 1 - lev0 - lb) : (NB - 1 - lb)) * Bg_bit;
+        const int sh = ((PKALL || (TMEM_PK && lev0 > 0)) ? (L - 1 - lev0 - lb) : (NB - 1 - lb)) * Bg_bit;
         double2 x[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
