@@ -185,25 +185,28 @@ __global__ void MB200_K1_BOUNDS blind_rotate_k1_kernel(K1Args A) {
 #else
   constexpr bool TMEM_XB = false;
 #endif
-#ifndef MB200_NO_TMEM_ACC
-  constexpr bool TMEM_ACC = TMEM_TW && !DIRECT && LOGM >= 9 && !TMEM_XB;     // the column budget goes to the exchange
-#else
-  constexpr bool TMEM_ACC = false;
-#endif
   constexpr int COL_X = 64;
   // ... and, when the l levels do not fit one 32-bit word per coefficient (PKALL = false) but the levels after the first
   // batch do, the low digit word of every coefficient: the digits are then extracted ONCE per step (one pass over the
   // accumulator, rotated reads included) instead of once per batch.  Needs 32 spare columns: N >= 2048 (256 per CTA).
 #ifndef MB200_NO_TMEM_PK
-  constexpr bool TMEM_PK = TMEM_TW && !PKALL && !DIRECT && LOGM >= 10 && (L - LB) <= LB && (L - LB) >= 1;
+  constexpr bool TMEM_PK = TMEM_TW && !PKALL && !DIRECT && LOGM >= 9 && !TMEM_XB && (L - LB) <= LB && (L - LB) >= 1;
 #else
   constexpr bool TMEM_PK = false;
 #endif
-  constexpr int COL_PK = 160;
+  // column budget: 256 per CTA at N = 2048 (everything fits); 128 at N = 1024, where the digit words (worth 3.6 %)
+  // take the place of the owned accumulator words (worth 1.8 %)
+  constexpr int COL_PK = LOGM >= 10 ? 160 : 64;
+#ifndef MB200_NO_TMEM_ACC
+  constexpr bool TMEM_ACC = TMEM_TW && !DIRECT && LOGM >= 9 && !TMEM_XB && !(TMEM_PK && LOGM == 9);
+#else
+  constexpr bool TMEM_ACC = false;
+#endif
   constexpr int COL_ACC = 64, COL_TB = TMEM_ACC ? 128 : 64;
-  constexpr bool TMEM_TB = TMEM_TW && !TMEM_XB && (R2 == 8 || (R2 == 4 && !TMEM_ACC));   // 4 CTAs x 128 columns at N = 1024
-  constexpr int TMEM_COLS = TMEM_PK ? 256 : TMEM_XB ? 128 : TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
-  static_assert(!TMEM_PK || (COL_TB + 32 <= COL_PK), "tensor-memory column layout");
+  constexpr bool TMEM_TB = TMEM_TW && !TMEM_XB && (R2 == 8 || (R2 == 4 && !TMEM_ACC && !TMEM_PK));   // 4 CTAs x 128 columns at N = 1024
+  constexpr int TMEM_COLS = (TMEM_PK && LOGM >= 10) ? 256 : (TMEM_PK || TMEM_XB) ? 128 : TMEM_TB ? (TMEM_ACC ? 256 : 128) : (TMEM_ACC ? 128 : 64);
+  static_assert(!(TMEM_PK && LOGM >= 10) || (COL_TB + 32 <= COL_PK), "tensor-memory column layout");
+  static_assert(!(TMEM_PK && TMEM_ACC && COL_PK == COL_ACC), "tensor-memory column layout");
   __shared__ unsigned tmem_base_s;
   unsigned tw_taddr = 0;
   if (TMEM_TW) {

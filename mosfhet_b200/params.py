@@ -54,4 +54,7 @@ SET_1 = Params(n=585, N=1024, k=1, l=2, Bg_bit=8, t=5, base_bit=2, lwe_sigma=9.1
 SET_2 = Params(n=744, N=2048, k=1, l=1, Bg_bit=23, t=5, base_bit=3, lwe_sigma=7.747831515176779e-6,
                rlwe_sigma=2.2148688116005568e-16)
 
-NAMED = {"level2": LEVEL2, "level1": LEVEL1, "set1": SET_1, "set2": SET_2}
+# circuit-bootstrap shape of scripts/bench_next.py config 4b: Level-2 gadget on the N = 1024 ring
+CB_1024 = Params(n=632, N=1024, k=1, l=4, Bg_bit=9, t=6, base_bit=4, lwe_sigma=2.0 ** -30, rlwe_sigma=2.0 ** -55)
+
+NAMED = {"level2": LEVEL2, "level1": LEVEL1, "set1": SET_1, "set2": SET_2, "cb1024": CB_1024}
