@@ -134,6 +134,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
       }
     }
     __syncthreads();
+    // key rows: double buffered in registers -- row 0 is requested here and flies under pass B, row rb + 1 under the
+    // butterflies of row rb (with one CTA per SM nothing else hides the L2 latency; the throughput kernel does not need this)
+    double2 kv[2][16];
+    auto load_keys = [&](double2 (&dst)[16], int rb) {
+      const double2 *__restrict__ k0 = key + (size_t)rb * 2 * M + tid;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
+    };
+    load_keys(kv[0], 0);
     // ------------------------------- pass B: radix R2 in shared memory ---------------------------------------
     constexpr int TASKS_B = L * 128 / T > 0 ? L * 128 / T : 1;
 #pragma unroll 2
@@ -151,19 +160,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     }
     __syncthreads();
     // ------------------------------- pass C + MAC against key rows p*l + lev -------------------------------
-#pragma unroll 2
-    for (int rb = 0; rb < L; ++rb) {
-      const double2 *__restrict__ k0 = key + (size_t)rb * 2 * M + tid;
-      double2 kv[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { kv[i] = ldg_key(k0 + i * C8); kv[8 + i] = ldg_key(k0 + M + i * C8); }
+    for (int rb = 0; rb < L; ++rb) {
+      if (rb + 1 < L) load_keys(kv[(rb + 1) & 1], rb + 1);
       const double2 *row = buf + rb * M;
       double2 x[8];
 #pragma unroll
       for (int m = 0; m < 8; ++m) x[m] = row[8 * tid + (m ^ (tid & 7))];
       reg_dif<8>(x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { cfma(f0[i], x[i], kv[i]); cfma(f1[i], x[i], kv[8 + i]); }
+      for (int i = 0; i < 8; ++i) { cfma(f0[i], x[i], kv[rb & 1][i]); cfma(f1[i], x[i], kv[rb & 1][8 + i]); }
     }
     // ------------------------------- exchange: the other polynomial's partial sum goes to the peer ------------
     double2 mine[8];

@@ -127,6 +127,16 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
         }
       }
       __syncthreads();
+      // key rows double buffered in registers (this is the small-batch kernel: few resident CTAs, nothing else hides
+      // the L2 latency): row 0 of the batch is requested here and flies under pass B, row lb + 1 under the butterflies of lb
+      double2 kv[2][16];
+      auto load_keys = [&](double2 (&dst)[16], int lb) {
+        const int r = hC * L + lev0 + lb;                               // TRGSW row (trgsw.c:394-419 order)
+        const double2 *__restrict__ k0 = key + (size_t)(r * 2) * M + cC;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
+      };
+      load_keys(kv[0], 0);
       // ------------------------------- pass B: RB*64 radix-R2 butterflies ------------------------
       constexpr int TASKS_B = (RB * 64 + T - 1) / T;
 #pragma unroll
@@ -149,18 +159,14 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
       // ------------------------------- pass C + MAC: rows of input polynomial hC -----------------
 #pragma unroll
       for (int lb = 0; lb < NB; ++lb) {
-        const int r = hC * L + lev0 + lb;                               // TRGSW row (trgsw.c:394-419 order)
-        const double2 *__restrict__ k0 = key + (size_t)(r * 2) * M + cC;
-        double2 kv[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { kv[i] = ldg_key(k0 + i * C8); kv[8 + i] = ldg_key(k0 + M + i * C8); }
+        if (lb + 1 < NB) load_keys(kv[(lb + 1) & 1], lb + 1);
         const double2 *row = buf + (hC * NB + lb) * M + 8 * cC;
         double2 x[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) x[m] = row[m ^ (cC & 7)];
         reg_dif<8>(x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[i]); cfma(fa[1][i], x[i], kv[8 + i]); }
+        for (int i = 0; i < 8; ++i) { cfma(fa[0][i], x[i], kv[lb & 1][i]); cfma(fa[1][i], x[i], kv[lb & 1][8 + i]); }
       }
       __syncthreads();
     };
