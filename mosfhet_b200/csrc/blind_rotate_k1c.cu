@@ -56,6 +56,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
   const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N + (size_t)p_own * N;
   const int Bg_bit = A.Bg_bit;
 
+  // The cluster barrier of every step invalidates L1 (it is a cluster-scope acquire), so twiddles re-read from global
+  // memory miss L1 every step (ncu: long scoreboard in pass A / B): they live in the thread's tensor-memory lane instead
+  // (columns 0..63: pass A / A', 64..64+4*R2: pass B / B').
+  __shared__ unsigned tmem_base_s;
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n\t"
+                 "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+                 ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tw_taddr = tmem_base_s + ((unsigned)(tid >> 5) << 21);
+  {
+    const int qA0 = tid % S;
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      double2 tw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tw[i] = __ldg(&TA[brev(4 * g4 + i, 4) * S + qA0]);
+      tmem_st4(tw_taddr + 16 * g4, tw);
+    }
+#pragma unroll
+    for (int g4 = 0; g4 < (R2 + 3) / 4; ++g4) {
+      double2 tw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tw[i] = __ldg(&TB[((4 * g4 + i) & (R2 - 1)) * 8 + (tid & 7)]);
+      tmem_st4(tw_taddr + 64 + 16 * g4, tw);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  auto load_tb = [&](double2 (&tb)[R2 < 4 ? 4 : R2]) {
+#pragma unroll
+    for (int g4 = 0; g4 < (R2 + 3) / 4; ++g4) {
+      double2 tw[4];
+      tmem_ld4(tw, tw_taddr + 64 + 16 * g4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tb[4 * g4 + i] = tw[i];
+    }
+  };
+
   int rot0 = 0;
   if (A.init_rotate) {
     u64 b = in[A.size];
@@ -96,6 +137,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     const int a_i = rot[step];
     if (a_i == 0) continue;                           // bootstrap.c:114 (both CTAs see the same mask)
     const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M + (size_t)(p_own * L) * 2 * M;
+    // a single bootstrap reads every key row exactly once (L2 hit rate 4 % at batch 1): pull the NEXT step's rows of
+    // this CTA (l rows x 2 polynomials x M x 16 B) into L2 now, one 128-byte line per thread and iteration
+    if (step + 1 < A.size) {
+      const char *nxt = reinterpret_cast<const char *>(key + (size_t)ROWS * 2 * M);
+      for (int off = tid * 128; off < L * 2 * M * 16; off += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + off));
+    }
 
     double2 f0[8], f1[8];                             // partial Fourier sums for output polynomials 0 and 1
 #pragma unroll
@@ -129,8 +176,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
         reg_dif<16>(x);
         double2 *row = buf + (2 * pA + it) * M;
 #pragma unroll
-        for (int pos = 0; pos < 16; ++pos)
-          row[pos * S + qsw[pos & (NVA - 1)]] = cmul(x[pos], __ldg(&TA[brev(pos, 4) * S + qA]));
+        for (int g4 = 0; g4 < 4; ++g4) {
+          double2 tw[4];
+          tmem_ld4(tw, tw_taddr + 16 * g4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) row[(4 * g4 + i) * S + qsw[(4 * g4 + i) & (NVA - 1)]] = cmul(x[4 * g4 + i], tw[i]);
+        }
       }
     }
     __syncthreads();
@@ -145,6 +196,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     load_keys(kv[0], 0);
     // ------------------------------- pass B: radix R2 in shared memory ---------------------------------------
     constexpr int TASKS_B = L * 128 / T > 0 ? L * 128 / T : 1;
+    double2 tb[R2 < 4 ? 4 : R2];
+    load_tb(tb);
 #pragma unroll 2
     for (int it = 0; it < TASKS_B; ++it) {
       double2 *blk = buf + ((it * T) >> 7) * M + (((it * T) & 127) >> 3) * S + bB0;
@@ -155,7 +208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
 #pragma unroll
       for (int pos = 0; pos < R2; ++pos) {
         const int k = brev(pos, LOGR2);
-        blk[8 * pos + qx[pos]] = k == 0 ? x[pos] : cmul(x[pos], __ldg(&TB[k * 8 + qpB]));
+        blk[8 * pos + qx[pos]] = k == 0 ? x[pos] : cmul(x[pos], tb[k]);
       }
     }
     __syncthreads();
@@ -198,7 +251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
       for (int pos = 0; pos < R2; ++pos) {
         const int k = brev(pos, LOGR2);
         const double2 y = blk[8 * pos + qx[pos]];
-        x[pos] = k == 0 ? y : cmul_conj(y, __ldg(&TB[k * 8 + qpB]));
+        x[pos] = k == 0 ? y : cmul_conj(y, tb[k]);
       }
       reg_dit_inv<R2>(x);
 #pragma unroll
@@ -208,8 +261,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     if (pA == 0) {
       double2 x[16];
 #pragma unroll
-      for (int pos = 0; pos < 16; ++pos)
-        x[pos] = cmul_conj(buf[pos * S + qsw[pos & (NVA - 1)]], __ldg(&TA[brev(pos, 4) * S + qA]));
+      for (int g4 = 0; g4 < 4; ++g4) {
+        double2 tw[4];
+        tmem_ld4(tw, tw_taddr + 16 * g4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[4 * g4 + i] = cmul_conj(buf[(4 * g4 + i) * S + qsw[(4 * g4 + i) & (NVA - 1)]], tw[i]);
+      }
       reg_dit_inv<16>(x);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
@@ -222,6 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     __syncthreads();
   }
 
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base_s) : "memory");
   // ---- epilogue: extraction at index 0 (a part from polynomial 0, b from coefficient 0 of polynomial 1) or raw ----
   if (A.extract) {
     u64 *o = A.out + (size_t)ct * (N + 1);

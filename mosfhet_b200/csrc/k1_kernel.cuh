@@ -8,113 +8,6 @@
 
 namespace mb {
 
-// ---- tensor memory as a per-thread constant store (disable with MB200_NO_TMEM_TW) -----------------------------------------------
-// The 16 pass-A / A' twiddles of a thread are thread constants that do not fit the register budget, so they were
-// re-read from global memory (through the L1 data pipe, the busiest unit of this kernel) three times per step.
-// Blackwell's tensor memory is private per lane and has its own datapath: each thread parks its 64 words there once
-// (tcgen05.st) and fetches them 16 words at a time (tcgen05.ld.32x32b.x16) when needed.
-__device__ __forceinline__ void tmem_st4(unsigned taddr, const double2 (&v)[4]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)),
-      "r"(__double2hiint(v[0].y)), "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)), "r"(__double2loint(v[1].y)),
-      "r"(__double2hiint(v[1].y)), "r"(__double2loint(v[2].x)), "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)),
-      "r"(__double2hiint(v[2].y)), "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)),
-      "r"(__double2hiint(v[3].y))
-      : "memory");
-}
-// 16 raw words: 4 x (acc[j], acc[j + M]) as u64 pairs
-__device__ __forceinline__ void tmem_st_u64x8(unsigned taddr, const u64 (&v)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"((unsigned)v[0]), "r"((unsigned)(v[0] >> 32)), "r"((unsigned)v[1]), "r"((unsigned)(v[1] >> 32)),
-      "r"((unsigned)v[2]), "r"((unsigned)(v[2] >> 32)), "r"((unsigned)v[3]), "r"((unsigned)(v[3] >> 32)),
-      "r"((unsigned)v[4]), "r"((unsigned)(v[4] >> 32)), "r"((unsigned)v[5]), "r"((unsigned)(v[5] >> 32)),
-      "r"((unsigned)v[6]), "r"((unsigned)(v[6] >> 32)), "r"((unsigned)v[7]), "r"((unsigned)(v[7] >> 32))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_u64x8(u64 (&v)[8], unsigned taddr) {
-  unsigned w[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
-        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = ((u64)w[2 * i + 1] << 32) | (u64)w[2 * i];
-}
-// tcgen05.ld.16x256b.x1 (measured mapping, profiles/r1r_tmem_shapes.log): thread t receives the 64-bit word at columns
-// 2(t%4), 2(t%4)+1 of lane L0 + t/4 and of lane L0 + 8 + t/4 (L0 = lane field of taddr, 0 or 16 inside the warp's window)
-__device__ __forceinline__ void tmem_ld_16x256(double &lo_lane, double &hi_lane, unsigned taddr) {
-  int w0, w1, w2, w3;
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(taddr) : "memory");
-  lo_lane = __hiloint2double(w1, w0);
-  hi_lane = __hiloint2double(w3, w2);
-}
-// .x4: four consecutive 256-bit windows (32 columns); registers 4i..4i+3 belong to window i with the same pattern
-__device__ __forceinline__ void tmem_ld_16x256_x4(double (&lo)[4], double (&hi)[4], unsigned taddr) {
-  int w[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
-        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    lo[i] = __hiloint2double(w[4 * i + 1], w[4 * i]);
-    hi[i] = __hiloint2double(w[4 * i + 3], w[4 * i + 2]);
-  }
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_f64x8(unsigned taddr, double a0, double a1, double a2, double a3, double a4,
-                                              double a5, double a6, double a7) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(__double2loint(a0)), "r"(__double2hiint(a0)), "r"(__double2loint(a1)), "r"(__double2hiint(a1)),
-      "r"(__double2loint(a2)), "r"(__double2hiint(a2)), "r"(__double2loint(a3)), "r"(__double2hiint(a3)),
-      "r"(__double2loint(a4)), "r"(__double2hiint(a4)), "r"(__double2loint(a5)), "r"(__double2hiint(a5)),
-      "r"(__double2loint(a6)), "r"(__double2hiint(a6)), "r"(__double2loint(a7)), "r"(__double2hiint(a7))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_u32x16(unsigned taddr, const unsigned (&w)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
-      "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_u32x16(unsigned (&w)[16], unsigned taddr) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
-        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
-  int w[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
-        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    v[i] = make_double2(__hiloint2double(w[4 * i + 1], w[4 * i]), __hiloint2double(w[4 * i + 3], w[4 * i + 2]));
-}
-
-// G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
-// memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
-// are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
-// CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
-// G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
 #ifdef MB200_K1_MAXNREG
 #define MB200_K1_BOUNDS __maxnreg__(MB200_K1_MAXNREG)       // experiment: explicit register cap (build-wide)
 #else
