@@ -67,6 +67,10 @@ int main(void) {
   S(_TRGSW_DFT); P(_TRGSW_DFT, samples); P(_TRGSW_DFT, l); P(_TRGSW_DFT, Bg_bit);
   S(_Bootstrap_Key); P(_Bootstrap_Key, s); P(_Bootstrap_Key, su); P(_Bootstrap_Key, n); P(_Bootstrap_Key, k);
   P(_Bootstrap_Key, N); P(_Bootstrap_Key, Bg_bit); P(_Bootstrap_Key, l); P(_Bootstrap_Key, unfolding);
+  S(_TRGSW); P(_TRGSW, samples); P(_TRGSW, l); P(_TRGSW, Bg_bit);
+  S(_Generic_KS_Key); P(_Generic_KS_Key, s); P(_Generic_KS_Key, base_bit); P(_Generic_KS_Key, t); P(_Generic_KS_Key, n);
+  P(_Generic_KS_Key, include_b);
+  S(_TRLWE_KS_Key); P(_TRLWE_KS_Key, s); P(_TRLWE_KS_Key, base_bit); P(_TRLWE_KS_Key, t); P(_TRLWE_KS_Key, k);
   return 0;
 }
 """
@@ -85,7 +89,8 @@ def ctypes_layout():
     from mosfhet_b200 import abi
     pairs = [("_TorusPolynomial", abi.TorusPolynomialS), ("_DFT_Polynomial", abi.DFTPolynomialS), ("_TLWE", abi.TLWES),
              ("_TLWE_KS_Key", abi.TLWEKSKeyS), ("_TRLWE", abi.TRLWES), ("_TRLWE_DFT", abi.TRLWEDFTS),
-             ("_TRGSW_DFT", abi.TRGSWDFTS), ("_Bootstrap_Key", abi.BootstrapKeyS)]
+             ("_TRGSW_DFT", abi.TRGSWDFTS), ("_Bootstrap_Key", abi.BootstrapKeyS), ("_TRGSW", abi.TRGSWS),
+             ("_Generic_KS_Key", abi.GenericKSKeyS), ("_TRLWE_KS_Key", abi.TRLWEKSKeyS)]
     lines = []
     for name, cls in pairs:
         lines.append(f"{name} {C.sizeof(cls)}")
@@ -128,3 +133,16 @@ def test_host_struct_builders_roundtrip():
     ksk = rng.integers(0, 2**64, size=(8, 2, 3, 5), dtype=np.uint64)
     assert np.array_equal(abi.ks_key_to_flat(abi.HostKSKey(ksk, 2).handle), ksk)
     assert abi.HostTRLWE(p).polys.ctypes.data % 64 == 0
+    # the handle types of the circuit bootstrap / unfolded keys
+    g = rng.integers(0, 2**64, size=(5, 2, 3, 2, 16), dtype=np.uint64)
+    hg = abi.HostGenericKSKey(g, 2, 1)
+    assert np.array_equal(abi.generic_ks_key_to_flat(hg.handle), g) and hg.struct.n == 4 and hg.struct.include_b == 1
+    r = rng.standard_normal((1, 3, 2, 16))
+    assert np.array_equal(abi.trlwe_ks_key_to_flat(abi.HostTRLWEKSKey(r, 2).handle), r)
+    pair = abi.HostTRLWEKSKeyPair(rng.standard_normal((2, 3, 2, 16)), 2)
+    assert pair.handle[0].contents.t == 3 and pair.handle[1].contents.k == 1
+    tg = rng.integers(0, 2**64, size=(4, 2, 16), dtype=np.uint64)
+    assert np.array_equal(abi.trgsw_to_flat(abi.HostTRGSW(tg, 2, 8).handle, 1), tg)
+    su = rng.integers(0, 2**64, size=(8, 4, 2, 16), dtype=np.uint64)       # n = 4, unfolding = 2 -> 2 groups x 4
+    hu = abi.HostUnfoldedBootstrapKey(su, 4, 2, 1, 2, 8)
+    assert hu.struct.unfolding == 2 and np.array_equal(abi.trgsw_to_flat(hu.struct.su[5], 1), su[5])

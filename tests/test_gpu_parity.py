@@ -1072,3 +1072,44 @@ def test_vertical_packing_batch(N, l, Bg_bit):
     ph1 = O.tlwe_phase(to_np(d_r1), rlwe_key)
     assert sdiff(np.uint64(O.tlwe_phase(res[0], rlwe_key)), np.uint64(ph1)) <= phase_tol(l, Bg_bit)
     trgsw_bits.free()
+
+
+def test_next_rows_empty_batches_and_aborts(golden_cb):
+    """Edge cases of the SURVEY 8(f) entry points: empty batches are no-ops; a circuit bootstrap whose output gadget
+    length differs from the key's (the reference indexes its LUT with both, bootstrap.c:328-333) and a key switch
+    whose input dimension does not match abort with a message, like the reference's asserts."""
+    import subprocess, sys, textwrap
+    g, P = golden_cb, golden_cb["P"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], P["k"], P["l"], P["Bg_bit"])
+    ka = abi.HostGenericKSKey(g["kska"], P["base_bit"], 1)
+    kb = abi.HostGenericKSKey(g["kskb"], P["base_bit"], 0)
+    api.circuit_bootstrap_2_batch([], [], hbsk, ka, kb)
+    api.circuit_bootstrap_batch([], [], hbsk, ka, kb)
+    api.trlwe_priv_keyswitch_batch([], [], ka)
+    api.trlwe_packing1_keyswitch_batch([], [], kb)
+    api.functional_bootstrap_trgsw_phase1_batch([], [], hbsk, 4)
+    api.release_bootstrap_key(hbsk)
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from conftest import load_golden
+        from mosfhet_b200 import abi, api
+        g = load_golden("tiny_cb_spqlios"); P = g["P"]
+        api.init(0); api.set_host_fft_layout(g["layout"])
+        hbsk = abi.HostBootstrapKey(g["bsk_host"], P["k"], P["l"], P["Bg_bit"])
+        ka = abi.HostGenericKSKey(g["kska"], P["base_bit"], 1)
+        kb = abi.HostGenericKSKey(g["kskb"], P["base_bit"], 0)
+        which = sys.argv[1]
+        if which == "gadget":
+            out = abi.HostTRGSW(np.zeros((2 * (P["l"] + 1), 2, P["N"]), np.uint64), P["l"] + 1, P["Bg_bit"])
+            api.circuit_bootstrap_2(out, abi.HostTLWE(g["cb_in"][0]), hbsk, ka, kb)
+        else:
+            out = abi.HostTRLWE.zeros(1, P["N"])
+            api.trlwe_priv_keyswitch(out, abi.HostTLWE(g["ks_in"][0][:-3]), ka)      # TLWE of the wrong dimension
+        print("NOT REACHED")
+    """) % (ROOT_DIR, TESTS_DIR)
+    for which, word in (("gadget", "out->l"), ("dim", "dimension")):
+        r = subprocess.run([sys.executable, "-c", code, which], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "NOT REACHED" not in r.stdout, which
+        assert "mosfhet_b200:" in r.stderr and word in r.stderr, r.stderr[-400:]
