@@ -19,9 +19,18 @@ def one(count):
     e0.record(st); api.pbs_dev(bsk, d_out, d_tv, 1, d_in, 4, count, st.cuda_stream); e1.record(st)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1)
+import subprocess
+def smi(tag):
+    q = "clocks.sm,clocks.mem,clocks.gr,pstate,power.draw,temperature.gpu,clocks_throttle_reasons.active"
+    print(tag, subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 print("quiet  :", " ".join(f"{one(1):.2f}" for _ in range(8)))
+smi("quiet smi :")
+print("quiet B=148:", " ".join(f"{one(148):.2f}" for _ in range(4)))
 for _ in range(3): one(B)
 print("loaded :", " ".join(f"{one(1):.2f}" for _ in range(12)))
+smi("loaded smi:")
+print("loaded B=148:", " ".join(f"{one(148):.2f}" for _ in range(4)))
+print("loaded B=1 again:", " ".join(f"{one(1):.2f}" for _ in range(4)))
 import subprocess
 print(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
