@@ -134,7 +134,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
         const int r = hC * L + lev0 + lb;                               // TRGSW row (trgsw.c:394-419 order)
         const double2 *__restrict__ k0 = key + (size_t)(r * 2) * M + cC;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
+        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key_keep(k0 + i * C8); dst[8 + i] = ldg_key_keep(k0 + M + i * C8); }
       };
       load_keys(kv[0], 0);
       // ------------------------------- pass B: RB*64 radix-R2 butterflies ------------------------

@@ -211,16 +211,12 @@ __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
     v[i] = make_double2(__hiloint2double(w[4 * i + 1], w[4 * i]), __hiloint2double(w[4 * i + 3], w[4 * i + 2]));
 }
 
-// G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
-// memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
-// are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
-// CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
-// G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
-__device__ __forceinline__ double2 ldg_key(const double2 *p) {
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
+// Key rows are read with the plain read-only load.  The streaming form (ld.global.nc.L1::no_allocate), used while the
+// twiddles still competed for the 28 KB of L1, also leaves the lines first in line for eviction from L2: a single
+// bootstrap then re-reads the whole key from HBM every time once something else has displaced it (2.6 -> 3.4 ms,
+// scripts/latency_after_load.py), and the full batch is 2.3 % slower (profiles/r1p_k1_tmem.log).
+__device__ __forceinline__ double2 ldg_key(const double2 *p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldg_key_keep(const double2 *p) { return __ldg(p); }
 
 
 }  // namespace mb

@@ -8,6 +8,11 @@
 
 namespace mb {
 
+// G ciphertexts per CTA (G*T threads, each group of T threads owns one ciphertext and its own shared
+// memory region).  The groups run in lockstep (block barriers), so their loads of the same key row
+// are issued within one L2 round trip of each other and merge in L1: the key streams from L2 once per
+// CTA instead of once per ciphertext (ablation: key loads are 19 % / 27 % of the kernel at level 1 / 2).
+// G > 1 is an experiment knob (MB200_K1_G): it measured slower than G = 1, see launch_blind_rotate_k1.
 #ifdef MB200_K1_MAXNREG
 #define MB200_K1_BOUNDS __maxnreg__(MB200_K1_MAXNREG)       // experiment: explicit register cap (build-wide)
 #else
