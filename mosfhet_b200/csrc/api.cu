@@ -33,7 +33,12 @@ namespace {
 std::mutex g_mu;
 int g_host_layout = MB200_FFT_AUTO;
 int g_policy = 0;
-std::string g_last_kernel = "none";
+#ifndef MB200_K1Q_DEFAULT
+#define MB200_K1Q_DEFAULT false     // full batches: T = M/4 throughput kernel instead of the T = M/8 one
+#endif
+// name of the blind-rotation kernel this host thread dispatched last (entry points may be called from several threads)
+thread_local char t_last_kernel[96] = "none";
+void set_last_kernel(const char *name) { snprintf(t_last_kernel, sizeof(t_last_kernel), "%s", name); }
 std::map<const void *, mb200_bsk *> g_bsk_cache;   // keyed by Bootstrap_Key->s (the TRGSW_DFT array)
 std::map<const void *, mb200_ksk *> g_ksk_cache;   // keyed by TLWE_KS_Key->s
 struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; };
@@ -346,32 +351,35 @@ void table_ks_trlwe_dev(GkskDev *g, int mode, u64 *d_out, const u64 *d_in, int c
 // ---- dispatch ----------------------------------------------------------------------------------
 void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   if (a.count <= 0) return;
-  const bool can_k1 = g_policy == 0 && !a.direct && mb::k1_supported(a.bsk->p);
-  // policy 0: fastest available; 2: force the T = M/8 kernel; 3: force the T = M/4 kernel.
-  // The T = M/4 kernel has half the serial work per thread: faster while the GPU is not full (small
-  // batches / latency, profiles/r1j_latency.log), slower at full occupancy (profiles/r1f_k1h_variants.log).
-  const char *eh = getenv("MB200_K1H");
-  bool want_h = g_policy == 3 || (g_policy == 0 && a.count <= 2 * mb::sm_count() && a.bsk->p.N <= 1024);
-  if (g_policy == 0 && eh) want_h = eh[0] == '1';
-  // policy 4 / small batches: one ciphertext per 2-CTA cluster (two SMs per bootstrap) while the batch leaves at
-  // least half the SMs idle otherwise
-  const char *ec = getenv("MB200_K1C");
-  // (measured, profiles/r1o_latency.log: at N = 2048 4.9 ms instead of 8.6 ms per bootstrap; at N <= 1024 the T = M/4
-  // kernel below is faster still, 2.7 ms against 3.3 ms)
-  bool want_c = g_policy == 4 || (g_policy == 0 && 2 * a.count <= mb::sm_count() && a.bsk->p.N > 1024);
-  if (g_policy == 0 && ec) want_c = ec[0] == '1';
-  if ((g_policy == 0 || g_policy == 4) && !a.direct && want_c && mb::k1c_supported(a.bsk->p)) {
-    mb::launch_blind_rotate_k1c(a, st);
-    g_last_kernel = mb::k1c_variant_name(a.bsk->p);
-  } else if ((g_policy == 0 || g_policy == 3) && !a.direct && want_h && mb::k1h_supported(a.bsk->p)) {
-    mb::launch_blind_rotate_k1h(a, st);
-    g_last_kernel = mb::k1h_variant_name(a.bsk->p);
-  } else if (can_k1 || (g_policy == 2 && !a.direct && mb::k1_supported(a.bsk->p))) {
-    mb::launch_blind_rotate_k1(a, st);
-    g_last_kernel = mb::k1_variant_name(a.bsk->p);
-  } else {
-    mb::launch_blind_rotate_generic(a, st);
-    g_last_kernel = "generic";
+  // policy 0: fastest available for the batch size; 1: generic kernel; 2: T = M/8 kernel (k1); 3: T = M/4 latency kernel
+  // (k1h); 4: 2-CTA cluster kernel (k1c); 5: T = M/4 throughput kernel (k1q).
+  //   full batches   k1q where it has the shape (N = 1024 / 2048; four warps per scheduler), else k1
+  //   small batches  k1h (N <= 1024, batch <= 2 x SMs: half the serial work per thread, profiles/r1j_latency.log) or
+  //                  k1c (N > 1024, 2 x batch <= SMs: two SMs per bootstrap, profiles/r1o_latency.log)
+  const mb::Params &p = a.bsk->p;
+  const int sms = mb::sm_count();
+  enum { GENERIC, K1, K1H, K1C, K1Q } pick = GENERIC;
+  auto env_flag = [](const char *name, bool dflt) { const char *e = getenv(name); return e ? e[0] == '1' : dflt; };
+  if (!a.direct) {
+    if (g_policy == 0) {
+      const bool want_c = env_flag("MB200_K1C", 2 * a.count <= sms && p.N > 1024);
+      const bool want_h = env_flag("MB200_K1H", a.count <= 2 * sms && p.N <= 1024);
+      const bool want_q = env_flag("MB200_K1Q", MB200_K1Q_DEFAULT);
+      if (want_c && mb::k1c_supported(p)) pick = K1C;
+      else if (want_h && mb::k1h_supported(p)) pick = K1H;
+      else if (want_q && mb::k1q_supported(p)) pick = K1Q;
+      else if (mb::k1_supported(p)) pick = K1;
+    } else if (g_policy == 2 && mb::k1_supported(p)) pick = K1;
+    else if (g_policy == 3 && mb::k1h_supported(p)) pick = K1H;
+    else if (g_policy == 4 && mb::k1c_supported(p)) pick = K1C;
+    else if (g_policy == 5 && mb::k1q_supported(p)) pick = K1Q;
+  }
+  switch (pick) {
+    case K1C: mb::launch_blind_rotate_k1c(a, st); mb::k1c_variant_name(p, t_last_kernel, sizeof(t_last_kernel)); break;
+    case K1H: mb::launch_blind_rotate_k1h(a, st); mb::k1h_variant_name(p, t_last_kernel, sizeof(t_last_kernel)); break;
+    case K1Q: mb::launch_blind_rotate_k1q(a, st); mb::k1q_variant_name(p, t_last_kernel, sizeof(t_last_kernel)); break;
+    case K1: mb::launch_blind_rotate_k1(a, st); mb::k1_variant_name(p, t_last_kernel, sizeof(t_last_kernel)); break;
+    default: mb::launch_blind_rotate_generic(a, st); set_last_kernel("generic");
   }
 }
 
@@ -380,10 +388,10 @@ void run_direct(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   if (a.count <= 0) return;
   if (g_policy != 1 && mb::k1_direct_supported(a)) {
     mb::launch_extprod_k1(a, st);
-    g_last_kernel = "k1-direct";
+    set_last_kernel("k1-direct");
   } else {
     mb::launch_blind_rotate_generic(a, st);
-    g_last_kernel = "generic";
+    set_last_kernel("generic");
   }
 }
 
@@ -475,7 +483,7 @@ void blind_rotate_unfolded_core(UbskDev *U, u64 *d_acc, const u64 *d_a, int a_st
       run_direct(a, st);                                        // trgsw_mul_trlwe_DFT + trlwe_from_DFT (:142-143)
     }
   }
-  g_last_kernel = "unfolded";
+  set_last_kernel("unfolded");
 }
 
 // acc = tv * X^(2N - round((b + 1/(4*torus_base)) * 2N)) for every ciphertext: the generic kernel with zero steps
@@ -891,7 +899,7 @@ void mb200_ks_host(mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_in, int c
 
 uint64_t mb200_launch_count(void) { return mb::launches(); }
 void mb200_reset_launch_count(void) { mb::reset_launches(); }
-const char *mb200_last_blind_rotate_kernel(void) { return g_last_kernel.c_str(); }
+const char *mb200_last_blind_rotate_kernel(void) { return t_last_kernel; }
 void mb200_set_kernel_policy(int policy) { g_policy = policy; }
 
 // ---- batched handle API ------------------------------------------------------------------------------
@@ -1048,7 +1056,7 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
   a.sel_const = -1;
   a.dft_out = d_out; a.dft_perm = maps.stored_to_host; a.dft_conj = maps.stored_conj;
   mb::launch_blind_rotate_generic(a, st);
-  g_last_kernel = "generic";
+  set_last_kernel("generic");
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   for (int i = 0; i < count; ++i) {

@@ -65,7 +65,7 @@ const double2 *k1_tables_for(int N) {
 // ---- dispatch --------------------------------------------------------------------------------------
 // Variant = (levels per smem batch LB, min resident CTAs per SM MINB -> register cap, PKALL = all
 // levels' digits packed once per step, PF = pass-C key prefetch mode).  The default per (N, l) is the
-// fastest measured on B200 (profiles/); MB200_K1_LB / _MINB / _PF override it for experiments.
+// fastest measured on B200 (profiles/); MB200_K1_LB / _PF select another instantiated one.
 struct K1Variant { int lb, minb, pf; };
 
 // Levels per shared-memory batch: as many as fit (a) the 32-bit packed-digit word, lb*Bg_bit <= 32, and
@@ -87,7 +87,6 @@ static K1Variant default_variant(int logm, int l, int Bg_bit) {
 static K1Variant chosen_variant(int logm, int l, int Bg_bit) {
   K1Variant v = default_variant(logm, l, Bg_bit);
   if (const char *e = getenv("MB200_K1_LB")) v.lb = atoi(e);
-  if (const char *e = getenv("MB200_K1_MINB")) v.minb = atoi(e);
   if (const char *e = getenv("MB200_K1_PF")) v.pf = atoi(e);
   return v;
 }
@@ -96,43 +95,38 @@ bool k1_supported(const Params &p) {
   if (p.k != 1) return false;
   const int logm = ilog2i(p.N) - 1;
   if (!(logm >= 8 && logm <= 11 && p.l >= 1 && p.l <= 4 && (1 << (logm + 1)) == p.N)) return false;
-  return p.Bg_bit >= 1 && p.Bg_bit <= 32;
+  // Bg_bit = 32 takes the generic kernel: the 32-bit digit mask and the 2^52 + Bg/2 bias of the specialised kernels are
+  // formed in 32-bit arithmetic
+  return p.Bg_bit >= 1 && p.Bg_bit <= 31;
 }
 
-static char g_name[96];
-static int g_last_grp = 1;
-const char *k1_variant_name(const Params &p) {
+void k1_variant_name(const Params &p, char *dst, size_t cap) {
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
-  snprintf(g_name, sizeof(g_name), "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d,g=%d>", p.N, p.l, v.lb, v.minb,
-           (int)(p.l * p.Bg_bit <= 32), v.pf, g_last_grp);
-  return g_name;
+  snprintf(dst, cap, "k1<N=%d,l=%d,lb=%d,minb=%d,pkall=%d,pf=%d>", p.N, p.l, v.lb, v.minb, (int)(p.l * p.Bg_bit <= 32), v.pf);
 }
 
-template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF, int G>
-static bool launch_one(const K1Args &a, int count, cudaStream_t st) {
+template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
+static void launch_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
-  const size_t region = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
-  const size_t smem = region * G;
-  if (G > 1 && smem > 227 * 1024) return false;        // caller falls back to one ciphertext per CTA
+  const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
   static size_t configured = 0;
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1 kernel: %zu B of shared memory needed (blind rotation too long)", smem);
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF, G>,
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF, G><<<(count + G - 1) / G, G * (M / 8), smem, st>>>(a);
+  blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF><<<count, M / 8, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
-  return true;
 }
 
-template <int LOGM, int L, int LB, int MINB, int PF, int G>
-static bool launch_pk(const K1Args &a, int count, cudaStream_t st) {
+template <int LOGM, int L, int LB, int MINB, int PF>
+static void launch_pk(const K1Args &a, int count, cudaStream_t st) {
   // all l levels fit one 32-bit word per coefficient -> pack once per step; otherwise once per batch
-  if (L * a.Bg_bit <= 32) return launch_one<LOGM, L, LB, MINB, true, PF, G>(a, count, st);
-  return launch_one<LOGM, L, LB, MINB, false, PF, G>(a, count, st);
+  if (L * a.Bg_bit <= 32) launch_one<LOGM, L, LB, MINB, true, PF>(a, count, st);
+  else launch_one<LOGM, L, LB, MINB, false, PF>(a, count, st);
 }
 
 void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
@@ -147,19 +141,8 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   const int logm = ilog2i(p.N) - 1;
   const K1Variant v = chosen_variant(logm, p.l, p.Bg_bit);
   MB_REQUIRE(v.lb * p.Bg_bit <= 32, "k1 kernel: digits of one batch must fit 32 bits");
-  // ciphertexts per CTA in lockstep, sharing key rows through L1.  MEASURED SLOWER (profiles/r1h_k1_groups.log:
-  // 71 ms vs 51 ms at level 1, 233 vs 141 at level 2): independent CTAs drift into different phases and overlap
-  // the FP64-heavy and shared-memory-heavy passes of different ciphertexts; lockstep removes that.  Opt-in only.
-  int grp = 1;
-  if (const char *e = getenv("MB200_K1_G")) grp = atoi(e);
-#define MB_K1_GCASE(LM, LL, LBB, MB_, PF_, G_) \
-  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_ && grp == G_) { \
-    if (launch_pk<LM, LL, LBB, MB_, PF_, G_>(a, b.count, st)) { g_last_grp = G_; return; } grp = 1; }
-  MB_K1_GCASE(9, 3, 3, 1, 1, 3) MB_K1_GCASE(9, 3, 3, 1, 1, 2) MB_K1_GCASE(10, 4, 2, 1, 0, 2)
-#undef MB_K1_GCASE
-  g_last_grp = 1;
 #define MB_K1_CASE(LM, LL, LBB, MB_, PF_) \
-  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_, 1>(a, b.count, st); return; }
+  if (logm == LM && p.l == LL && v.lb == LBB && v.minb == MB_ && v.pf == PF_) { launch_pk<LM, LL, LBB, MB_, PF_>(a, b.count, st); return; }
   // N = 512, 1024: batch = all levels (double-buffered keys for l <= 3), or 2 / 1 levels when l*Bg_bit > 32
   MB_K1_CASE(8, 1, 1, 1, 1) MB_K1_CASE(8, 2, 2, 1, 1) MB_K1_CASE(8, 3, 3, 1, 1) MB_K1_CASE(8, 4, 4, 1, 0)
   MB_K1_CASE(8, 2, 1, 1, 0) MB_K1_CASE(8, 3, 2, 1, 0) MB_K1_CASE(8, 3, 1, 1, 0) MB_K1_CASE(8, 4, 2, 1, 0) MB_K1_CASE(8, 4, 1, 1, 0)
@@ -169,12 +152,6 @@ void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
   MB_K1_CASE(10, 1, 1, 1, 0) MB_K1_CASE(10, 2, 2, 1, 0) MB_K1_CASE(10, 3, 2, 1, 0) MB_K1_CASE(10, 4, 2, 1, 0)
   MB_K1_CASE(10, 2, 1, 1, 0) MB_K1_CASE(10, 3, 1, 1, 0) MB_K1_CASE(10, 4, 1, 1, 0)
   MB_K1_CASE(11, 1, 1, 1, 0) MB_K1_CASE(11, 2, 1, 1, 0) MB_K1_CASE(11, 3, 1, 1, 0) MB_K1_CASE(11, 4, 1, 1, 0)
-#ifdef MB200_K1_EXPERIMENTS
-  MB_K1_CASE(9, 3, 3, 1, 0) MB_K1_CASE(9, 3, 2, 4, 0) MB_K1_CASE(9, 3, 2, 4, 1) MB_K1_CASE(10, 4, 2, 1, 1) MB_K1_CASE(10, 3, 3, 1, 0)
-  MB_K1_CASE(9, 3, 2, 1, 2) MB_K1_CASE(9, 3, 3, 1, 2) MB_K1_CASE(10, 4, 2, 1, 2)
-  MB_K1_CASE(9, 3, 2, 1, 3) MB_K1_CASE(9, 3, 3, 1, 3) MB_K1_CASE(10, 4, 2, 1, 3)
-  MB_K1_CASE(9, 3, 1, 5, 0) MB_K1_CASE(9, 3, 1, 6, 0) MB_K1_CASE(9, 3, 1, 5, 3) MB_K1_CASE(9, 3, 1, 6, 3) MB_K1_CASE(9, 3, 1, 1, 3)
-#endif
 #undef MB_K1_CASE
   MB_FATAL("k1 kernel: no instantiation for N=%d l=%d lb=%d minb=%d pf=%d", p.N, p.l, v.lb, v.minb, v.pf);
 }

@@ -21,11 +21,11 @@ static void launch_direct_one(const K1Args &a, int count, cudaStream_t st) {
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + 16;
   static bool configured = false;
   if (!configured) {
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, 1, PKALL, 0, 1, true>,
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, 1, PKALL, 0, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  blind_rotate_k1_kernel<LOGM, L, LB, 1, PKALL, 0, 1, true><<<count, M / 8, smem, st>>>(a);
+  blind_rotate_k1_kernel<LOGM, L, LB, 1, PKALL, 0, true><<<count, M / 8, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }

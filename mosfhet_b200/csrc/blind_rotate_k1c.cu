@@ -301,11 +301,7 @@ bool k1c_supported(const Params &p) {
   return logm >= 9 && logm <= 10 && (p.l == 1 || 2 * p.Bg_bit <= 32);
 }
 
-static char g_k1c_name[64];
-const char *k1c_variant_name(const Params &p) {
-  snprintf(g_k1c_name, sizeof(g_k1c_name), "k1c<N=%d,l=%d,cluster=2>", p.N, p.l);
-  return g_k1c_name;
-}
+void k1c_variant_name(const Params &p, char *dst, size_t cap) { snprintf(dst, cap, "k1c<N=%d,l=%d,cluster=2>", p.N, p.l); }
 
 template <int LOGM, int L>
 static void launch_k1c_one(const K1Args &a, int count, cudaStream_t st) {

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
         const int r = hC * L + lev0 + lb;                               // TRGSW row (trgsw.c:394-419 order)
         const double2 *__restrict__ k0 = key + (size_t)(r * 2) * M + cC;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key_keep(k0 + i * C8); dst[8 + i] = ldg_key_keep(k0 + M + i * C8); }
+        for (int i = 0; i < 8; ++i) { dst[i] = ldg_key(k0 + i * C8); dst[8 + i] = ldg_key(k0 + M + i * C8); }
       };
       load_keys(kv[0], 0);
       // ------------------------------- pass B: RB*64 radix-R2 butterflies ------------------------
@@ -308,13 +308,11 @@ bool k1h_supported(const Params &p) {
   if (p.k != 1) return false;
   const int logm = ilog2i(p.N) - 1;
   if (!(logm >= 8 && logm <= 10 && (1 << (logm + 1)) == p.N && p.l >= 1 && p.l <= 4)) return false;
-  return p.Bg_bit >= 1 && p.Bg_bit <= 32;
+  return p.Bg_bit >= 1 && p.Bg_bit <= 31;   // see k1_supported
 }
 
-static char g_hname[80];
-const char *k1h_variant_name(const Params &p) {
-  snprintf(g_hname, sizeof(g_hname), "k1h<N=%d,l=%d,lb=%d,T=%d>", p.N, p.l, k1h_lb(ilog2i(p.N) - 1, p.l, p.Bg_bit), p.N / 8);
-  return g_hname;
+void k1h_variant_name(const Params &p, char *dst, size_t cap) {
+  snprintf(dst, cap, "k1h<N=%d,l=%d,lb=%d,T=%d>", p.N, p.l, k1h_lb(ilog2i(p.N) - 1, p.l, p.Bg_bit), p.N / 8);
 }
 
 void launch_blind_rotate_k1h(const BlindRotateLaunch &b, cudaStream_t st) {

@@ -1,0 +1,460 @@
+// blind_rotate_k1q.cu -- the k = 1 blind rotation at FOUR warps per scheduler: T = M/4 threads per ciphertext
+// (128 at N = 1024, 256 at N = 2048) with a quarter of the per-thread state of blind_rotate_k1.cu, so that 16 warps
+// are resident per SM at <= 128 registers instead of 8 warps at 254 (ncu on that kernel, profiles/r1u: 1.94 warps per
+// scheduler, issue slots 45 % busy, stall mix dominated by fixed-latency and shared-memory waits).
+//
+// Every N/2-point negacyclic transform is three register-resident passes, radix RA x 16 x 4 (RA = M/64), in the same
+// position order as the other k = 1 kernels (position s holds the value at root exponent 1 + 4*bitrev(s)), so the
+// resident key layout of keys.cu is shared:
+//
+//   pass A  thread (row slot, q), q < 64: coefficients q + 64 m (+M), m < RA, of one polynomial and one gadget level:
+//           (X^a - 1)*acc, digit -> f64, fold/twist, radix-RA DIF, twiddle w^q W_M^(q k1), -> smem block pos1
+//   pass B  task (row, pos1, r), r < 4: the 16 elements r + 4 m2 of block pos1: radix-16 DIF in place, NO twiddle
+//   pass C  thread c owns positions 4c..4c+3: twiddle W_64^(r k2) on load (3 thread-constant values), radix-4 DIF,
+//           Fourier-domain multiply-accumulate against both output polynomials' key rows from registers
+//   inverse C' -> B' -> A' mirrors it (DIT, conjugate twiddles); A' untwists, reduces mod 2^64 and accumulates.
+//
+// Shared-memory elements are 16-byte complex values at phys(i) = i ^ (bit6(i) << 2) ^ ((i >> 3) & 3): all three
+// access patterns are bank-conflict free (scripts/experiments/k1q_index_model.py checks this and the index algebra on
+// the CPU).  Thread constants that do not fit 128 registers live in tensor memory as in blind_rotate_k1.cu: the RA
+// pass-A twiddles, the 3 pass-C twiddles and (N = 1024) the accumulator words the thread owns.
+//
+// Reference functions fused: bootstrap.c:107-122, 192-206, polynomial.c:74-89, 220-235, 359-375 (+ src/fft),
+// trlwe.c:437, 491-505, 540-552, 629-634 -- see blind_rotate_k1.cu.
+#include <map>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "k1_common.cuh"
+
+namespace mb {
+
+// y = x * 2^-64 / M reduced mod 1, as a 64-bit torus word; round to nearest like fft_processor_spqlios.c:158-164.
+// s = t + 1.5*2^52 rounds t to an integer r = s - 1.5*2^52; (t - r) * 2^64 is formed exactly by two FMAs.
+__device__ __forceinline__ u64 f64_to_torus_scaled(double x, double scale /* 2^-64 / M */) {
+  const double C = 6755399441055744.0, P64 = 18446744073709551616.0;
+  const double t = x * scale;
+  const double s = t + C;
+  const double q = fma(s, -P64, C * P64);          // -(r * 2^64), exact (C * 2^64 is a power-of-two multiple of C)
+  const double y = fma(t, P64, q);                 // (t - r) * 2^64, exact
+  return (u64)__double2ll_rn(y);
+}
+
+// Kernel-uniform constants travel in the parameter block: FP64 and integer instructions take c[0][..] operands directly,
+// which keeps them out of the 128-register budget (at 128 registers every long-lived scalar counts).
+struct K1QArgs {
+  K1Args a;
+  u64 off;            // decomp_offset(Bg_bit, l)                                  (polynomial.c:80-83)
+  double dbias;       // 2^52 + Bg/2: digit u in [0, Bg) -> double(u - Bg/2) = hiloint2double(0x43300000, u) - dbias, exact
+  double out_scale;   // 2^-64 / M
+  unsigned dmask;     // Bg - 1
+};
+
+template <int LOGM, int L, int LB, bool PKALL>
+__global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blind_rotate_k1q_kernel(const __grid_constant__ K1QArgs Q) {
+  const K1Args &A = Q.a;
+  constexpr int M = 1 << LOGM, N = 2 * M, T = M / 4, RA = M / 64, LOGRA = LOGM - 6;
+  constexpr int SLOTS = T / 64;                       // pass-A rows in flight: 2 (N = 1024), 4 (N = 2048)
+  constexpr int LBO = SLOTS / 2;                      // gadget levels per pass-A round
+  constexpr int TPR = T / 4;                          // pass-B tasks per row = M/16
+  constexpr int ROWS = 2 * L;
+  constexpr int WQ = 2048 / N;                        // w^(64 m) = W_64^(WQ * m)
+  static_assert(LOGM == 9 || LOGM == 10, "k1q: N = 1024 or 2048");
+  static_assert(LB >= 1 && LB <= L && LB <= 2, "levels per batch");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64 *acc = reinterpret_cast<u64 *>(smem_raw);                       // [2][N]
+  double2 *buf = reinterpret_cast<double2 *>(acc + 2 * N);            // [2*LB][M]
+  unsigned short *rot = reinterpret_cast<unsigned short *>(buf + 2 * LB * M);
+  __shared__ unsigned tmem_base_s;
+
+  const int tid = threadIdx.x, ct = blockIdx.x;
+  const int log_N2 = LOGM + 2;
+  const u64 *in = A.in + (size_t)(ct / A.in_div) * A.in_stride;
+  const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
+  const int Bg_bit = A.Bg_bit;
+
+  // ---- thread roles ------------------------------------------------------------------------------------------
+  const int slot = tid >> 6, qA = tid & 63;           // pass A / A': row slot and in-block index
+  const int pA = slot & 1, lboA = slot >> 1;          // polynomial and level offset inside a round
+  const int rowB = tid / TPR, trB = tid - rowB * TPR; // pass B / B': row of the batch and task inside the row
+  const int pos1B = trB >> 2, rB = trB & 3;
+  const int cC = tid, pos2C = cC & 15;                // pass C / C'
+  // swizzled offsets (elements): see the header
+  const int qs0 = qA ^ ((qA >> 3) & 3), qs1 = qs0 ^ 4;                // pass A: block pos1 even / odd
+  const int b4B = (pos1B & 1) << 2;                                    // pass B: bit 2 flips in odd blocks
+  const int cbase = (4 * cC) ^ (((cC >> 4) & 1) << 2), cxor = (cC >> 1) & 3;
+
+  // ---- tensor memory: per-thread constants and state ------------------------------------------------------------
+  constexpr bool TMEM_ACC = (LOGM == 9);              // N = 2048: two warps share a lane quarter and pass-A threads are not the owners
+  constexpr int CPT = 128;                            // columns per thread
+  constexpr int TMEM_COLS = CPT * (T / 128);
+  // N = 1024: TA 0..31, TC 32..47, ACC 64..95, PK 96..111; N = 2048: TA 0..63, TC 64..79, PK 80..111
+  constexpr int COL_TA = 0, COL_TC = 4 * RA, COL_ACC = 64, COL_PK = (LOGM == 9) ? 96 : 80;
+  constexpr bool PK_PARK = PKALL && (L > LB);         // the packed digit words outlive the first batch: keep them out of passes B, C
+  static_assert(!TMEM_ACC || (COL_TC + 16 <= 64 && COL_ACC == 64), "tensor-memory column layout");
+  static_assert(COL_PK + 2 * RA <= CPT && COL_TC + 16 <= COL_PK, "tensor-memory column layout");
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n\t"
+                 "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+                 ::"r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // lane field (bits 31:16) = 32 * (warp % 4); warps 4..7 (N = 2048) use the second half of the columns
+  const unsigned taddr = tmem_base_s + ((unsigned)((tid >> 5) & 3) << 21) + (unsigned)((tid >> 7) * CPT);
+  {
+    // pass-A twiddles w^q * W_M^(q k1), k1 = brev(pos1): A.tab[k1 * 64 + q]
+#pragma unroll
+    for (int g4 = 0; g4 < RA / 4; ++g4) {
+      double2 tw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tw[i] = __ldg(&A.tab[brev(4 * g4 + i, LOGRA) * 64 + qA]);
+      tmem_st4(taddr + COL_TA + 16 * g4, tw);
+    }
+    // pass-C twiddles W_64^(r k2), r = 1..3, k2 = brev(pos2): A.tab[RA * 64 + k2 * 4 + r]
+    double2 tw[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tw[r] = __ldg(&A.tab[RA * 64 + brev(pos2C, 4) * 4 + r]);
+    tmem_st4(taddr + COL_TC, tw);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+
+  // ---- initial accumulator: tv * X^(2N - round((b + 1/(4*torus_base)) * 2N))  (bootstrap.c:194-195) ----------------
+  int rot0 = 0;
+  if (A.init_rotate) {
+    u64 b = in[A.size];
+    if (A.preprocess) b = pb_preprocess(b, A.kappa, A.theta, log_N2);
+    rot0 = (2 * N - (int)torus2int(b + A.prec_offset, log_N2)) & (2 * N - 1);
+  }
+  for (int c = tid; c < 2 * N; c += T) {
+    const int p = c / N, i = c - p * N;
+    acc[c] = rot0 ? rotated_coeff(tv + (size_t)p * N, i, rot0, N) : tv[c];
+  }
+  for (int i = tid; i < A.size; i += T) {             // all rotation amounts up front (bootstrap.c:113)
+    u64 av = in[i];
+    if (A.preprocess) av = pb_preprocess(av, A.kappa, A.theta, log_N2);
+    rot[i] = (unsigned short)(torus2int(av, log_N2) & (2 * N - 1));
+  }
+  __syncthreads();
+  if (TMEM_ACC) {                                     // park the accumulator words this thread owns: (j, j + M), j = q + 64 m
+    const u64 *ap0 = acc + pA * N;
+#pragma unroll
+    for (int g4 = 0; g4 < RA / 4; ++g4) {
+      u64 v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = ap0[qA + (4 * g4 + i) * 64]; v[2 * i + 1] = ap0[qA + (4 * g4 + i) * 64 + M]; }
+      tmem_st_u64x8(taddr + COL_ACC + 16 * g4, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+
+
+  for (int step = 0; step < A.size; ++step) {
+    const int a_i = rot[step];
+    if (a_i == 0) continue;                           // bootstrap.c:114
+    const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M;
+
+    double2 fa[2][4];                                 // Fourier accumulators: positions 4c..4c+3 of both outputs
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fa[o][i] = make_double2(0.0, 0.0);
+
+    // coefficient pair m of (X^a - 1)*acc + rounding offset (polynomial.c:74-89, 220-235): j = q + 64 m and j + M
+    const u64 *ap = acc + pA * N;
+    const int base = (qA - a_i) & (2 * N - 1);        // index of coefficient qA in acc * X^a (sign in bit log2 N)
+    u64 own[8];
+    auto coef_pair = [&](int m, u64 &v0, u64 &v1) {
+      const int j = qA + m * 64;
+      const int s0 = (base + m * 64) & (2 * N - 1), s1 = (s0 + M) & (2 * N - 1);
+      const u64 r0 = ap[s0 & (N - 1)], r1 = ap[s1 & (N - 1)];
+      if (TMEM_ACC && (m & 3) == 0) tmem_ld_u64x8(own, taddr + COL_ACC + 4 * m);
+      const u64 t0 = Q.off - (TMEM_ACC ? own[2 * (m & 3)] : ap[j]), t1 = Q.off - (TMEM_ACC ? own[2 * (m & 3) + 1] : ap[j + M]);
+      v0 = (s0 & N) ? t0 - r0 : t0 + r0;
+      v1 = (s1 & N) ? t1 - r1 : t1 + r1;
+    };
+    // FUSED: a thread transforms ONE level per batch (N = 2048: the four row slots are 2 polynomials x 2 levels), so the
+    // digit is taken straight from the coefficient; otherwise the top lev_end*Bg_bit bits of every coefficient are packed
+    // into one 32-bit word and serve the levels of the batch (PKALL: of the whole step)
+    constexpr bool FUSED = !PKALL && (LBO >= LB);
+    unsigned pk0[FUSED ? 1 : RA], pk1[FUSED ? 1 : RA];
+    auto pack_digits = [&](int lev_end) {
+      const int pk_shift = 64 - lev_end * Bg_bit;
+#pragma unroll
+      for (int m = 0; m < RA; ++m) {
+        u64 v0, v1;
+        coef_pair(m, v0, v1);
+        pk0[FUSED ? 0 : m] = (unsigned)(v0 >> pk_shift);
+        pk1[FUSED ? 0 : m] = (unsigned)(v1 >> pk_shift);
+      }
+    };
+    if (PKALL) {
+      pack_digits(L);
+      if (PK_PARK) {
+#pragma unroll
+        for (int h = 0; h < RA / 8; ++h) {
+          unsigned w[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { w[2 * i] = pk0[8 * h + i]; w[2 * i + 1] = pk1[8 * h + i]; }
+          tmem_st_u32x16(taddr + COL_PK + 16 * h, w);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+    }
+
+    auto batch = [&](auto nb_tag, const int lev0) {
+      constexpr int NB = decltype(nb_tag)::value, RB = 2 * NB;
+      // ------------------------------- pass A -----------------------------------------------------------------
+      if (!PKALL && !FUSED) pack_digits(lev0 + NB);
+      if (PK_PARK && lev0 > 0) {
+#pragma unroll
+        for (int h = 0; h < RA / 8; ++h) {
+          unsigned w[16];
+          tmem_ld_u32x16(w, taddr + COL_PK + 16 * h);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { pk0[8 * h + i] = w[2 * i]; pk1[8 * h + i] = w[2 * i + 1]; }
+        }
+      }
+      constexpr int ROUNDS = (NB + LBO - 1) / LBO;
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int lb = rd * LBO + lboA;
+        if (LBO > 1 && lb >= NB) continue;           // warp-uniform (slot is a multiple of two warps)
+        const int sh = FUSED ? 64 - (lev0 + lb + 1) * Bg_bit : ((PKALL ? (L - 1 - lev0) : (NB - 1)) - lb) * Bg_bit;
+        double2 x[RA];
+#pragma unroll
+        for (int m = 0; m < RA; ++m) {
+          unsigned u0, u1;
+          if (FUSED) {
+            u64 v0, v1;
+            coef_pair(m, v0, v1);
+            u0 = (unsigned)(v0 >> sh) & Q.dmask; u1 = (unsigned)(v1 >> sh) & Q.dmask;
+          } else {
+            u0 = (pk0[m] >> sh) & Q.dmask; u1 = (pk1[m] >> sh) & Q.dmask;
+          }
+          const double d0 = __hiloint2double(0x43300000, (int)u0) - Q.dbias;
+          const double d1 = __hiloint2double(0x43300000, (int)u1) - Q.dbias;
+          x[m] = mul_w64(make_double2(d0, d1), WQ * m, false);         // fold z = d0 + i d1, constant part of the twist
+        }
+        reg_dif<RA>(x);
+        double2 *row = buf + (pA * NB + lb) * M;
+#pragma unroll
+        for (int g4 = 0; g4 < RA / 4; ++g4) {
+          double2 tw[4];
+          tmem_ld4(tw, taddr + COL_TA + 16 * g4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pos = 4 * g4 + i;
+            row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tw[i]);
+          }
+        }
+      }
+      __syncthreads();
+      // ------------------------------- pass B: radix 16 in place, no twiddle --------------------------------------
+      if (rowB < RB) {                                // warp-uniform: a row is TPR = 32 / 64 tasks
+        double2 *blk = buf + rowB * M + pos1B * 64;
+        double2 x[16];
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[((4 * m2) ^ b4B) + (rB ^ ((m2 >> 1) & 3))];
+        reg_dif<16>(x);
+#pragma unroll
+        for (int pos = 0; pos < 16; ++pos) blk[((4 * pos) ^ b4B) + (rB ^ ((pos >> 1) & 3))] = x[pos];
+      }
+      __syncthreads();
+      // ------------------------------- pass C + MAC ----------------------------------------------------------------
+      {
+        double2 twc[4];
+        tmem_ld4(twc, taddr + COL_TC);
+        // key position 4c + pos3 = 8c' + m' is stored at m' * (M/8) + c'
+        const double2 *__restrict__ kbase = key + (4 * (cC & 1)) * (M / 8) + (cC >> 1);
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          const int p = rb / NB, lev = lev0 + (rb - p * NB);
+          const double2 *__restrict__ k0 = kbase + (size_t)((p * L + lev) * 2) * M;   // TRGSW row order of trgsw.c:394-419
+          double2 kv[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { kv[i] = ldg_key(k0 + i * (M / 8)); kv[4 + i] = ldg_key(k0 + M + i * (M / 8)); }
+          const double2 *row = buf + rb * M + cbase;
+          double2 x[4];
+          x[0] = row[0 ^ cxor];
+#pragma unroll
+          for (int r = 1; r < 4; ++r) x[r] = cmul(row[r ^ cxor], twc[r]);
+          reg_dif<4>(x);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cfma(fa[0][i], x[i], kv[i]); cfma(fa[1][i], x[i], kv[4 + i]); }
+        }
+      }
+      __syncthreads();
+    };
+#pragma unroll
+    for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
+    if constexpr (L % LB != 0) batch(std::integral_constant<int, L % LB>{}, L - L % LB);
+
+    // ---------------------------------- inverse: C' ----------------------------------------------------------------
+    {
+      double2 twc[4];
+      tmem_ld4(twc, taddr + COL_TC);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        reg_dit_inv<4>(fa[o]);
+        double2 *row = buf + o * M + cbase;
+        row[0 ^ cxor] = fa[o][0];
+#pragma unroll
+        for (int r = 1; r < 4; ++r) row[r ^ cxor] = cmul_conj(fa[o][r], twc[r]);
+      }
+    }
+    __syncthreads();
+    // ---------------------------------- B' ---------------------------------------------------------------------------
+    if (rowB < 2) {
+      double2 *blk = buf + rowB * M + pos1B * 64;
+      double2 x[16];
+#pragma unroll
+      for (int pos = 0; pos < 16; ++pos) x[pos] = blk[((4 * pos) ^ b4B) + (rB ^ ((pos >> 1) & 3))];
+      reg_dit_inv<16>(x);
+#pragma unroll
+      for (int m2 = 0; m2 < 16; ++m2) blk[((4 * m2) ^ b4B) + (rB ^ ((m2 >> 1) & 3))] = x[m2];
+    }
+    __syncthreads();
+    // ---------------------------------- A' + accumulate ----------------------------------------------------------------
+    if (SLOTS == 2 || slot < 2) {
+      const double2 *row = buf + pA * M;
+      double2 x[RA];
+#pragma unroll
+      for (int g4 = 0; g4 < RA / 4; ++g4) {
+        double2 tw[4];
+        tmem_ld4(tw, taddr + COL_TA + 16 * g4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pos = 4 * g4 + i;
+          x[pos] = cmul_conj(row[pos * 64 + ((pos & 1) ? qs1 : qs0)], tw[i]);
+        }
+      }
+      reg_dit_inv<RA>(x);
+      u64 *ap = acc + pA * N;
+      u64 ownA[8];
+#pragma unroll
+      for (int m = 0; m < RA; ++m) {
+        const double2 z = mul_w64(x[m], WQ * m, true);
+        const int j = qA + m * 64;
+        const u64 d0 = f64_to_torus_scaled(z.x, Q.out_scale), d1 = f64_to_torus_scaled(z.y, Q.out_scale);
+        if (TMEM_ACC) {
+          if ((m & 3) == 0) tmem_ld_u64x8(ownA, taddr + COL_ACC + 4 * m);
+          const u64 n0 = ownA[2 * (m & 3)] + d0, n1 = ownA[2 * (m & 3) + 1] + d1;
+          ownA[2 * (m & 3)] = n0; ownA[2 * (m & 3) + 1] = n1;
+          ap[j] = n0;                                 // shared copy: read (rotated) by other threads in the next step
+          ap[j + M] = n1;
+          if ((m & 3) == 3) tmem_st_u64x8(taddr + COL_ACC + 4 * (m - 3), ownA);
+        } else {
+          ap[j] += d0;                                // trlwe_from_DFT + trlwe_addto
+          ap[j + M] += d1;
+        }
+      }
+      if (TMEM_ACC) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+  }
+
+  // every thread is past its last tensor-memory access before the columns are released (also when no step ran)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(TMEM_COLS) : "memory");
+  // ---- epilogue: sample extraction at index 0 (trlwe.c:540-552) or the raw accumulator -----------------------------
+  if (A.extract) {
+    u64 *o = A.out + (size_t)ct * (N + 1);
+    for (int c = tid; c < N; c += T) o[c] = (c == 0) ? acc[0] : (0ull - acc[N - c]);
+    if (tid == 0) o[N] = acc[N];
+  } else {
+    u64 *o = A.out + (size_t)ct * 2 * N;
+    for (int c = tid; c < 2 * N; c += T) o[c] = acc[c];
+  }
+}
+
+// ---- tables: TA[RA][64] then TC[16][4] -----------------------------------------------------------------------------
+static std::mutex g_k1q_mu;
+static std::map<int, double2 *> g_k1q_tab;
+
+static const double2 *k1q_tables_for(int N) {
+  ensure_init();
+  std::lock_guard<std::mutex> lk(g_k1q_mu);
+  auto it = g_k1q_tab.find(N);
+  if (it != g_k1q_tab.end()) return it->second;
+  const int M = N / 2, RA = M / 64;
+  std::vector<double2> h((size_t)RA * 64 + 64);
+  for (int k1 = 0; k1 < RA; ++k1)
+    for (int q = 0; q < 64; ++q) {
+      // w^q * W_M^(q*k1) = exp(i*pi*q*(4*k1+1)/N)
+      const long double ang = M_PIl * (long double)((long long)q * (4 * k1 + 1)) / (long double)N;
+      h[(size_t)k1 * 64 + q] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+  for (int k2 = 0; k2 < 16; ++k2)
+    for (int r = 0; r < 4; ++r) {
+      const long double ang = 2.0L * M_PIl * (long double)(r * k2) / 64.0L;   // W_64^(r k2)
+      h[(size_t)RA * 64 + k2 * 4 + r] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+  double2 *d = nullptr;
+  MB_CHECK(cudaMalloc(&d, sizeof(double2) * h.size()));
+  MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+  MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
+  g_k1q_tab[N] = d;
+  return d;
+}
+
+template <int LOGM, int L, int LB, bool PKALL>
+static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
+  constexpr int M = 1 << LOGM;
+  const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.a.size * 2 + 15) & ~(size_t)15);
+  static size_t configured = 0;
+  if (smem > configured) {
+    MB_REQUIRE(smem <= 227 * 1024, "k1q kernel: %zu B of shared memory needed (blind rotation too long)", smem);
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  blind_rotate_k1q_kernel<LOGM, L, LB, PKALL><<<count, M / 4, smem, st>>>(a);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+// levels per shared-memory batch: 2 when two levels' digits fit the 32-bit packed word, else 1
+static int k1q_lb(int l, int Bg_bit) { return (l >= 2 && 2 * Bg_bit <= 32) ? 2 : 1; }
+
+bool k1q_supported(const Params &p) {
+  if (p.k != 1 || !(p.N == 1024 || p.N == 2048)) return false;
+  return p.l >= 1 && p.l <= 4 && p.Bg_bit >= 1 && p.Bg_bit <= 31;
+}
+
+void k1q_variant_name(const Params &p, char *dst, size_t cap) {
+  snprintf(dst, cap, "k1q<N=%d,l=%d,lb=%d,T=%d>", p.N, p.l, k1q_lb(p.l, p.Bg_bit), p.N / 8);
+}
+
+void launch_blind_rotate_k1q(const BlindRotateLaunch &b, cudaStream_t st) {
+  const Params &p = b.bsk->p;
+  MB_REQUIRE(k1q_supported(p) && !b.direct, "k1q kernel: unsupported parameters");
+  upload_w64();
+  K1QArgs qa;
+  K1Args &a = qa.a;
+  qa.off = 1ull << (64 - p.l * p.Bg_bit - 1);
+  for (int i = 0; i < p.l; ++i) qa.off += 1ull << (64 - i * p.Bg_bit - 1);
+  qa.dbias = 4503599627370496.0 + (double)(1ull << (p.Bg_bit - 1));
+  qa.out_scale = 5.42101086242752217e-20 / (double)(p.N / 2);
+  qa.dmask = (unsigned)((1ull << p.Bg_bit) - 1ull);
+  a.bsk = b.bsk->d; a.tab = k1q_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
+  a.in_stride = b.in_stride; a.in_div = b.in_div > 0 ? b.in_div : 1; a.size = b.size; a.out = b.out; a.extract = b.extract;
+  a.init_rotate = b.init_rotate; a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta;
+  a.Bg_bit = p.Bg_bit; a.count = b.count;
+  const int logm = ilog2i(p.N) - 1, lb = k1q_lb(p.l, p.Bg_bit);
+  const bool pkall = p.l * p.Bg_bit <= 32;
+#define MB_K1Q_CASE(LM, LL, LBB) \
+  if (logm == LM && p.l == LL && lb == LBB) { \
+    if (pkall) launch_q<LM, LL, LBB, true>(qa, b.count, st); else launch_q<LM, LL, LBB, false>(qa, b.count, st); \
+    return; }
+  MB_K1Q_CASE(9, 1, 1) MB_K1Q_CASE(9, 2, 2) MB_K1Q_CASE(9, 2, 1) MB_K1Q_CASE(9, 3, 2) MB_K1Q_CASE(9, 3, 1) MB_K1Q_CASE(9, 4, 2) MB_K1Q_CASE(9, 4, 1)
+  MB_K1Q_CASE(10, 1, 1) MB_K1Q_CASE(10, 2, 2) MB_K1Q_CASE(10, 2, 1) MB_K1Q_CASE(10, 3, 2) MB_K1Q_CASE(10, 3, 1) MB_K1Q_CASE(10, 4, 2) MB_K1Q_CASE(10, 4, 1)
+#undef MB_K1Q_CASE
+  MB_FATAL("k1q kernel: no instantiation for N=%d l=%d lb=%d", p.N, p.l, lb);
+}
+
+}  // namespace mb

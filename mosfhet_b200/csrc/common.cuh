@@ -112,13 +112,16 @@ bool k1_supported(const Params &p);
 bool k1_direct_supported(const BlindRotateLaunch &a);     // one external product / CMUX on the k = 1 kernel
 void launch_extprod_k1(const BlindRotateLaunch &a, cudaStream_t st);
 void launch_blind_rotate_k1(const BlindRotateLaunch &a, cudaStream_t st);
-const char *k1_variant_name(const Params &p);
+void k1_variant_name(const Params &p, char *dst, size_t cap);   // variant names are written into the caller's buffer
 bool k1h_supported(const Params &p);
 bool k1c_supported(const Params &p);                      // one ciphertext per 2-CTA cluster (latency)
 void launch_blind_rotate_k1c(const BlindRotateLaunch &a, cudaStream_t st);
-const char *k1c_variant_name(const Params &p);
+void k1c_variant_name(const Params &p, char *dst, size_t cap);
 void launch_blind_rotate_k1h(const BlindRotateLaunch &a, cudaStream_t st);
-const char *k1h_variant_name(const Params &p);
+void k1h_variant_name(const Params &p, char *dst, size_t cap);
+bool k1q_supported(const Params &p);                      // T = M/4 threads, radix RA x 16 x 4, four warps per scheduler
+void launch_blind_rotate_k1q(const BlindRotateLaunch &a, cudaStream_t st);
+void k1q_variant_name(const Params &p, char *dst, size_t cap);
 
 void launch_keyswitch(const KskDev *ksk, u64 *out, const u64 *in, int count, cudaStream_t st);
 void launch_table_keyswitch(const u64 *table, int row_stride, int n_entries, int t, int base_bit, u64 *out,

@@ -18,22 +18,28 @@ static void upload_w64() {
   done = true;
 }
 
-// x * W_64^idx (or its conjugate).  idx is a compile-time constant after unrolling, so the trivial
-// cases cost nothing and the 8th roots cost 2 mul + 2 add.
+// x * W_64^idx (or its conjugate).  idx is a compile-time constant after unrolling, so the trivial cases cost nothing
+// and the 8th roots cost 2 mul + 2 add.  Every other power is folded onto the first octant, W = i^qd * (c + i s) with
+// (c, s) or (s, c) taken from entries 1..7 of the tables: 14 distinct constants in all, which the compiler keeps in
+// uniform registers (with one entry per power the N = 2048 kernels need 72 of the 63 uniform registers and spill them
+// through local memory).  The tables hold correctly rounded values, so cos(t) read as sin(pi/2 - t) is the same double
+// and the folded product rounds exactly like the direct one.
 __device__ __forceinline__ double2 mul_w64(double2 x, int idx, bool conj) {
   idx &= 63;
   if (conj) idx = (64 - idx) & 63;
   const double h = 0.70710678118654752440;
-  if (idx == 0) return x;
-  if (idx == 16) return make_double2(-x.y, x.x);
-  if (idx == 32) return make_double2(-x.x, -x.y);
-  if (idx == 48) return make_double2(x.y, -x.x);
-  if (idx == 8) return make_double2((x.x - x.y) * h, (x.x + x.y) * h);
-  if (idx == 24) return make_double2((-x.x - x.y) * h, (x.x - x.y) * h);
-  if (idx == 40) return make_double2((x.y - x.x) * h, (-x.x - x.y) * h);
-  if (idx == 56) return make_double2((x.x + x.y) * h, (x.y - x.x) * h);
-  const double c = CW64C[idx], s = CW64S[idx];
-  return make_double2(fma(x.x, c, -x.y * s), fma(x.x, s, x.y * c));
+  const int qd = idx >> 4, rem = idx & 15;
+  double2 y;                                           // x * e^(2 pi i rem / 64)
+  if (rem == 0) y = x;
+  else if (rem == 8) y = make_double2((x.x - x.y) * h, (x.x + x.y) * h);
+  else {
+    const double c = rem < 8 ? CW64C[rem] : CW64S[16 - rem], s = rem < 8 ? CW64S[rem] : CW64C[16 - rem];
+    y = make_double2(fma(x.x, c, -x.y * s), fma(x.x, s, x.y * c));
+  }
+  if (qd == 0) return y;                               // times i^qd
+  if (qd == 1) return make_double2(-y.y, y.x);
+  if (qd == 2) return make_double2(-y.x, -y.y);
+  return make_double2(y.y, -y.x);
 }
 
 __host__ __device__ constexpr int brev(int x, int bits) {
@@ -109,7 +115,7 @@ __device__ __forceinline__ u64 f64_to_torus_fast(double x) {
   return (u64)__double2ll_rn(y);
 }
 
-// ---- tensor memory as a per-thread constant store (disable with MB200_NO_TMEM_TW) -----------------------------------------------
+// ---- tensor memory as a per-thread constant store -----------------------------------------------
 // The 16 pass-A / A' twiddles of a thread are thread constants that do not fit the register budget, so they were
 // re-read from global memory (through the L1 data pipe, the busiest unit of this kernel) three times per step.
 // Blackwell's tensor memory is private per lane and has its own datapath: each thread parks its 64 words there once
@@ -216,7 +222,6 @@ __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
 // bootstrap then re-reads the whole key from HBM every time once something else has displaced it (2.6 -> 3.4 ms,
 // scripts/latency_after_load.py), and the full batch is 2.3 % slower (profiles/r1p_k1_tmem.log).
 __device__ __forceinline__ double2 ldg_key(const double2 *p) { return __ldg(p); }
-__device__ __forceinline__ double2 ldg_key_keep(const double2 *p) { return __ldg(p); }
 
 
 }  // namespace mb

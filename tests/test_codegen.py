@@ -27,9 +27,9 @@ def _usage(obj):
 
 def test_default_bootstrap_kernels_do_not_spill():
     res = _usage(os.path.join(BUILD, "blind_rotate_k1.o"))
-    # <LOGM, L, LB, MINB, PKALL, PF, G, DIRECT>: Level 1 (N=1024, l=3, batches of 2+1 levels) and Level 2 (N=2048, l=4)
-    level1 = [v for k, v in res.items() if "Li9ELi3ELi2ELi1ELb1ELi0ELi1ELb0E" in k]
-    level2 = [v for k, v in res.items() if "Li10ELi4ELi2ELi1ELb0ELi0ELi1ELb0E" in k]
+    # <LOGM, L, LB, MINB, PKALL, PF, DIRECT>: Level 1 (N=1024, l=3, batches of 2+1 levels) and Level 2 (N=2048, l=4)
+    level1 = [v for k, v in res.items() if "Li9ELi3ELi2ELi1ELb1ELi0ELb0E" in k]
+    level2 = [v for k, v in res.items() if "Li10ELi4ELi2ELi1ELb0ELi0ELb0E" in k]
     assert level1 and level2, "default instantiations missing from blind_rotate_k1.o"
     assert level1[0][1] == 0, f"Level-1 kernel spills: REG/STACK = {level1[0]}"
     assert level2[0][1] <= 16, f"Level-2 kernel spills more than its 16-byte baseline: REG/STACK = {level2[0]}"
@@ -40,3 +40,15 @@ def test_keyswitch_kernel_register_budget():
     ks = [v for k, v in res.items() if "keyswitch_warp_kernelILi10ELb0E" in k]
     assert ks, "TLWE key-switch instantiation (640-word rows) missing"
     assert ks[0][0] <= 72, f"28 warps per SM need <= 72 registers, got {ks[0]}"
+
+
+def test_k1q_kernels_fit_four_warps_per_scheduler():
+    """The T = M/4 kernels exist to run 16 warps per SM: 128 registers at most, and only a few spilled words."""
+    res = _usage(os.path.join(BUILD, "blind_rotate_k1q.o"))
+    # <LOGM, L, LB, PKALL>
+    level1 = [v for k, v in res.items() if "k1q_kernelILi9ELi3ELi2ELb1E" in k]
+    level2 = [v for k, v in res.items() if "k1q_kernelILi10ELi4ELi2ELb0E" in k]
+    assert level1 and level2, "benchmark instantiations missing from blind_rotate_k1q.o"
+    for name, (reg, stack) in (("level 1", level1[0]), ("level 2", level2[0])):
+        assert reg <= 128, f"{name}: {reg} registers"
+    assert level1[0][1] <= 64, f"Level-1 k1q kernel spills: REG/STACK = {level1[0]}"

@@ -433,7 +433,7 @@ def test_k1_instantiations_vs_generic(N, l, Bg_bit):
     lut = syn.splitmix64_stream(N + 17, 4)
     tv = syn.test_vector(lut, P.N, 1)
     outs = {}
-    for name, policy in (("generic", 1), ("k1", 2), ("k1h", 3), ("k1c", 4)):
+    for name, policy in (("generic", 1), ("k1", 2), ("k1h", 3), ("k1c", 4), ("k1q", 5)):
         api.set_kernel_policy(policy)
         outs[name] = api.pbs_host(bsk, tv, cts, 4).copy()
         outs[name + "_kernel"] = api.last_blind_rotate_kernel()
@@ -442,9 +442,11 @@ def test_k1_instantiations_vs_generic(N, l, Bg_bit):
     assert outs["k1_kernel"].startswith("k1<"), outs["k1_kernel"]
     if N in (1024, 2048) and (l == 1 or 2 * Bg_bit <= 32):
         assert outs["k1c_kernel"].startswith("k1c<"), outs["k1c_kernel"]      # the 2-CTA cluster kernel
+    if N in (1024, 2048):
+        assert outs["k1q_kernel"].startswith("k1q<"), outs["k1q_kernel"]      # the T = M/4 throughput kernel
     tol = phase_tol(l, Bg_bit)
     ph_g = syn.tlwe_phase(outs["generic"], rlwe_key)
-    for name in ("k1", "k1h", "k1c"):
+    for name in ("k1", "k1h", "k1c", "k1q"):
         ph = syn.tlwe_phase(outs[name], rlwe_key)
         assert syn.torus_distance(ph, ph_g).max() <= tol, (name, outs[name + "_kernel"])
     # the oracle on the first ciphertext (keys read back from the resident layout)
