@@ -14,7 +14,7 @@
 //           Fourier-domain multiply-accumulate against both output polynomials' key rows from registers
 //   inverse C' -> B' -> A' mirrors it (DIT, conjugate twiddles); A' untwists, reduces mod 2^64 and accumulates.
 //
-// Shared-memory elements are 16-byte complex values at phys(i) = i ^ (bit6(i) << 2) ^ ((i >> 3) & 3): all three
+// Shared-memory elements are 16-byte complex values at phys(i) = i ^ ((i >> 3) & 7) ^ (bit6(i) << 2): all three
 // access patterns are bank-conflict free (scripts/experiments/k1q_index_model.py checks this and the index algebra on
 // the CPU).  Thread constants that do not fit 128 registers live in tensor memory as in blind_rotate_k1.cu: the RA
 // pass-A twiddles, the 3 pass-C twiddles and (N = 1024) the accumulator words the thread owns.
@@ -51,13 +51,12 @@ struct K1QArgs {
   unsigned dmask;     // Bg - 1
 };
 
-template <int LOGM, int L, int LB, bool PKALL>
+template <int LOGM, int L, int LB, bool PKALL, bool KPF>
 __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blind_rotate_k1q_kernel(const __grid_constant__ K1QArgs Q) {
   const K1Args &A = Q.a;
   constexpr int M = 1 << LOGM, N = 2 * M, T = M / 4, RA = M / 64, LOGRA = LOGM - 6;
   constexpr int SLOTS = T / 64;                       // pass-A rows in flight: 2 (N = 1024), 4 (N = 2048)
   constexpr int LBO = SLOTS / 2;                      // gadget levels per pass-A round
-  constexpr int TPR = T / 4;                          // pass-B tasks per row = M/16
   constexpr int ROWS = 2 * L;
   constexpr int WQ = 2048 / N;                        // w^(64 m) = W_64^(WQ * m)
   static_assert(LOGM == 9 || LOGM == 10, "k1q: N = 1024 or 2048");
@@ -78,21 +77,36 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   // ---- thread roles ------------------------------------------------------------------------------------------
   const int slot = tid >> 6, qA = tid & 63;           // pass A / A': row slot and in-block index
   const int pA = slot & 1, lboA = slot >> 1;          // polynomial and level offset inside a round
-  const int rowB = tid / TPR, trB = tid - rowB * TPR; // pass B / B': row of the batch and task inside the row
-  const int pos1B = trB >> 2, rB = trB & 3;
-  const int cC = tid, pos2C = cC & 15;                // pass C / C'
+  // pass B / B' run PER WARP on the two blocks pos1 = 2*warp + {0, 1} whose positions the same warp's pass C / C' threads
+  // own, so that B -> C and C' -> B' need a warp barrier only: lane = (row of the batch, block bit, r)
+  const int warp = tid >> 5, lane = tid & 31;
+  const int rowB = lane >> 3, pos1B = 2 * warp + ((lane >> 2) & 1), rB = lane & 3;
+  // pass C / C': lanes 0..15 take the key columns c' = 16*warp + lane of the even position groups, lanes 16..31 of the odd
+  // ones: the 8 lanes of a quarter warp read 8 consecutive 16-byte key words, one 128-byte line per request (with c = tid
+  // a request straddles two lines and the key loads cost twice the L1 wavefronts: profiles/r2a)
+  const int cpC = 16 * warp + (lane & 15), halfC = lane >> 4;
+  const int cC = 2 * cpC + halfC, pos2C = cC & 15;
   // swizzled offsets (elements): see the header
-  const int qs0 = qA ^ ((qA >> 3) & 3), qs1 = qs0 ^ 4;                // pass A: block pos1 even / odd
+  const int qs0 = qA ^ ((qA >> 3) & 7), qs1 = qs0 ^ 4;                // pass A: block pos1 even / odd
   const int b4B = (pos1B & 1) << 2;                                    // pass B: bit 2 flips in odd blocks
-  const int cbase = (4 * cC) ^ (((cC >> 4) & 1) << 2), cxor = (cC >> 1) & 3;
+  const int cbase = 8 * cpC, cxor = (4 * halfC) ^ (cpC & 7) ^ (((cpC >> 3) & 1) << 2);   // pass C: element r at cbase + (r ^ cxor)
+
+  // element 4*e + rB of a block (e < 16), swizzled: bits 0-1 ^= (e >> 1) & 3, bit 2 ^= bit 2 of (e >> 1) and the block bit
+  auto swz_b = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4B) + (rB ^ ((e >> 1) & 3)); };
 
   // ---- tensor memory: per-thread constants and state ------------------------------------------------------------
   constexpr bool TMEM_ACC = (LOGM == 9);              // N = 2048: two warps share a lane quarter and pass-A threads are not the owners
   constexpr int CPT = 128;                            // columns per thread
   constexpr int TMEM_COLS = CPT * (T / 128);
-  // N = 1024: TA 0..31, TC 32..47, ACC 64..95, PK 96..111; N = 2048: TA 0..63, TC 64..79, PK 80..111
-  constexpr int COL_TA = 0, COL_TC = 4 * RA, COL_ACC = 64, COL_PK = (LOGM == 9) ? 96 : 80;
-  constexpr bool PK_PARK = PKALL && (L > LB);         // the packed digit words outlive the first batch: keep them out of passes B, C
+  // N = 1024: TA 0..31, TC 32..47, FA 48..63 + 112..127, ACC 64..95, PK 96..111; N = 2048: TA 0..63, TC 64..79, FA 80..111
+  constexpr int COL_TA = 0, COL_TC = 4 * RA, COL_ACC = 64, COL_PK = 96;
+  // the packed digit words outlive the first batch: keep them out of passes B, C (N = 1024; at N = 2048 the columns are taken)
+  constexpr bool PK_PARK = PKALL && (L > LB) && LOGM == 9;
+  // The 2 x 4 Fourier accumulators (32 registers) are only touched in pass C: between batches they wait in tensor memory,
+  // which is what lets passes A and B (16 complex values in flight) fit 128 registers without spilling
+  constexpr bool FA_PARK = (L > LB);
+  constexpr int COL_FA0 = (LOGM == 9) ? 48 : 80, COL_FA1 = (LOGM == 9) ? 112 : 96;
+  static_assert(COL_FA1 + 16 <= CPT && (LOGM == 9 || COL_TC + 16 <= COL_FA0), "tensor-memory column layout");
   static_assert(!TMEM_ACC || (COL_TC + 16 <= 64 && COL_ACC == 64), "tensor-memory column layout");
   static_assert(COL_PK + 2 * RA <= CPT && COL_TC + 16 <= COL_PK, "tensor-memory column layout");
   if (tid < 32) {
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
 
     // coefficient pair m of (X^a - 1)*acc + rounding offset (polynomial.c:74-89, 220-235): j = q + 64 m and j + M
     const u64 *ap = acc + pA * N;
-    const int base = (qA - a_i) & (2 * N - 1);        // index of coefficient qA in acc * X^a (sign in bit log2 N)
+    int base = (qA - a_i) & (2 * N - 1);              // index of coefficient qA in acc * X^a (sign in bit log2 N)
     u64 own[8];
     auto coef_pair = [&](int m, u64 &v0, u64 &v1) {
       const int j = qA + m * 64;
@@ -208,6 +222,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     auto batch = [&](auto nb_tag, const int lev0) {
       constexpr int NB = decltype(nb_tag)::value, RB = 2 * NB;
       // ------------------------------- pass A -----------------------------------------------------------------
+      // FUSED: every batch re-reads the coefficients; hide the common subexpressions (32 shared-memory addresses) from the
+      // compiler, which otherwise keeps them across the batch in registers it does not have and spills them
+      if (FUSED) asm volatile("" : "+r"(base));
       if (!PKALL && !FUSED) pack_digits(lev0 + NB);
       if (PK_PARK && lev0 > 0) {
 #pragma unroll
@@ -253,30 +270,37 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         }
       }
       __syncthreads();
+      // key position 4c + pos3 = 8c' + m' is stored at m' * (M/8) + c'; TRGSW row order of trgsw.c:394-419
+      const double2 *__restrict__ kbase = key + (4 * halfC) * (M / 8) + cpC;
+      auto load_half = [&](double2 (&dst)[4], int rb, int o) {        // key row of buffer rb, output polynomial o
+        const int p = rb / NB, lev = lev0 + (rb - p * NB);
+        const double2 *__restrict__ k0 = kbase + (size_t)((p * L + lev) * 2 + o) * M;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = ldg_key(k0 + i * (M / 8));
+      };
+      // KPF: the first row's key values are requested before pass B (the Fourier accumulators are zero or parked, so the
+      // registers are there), and inside pass C each half is re-requested for the next row as soon as its MACs are done
+      double2 kv0[4], kv1[4];
+      if (KPF) { load_half(kv0, 0, 0); load_half(kv1, 0, 1); }
       // ------------------------------- pass B: radix 16 in place, no twiddle --------------------------------------
-      if (rowB < RB) {                                // warp-uniform: a row is TPR = 32 / 64 tasks
+      if (rowB < RB) {
         double2 *blk = buf + rowB * M + pos1B * 64;
         double2 x[16];
 #pragma unroll
-        for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[((4 * m2) ^ b4B) + (rB ^ ((m2 >> 1) & 3))];
+        for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[swz_b(m2)];
         reg_dif<16>(x);
 #pragma unroll
-        for (int pos = 0; pos < 16; ++pos) blk[((4 * pos) ^ b4B) + (rB ^ ((pos >> 1) & 3))] = x[pos];
+        for (int pos = 0; pos < 16; ++pos) blk[swz_b(pos)] = x[pos];
       }
-      __syncthreads();
+      __syncwarp();                                   // pass C below reads only the blocks this warp just transformed
       // ------------------------------- pass C + MAC ----------------------------------------------------------------
       {
+        if (FA_PARK && lev0 > 0) { tmem_ld4(fa[0], taddr + COL_FA0); tmem_ld4(fa[1], taddr + COL_FA1); }
         double2 twc[4];
         tmem_ld4(twc, taddr + COL_TC);
-        // key position 4c + pos3 = 8c' + m' is stored at m' * (M/8) + c'
-        const double2 *__restrict__ kbase = key + (4 * (cC & 1)) * (M / 8) + (cC >> 1);
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
-          const int p = rb / NB, lev = lev0 + (rb - p * NB);
-          const double2 *__restrict__ k0 = kbase + (size_t)((p * L + lev) * 2) * M;   // TRGSW row order of trgsw.c:394-419
-          double2 kv[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { kv[i] = ldg_key(k0 + i * (M / 8)); kv[4 + i] = ldg_key(k0 + M + i * (M / 8)); }
+          if (!KPF) { load_half(kv0, rb, 0); load_half(kv1, rb, 1); }
           const double2 *row = buf + rb * M + cbase;
           double2 x[4];
           x[0] = row[0 ^ cxor];
@@ -284,10 +308,24 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
           for (int r = 1; r < 4; ++r) x[r] = cmul(row[r ^ cxor], twc[r]);
           reg_dif<4>(x);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { cfma(fa[0][i], x[i], kv[i]); cfma(fa[1][i], x[i], kv[4 + i]); }
+          for (int i = 0; i < 4; ++i) cfma(fa[0][i], x[i], kv0[i]);
+          if (KPF && rb + 1 < RB) load_half(kv0, rb + 1, 0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cfma(fa[1][i], x[i], kv1[i]);
+          if (KPF && rb + 1 < RB) load_half(kv1, rb + 1, 1);
         }
       }
-      __syncthreads();
+      // the next batch's pass A overwrites every block of the row buffers; after the LAST batch the inverse starts in
+      // this warp's own blocks (C', B'), so no block barrier is needed there
+      if (lev0 + NB < L) {
+        if (FA_PARK) {
+          tmem_st4(taddr + COL_FA0, fa[0]); tmem_st4(taddr + COL_FA1, fa[1]);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        __syncthreads();
+      } else {
+        __syncwarp();
+      }
     };
 #pragma unroll
     for (int lev0 = 0; lev0 + LB <= L; lev0 += LB) batch(std::integral_constant<int, LB>{}, lev0);
@@ -306,16 +344,16 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         for (int r = 1; r < 4; ++r) row[r ^ cxor] = cmul_conj(fa[o][r], twc[r]);
       }
     }
-    __syncthreads();
-    // ---------------------------------- B' ---------------------------------------------------------------------------
+    __syncwarp();
+    // ---------------------------------- B' (per warp, own blocks) -----------------------------------------------------
     if (rowB < 2) {
       double2 *blk = buf + rowB * M + pos1B * 64;
       double2 x[16];
 #pragma unroll
-      for (int pos = 0; pos < 16; ++pos) x[pos] = blk[((4 * pos) ^ b4B) + (rB ^ ((pos >> 1) & 3))];
+      for (int pos = 0; pos < 16; ++pos) x[pos] = blk[swz_b(pos)];
       reg_dit_inv<16>(x);
 #pragma unroll
-      for (int m2 = 0; m2 < 16; ++m2) blk[((4 * m2) ^ b4B) + (rB ^ ((m2 >> 1) & 3))] = x[m2];
+      for (int m2 = 0; m2 < 16; ++m2) blk[swz_b(m2)] = x[m2];
     }
     __syncthreads();
     // ---------------------------------- A' + accumulate ----------------------------------------------------------------
@@ -403,20 +441,22 @@ static const double2 *k1q_tables_for(int N) {
   return d;
 }
 
-template <int LOGM, int L, int LB, bool PKALL>
+template <int LOGM, int L, int LB, bool PKALL, bool KPF>
 static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.a.size * 2 + 15) & ~(size_t)15);
   static size_t configured = 0;
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1q kernel: %zu B of shared memory needed (blind rotation too long)", smem);
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, KPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  blind_rotate_k1q_kernel<LOGM, L, LB, PKALL><<<count, M / 4, smem, st>>>(a);
+  blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, KPF><<<count, M / 4, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }
+
+constexpr bool K1Q_KPF = true;    // default pass-C key schedule (see the kernel)
 
 // levels per shared-memory batch: 2 when two levels' digits fit the 32-bit packed word, else 1
 static int k1q_lb(int l, int Bg_bit) { return (l >= 2 && 2 * Bg_bit <= 32) ? 2 : 1; }
@@ -447,9 +487,15 @@ void launch_blind_rotate_k1q(const BlindRotateLaunch &b, cudaStream_t st) {
   a.Bg_bit = p.Bg_bit; a.count = b.count;
   const int logm = ilog2i(p.N) - 1, lb = k1q_lb(p.l, p.Bg_bit);
   const bool pkall = p.l * p.Bg_bit <= 32;
+  // experiment knob (benchmark shapes only): MB200_K1Q_KPF=0/1 selects the pass-C key schedule
+  if (const char *e = getenv("MB200_K1Q_KPF")) {
+    const bool kpf = e[0] == '1';
+    if (kpf != K1Q_KPF && logm == 9 && p.l == 3 && lb == 2 && pkall) { launch_q<9, 3, 2, true, !K1Q_KPF>(qa, b.count, st); return; }
+    if (kpf != K1Q_KPF && logm == 10 && p.l == 4 && lb == 2 && !pkall) { launch_q<10, 4, 2, false, !K1Q_KPF>(qa, b.count, st); return; }
+  }
 #define MB_K1Q_CASE(LM, LL, LBB) \
   if (logm == LM && p.l == LL && lb == LBB) { \
-    if (pkall) launch_q<LM, LL, LBB, true>(qa, b.count, st); else launch_q<LM, LL, LBB, false>(qa, b.count, st); \
+    if (pkall) launch_q<LM, LL, LBB, true, K1Q_KPF>(qa, b.count, st); else launch_q<LM, LL, LBB, false, K1Q_KPF>(qa, b.count, st); \
     return; }
   MB_K1Q_CASE(9, 1, 1) MB_K1Q_CASE(9, 2, 2) MB_K1Q_CASE(9, 2, 1) MB_K1Q_CASE(9, 3, 2) MB_K1Q_CASE(9, 3, 1) MB_K1Q_CASE(9, 4, 2) MB_K1Q_CASE(9, 4, 1)
   MB_K1Q_CASE(10, 1, 1) MB_K1Q_CASE(10, 2, 2) MB_K1Q_CASE(10, 2, 1) MB_K1Q_CASE(10, 3, 2) MB_K1Q_CASE(10, 3, 1) MB_K1Q_CASE(10, 4, 2) MB_K1Q_CASE(10, 4, 1)

@@ -12,7 +12,16 @@ def brev(x, bits):
 
 
 def swz(idx):
-    return idx ^ (((idx >> 6) & 1) << 2) ^ ((idx >> 3) & 3)
+    return idx ^ ((idx >> 3) & 7) ^ (((idx >> 6) & 1) << 2)
+
+
+def c_of_thread(tid):
+    """pass C / C': thread -> position group c (positions 4c..4c+3).  Lanes 0..15 of warp w take the even groups of
+    key columns c' = 16w + lane, lanes 16..31 the odd ones, so that the 8 lanes of a quarter warp read 8 consecutive
+    16-byte key words (ONE 128-byte line per quarter-warp request; with c = tid they straddle two lines and the key
+    loads cost twice the L1 wavefronts: ncu r2a)."""
+    w, lane = tid >> 5, tid & 31
+    return 2 * (16 * w + (lane & 15)) + (lane >> 4)
 
 
 def dif(x):
@@ -107,14 +116,22 @@ def check_conflicts(M):
     for qw in range(8):                                   # pass A / A': 8 consecutive q, any pos1
         for pos1 in range(RA):
             assert ok([pos1 * 64 + 8 * qw + i for i in range(8)])
-    for w0 in range(0, RA * 4, 8):                        # pass B / B': lane = (pos1 % 8) * 4 + r
+    for w0 in range(0, RA * 4, 8):                        # pass B / B': lanes (row, pos1 & 1, r), pos1 = 2*warp + bit
         tasks = [(t // 4, t % 4) for t in range(w0, w0 + 8)]
         for m2 in range(16):
             assert ok([p1 * 64 + r + 4 * m2 for p1, r in tasks])
             assert ok([p1 * 64 + m2 * 4 + r for p1, r in tasks])
-    for c0 in range(0, M // 4, 8):                        # pass C / C'
+    for t0 in range(0, M // 4, 8):                        # pass C / C'
+        cs = [c_of_thread(t0 + i) for i in range(8)]
         for r in range(4):
-            assert ok([4 * (c0 + i) + r for i in range(8)])
+            assert ok([4 * c + r for c in cs])
+        # key loads: position 4c + i = 8c' + m' is stored at m' * (M/8) + c': one 128-byte line per quarter warp
+        for i in range(4):
+            words = [(4 * (c & 1) + i) * (M // 8) + (c >> 1) for c in cs]
+            assert max(words) - min(words) == 7 and min(words) % 8 == 0, words
+    # pass B / B' run per warp on the blocks pos1 in {2w, 2w+1} that the same warp's pass C / C' threads own
+    for t in range(M // 4):
+        assert (c_of_thread(t) >> 4) >> 1 == t >> 5
 
 
 for N in (512, 1024, 2048):
