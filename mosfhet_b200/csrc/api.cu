@@ -23,8 +23,9 @@ void reset_launches();
 void drop_tables();
 }  // namespace mb
 
-struct mb200_bsk : mb::BskDev {};
-struct mb200_ksk : mb::KskDev {};
+// `print`: fingerprint of the host key an upload was made from (see key_print below); 0 for keys without a host tree
+struct mb200_bsk : mb::BskDev { unsigned long long print = 0; };
+struct mb200_ksk : mb::KskDev { unsigned long long print = 0; };
 
 namespace {
 
@@ -41,14 +42,100 @@ thread_local char t_last_kernel[96] = "none";
 void set_last_kernel(const char *name) { snprintf(t_last_kernel, sizeof(t_last_kernel), "%s", name); }
 std::map<const void *, mb200_bsk *> g_bsk_cache;   // keyed by Bootstrap_Key->s (the TRGSW_DFT array)
 std::map<const void *, mb200_ksk *> g_ksk_cache;   // keyed by TLWE_KS_Key->s
-struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; };
+struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; unsigned long long print = 0; };
 }  // namespace
 struct mb200_gksk : GkskDev {};
 namespace {
 std::map<const void *, GkskDev *> g_gksk_cache;    // keyed by Generic_KS_Key->s
-struct UbskDev { u64 *d; mb::Params p; int unfolding; };   // torus-domain key of bootstrap.c:23-48, p.n = LWE dimension
+struct UbskDev { u64 *d; mb::Params p; int unfolding; unsigned long long print = 0; };   // torus-domain key of bootstrap.c:23-48, p.n = LWE dimension
 std::map<const void *, UbskDev *> g_ubsk_cache;    // keyed by Bootstrap_Key->su
 std::map<const void *, mb200_bsk *> g_rksk_cache;  // keyed by TRLWE_KS_Key->s, or by the TRLWE_KS_Key[2] array
+
+// ---- resident keys are cached by host pointer; a fingerprint guards the pointer ---------------------------------------
+// The reference's callers free keys and generate new ones (its tests do), and malloc readily hands the same address
+// back; a key can also be regenerated in place.  Every cache entry therefore carries a fingerprint of the host tree it
+// was uploaded from -- the shape, the first / last row pointers and 16 sampled words spread over the key -- which is
+// recomputed (a handful of host reads) on every lookup: a mismatch drops the stale upload and uploads again.  The
+// reference's free_* functions are interposed as well (end of this file) and drop the entry at once.
+struct Printer {
+  unsigned long long h = 0xcbf29ce484222325ull;
+  void add(unsigned long long v) { h = (h ^ v) * 0x100000001b3ull; h ^= h >> 29; }
+  void addp(const void *p) { add((unsigned long long)(uintptr_t)p); }
+  void addd(double v) { unsigned long long b; memcpy(&b, &v, 8); add(b); }
+  unsigned long long done() const { return h | 1ull; }       // never 0 (0 = "no host tree")
+};
+unsigned long long bsk_print(Bootstrap_Key key) {
+  Printer P;
+  P.add(key->n); P.add(key->N); P.add(key->k); P.add(key->l); P.add(key->Bg_bit);
+  const int rows = (key->k + 1) * key->l;
+  for (int a = 0; a < 4; ++a) {
+    const int i = (int)((long long)(key->n - 1) * a / 3);
+    TRGSW_DFT g = key->s[i];
+    P.addp(g);
+    for (int b = 0; b < 2; ++b) {
+      TRLWE_DFT row = g->samples[b ? rows - 1 : 0];
+      P.addp(row);
+      P.addd(row->b->coeffs[(a * 37 + b * 11) % key->N]);
+      P.addd(row->a[0]->coeffs[(a * 101 + b * 7 + 1) % key->N]);
+    }
+  }
+  return P.done();
+}
+unsigned long long ksk_print(TLWE_KS_Key key) {
+  Printer P;
+  const int bm1 = (1 << key->base_bit) - 1, n_out = key->s[0][0][0]->n;
+  P.add(key->n); P.add(key->t); P.add(key->base_bit); P.add(n_out);
+  for (int a = 0; a < 8; ++a) {
+    const int i = (int)((long long)(key->n - 1) * a / 7), j = a % key->t, d = a % bm1;
+    TLWE row = key->s[i][j][d];
+    P.addp(row);
+    P.add(row->b);
+    P.add(row->a[(a * 53) % n_out]);
+  }
+  return P.done();
+}
+unsigned long long gksk_print(Generic_KS_Key key) {
+  Printer P;
+  const int bm1 = (1 << key->base_bit) - 1, entries = key->n + key->include_b;
+  P.add(key->n); P.add(key->t); P.add(key->base_bit); P.add(key->include_b);
+  for (int a = 0; a < 8; ++a) {
+    const int i = (int)((long long)(entries - 1) * a / 7), j = a % key->t, d = a % bm1;
+    TRLWE row = key->s[i][j][d];
+    P.addp(row);
+    P.add(row->b->coeffs[(a * 29) % row->b->N]);
+    P.add(row->a[0]->coeffs[0]);                        // seed word of a compressed row, first coefficient otherwise
+  }
+  return P.done();
+}
+unsigned long long ubsk_print(Bootstrap_Key key) {
+  Printer P;
+  P.add(key->n); P.add(key->N); P.add(key->k); P.add(key->l); P.add(key->Bg_bit); P.add(key->unfolding);
+  const long long n_trgsw = (long long)(key->n / key->unfolding) << key->unfolding;
+  const int rows = (key->k + 1) * key->l;
+  for (int a = 0; a < 8; ++a) {
+    TRGSW g = key->su[(n_trgsw - 1) * a / 7];
+    P.addp(g);
+    TRLWE row = g->samples[a % rows];
+    P.add(row->b->coeffs[(a * 41) % key->N]);
+    P.add(row->a[0]->coeffs[(a * 17 + 3) % key->N]);
+  }
+  return P.done();
+}
+unsigned long long rksk_print(TRLWE_KS_Key k0, TRLWE_KS_Key k1) {
+  Printer P;
+  for (TRLWE_KS_Key key : {k0, k1}) {
+    if (!key) continue;
+    P.add(key->k); P.add(key->t); P.add(key->base_bit);
+    for (int a = 0; a < 4; ++a) {
+      TRLWE_DFT row = key->s[a % key->k][(a * 3) % key->t];
+      P.addp(row);
+      P.addd(row->b->coeffs[(a * 23) % row->b->N]);
+      P.addd(row->a[0]->coeffs[(a * 5 + 1) % row->b->N]);
+    }
+  }
+  return P.done();
+}
+void free_bsk_obj(mb200_bsk *b) { if (b->owned) cudaFree(b->d); delete b; }
 
 mb::Params to_params(const mb200_params *p) {
   mb::Params q;
@@ -92,7 +179,7 @@ struct Scratch {
     h = d = nullptr; hcap = dcap = 0;
   }
 };
-enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_UX, S_UD, S_US, S_COUNT };
+enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_UX, S_UD, S_US, S_PRE, S_COUNT };
 thread_local Scratch t_scratch[S_COUNT];
 
 // ---- host FFT slot order ----------------------------------------------------------------------
@@ -205,16 +292,8 @@ mb200_bsk *bsk_from_host_array(const mb::Params &p, const double *h_bsk, int lay
   return b;
 }
 
-mb200_bsk *lookup_bsk(Bootstrap_Key key) {
-  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
-  MB_REQUIRE(key->unfolding == 1,
-             "Bootstrap_Key with unfolding=%d: only unfolding==1 keys (Fourier-domain ->s) are accelerated",
-             key->unfolding);
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_bsk_cache.find((const void *)key->s);
-    if (it != g_bsk_cache.end()) return it->second;
-  }
+// Uploads a Bootstrap_Key (unfolding == 1) WITHOUT touching the cache: the caller owns the result.
+mb200_bsk *upload_bsk(Bootstrap_Key key) {
   mb::Params p{};
   p.n = key->n; p.N = key->N; p.k = key->k; p.l = key->l; p.Bg_bit = key->Bg_bit; p.t = 0; p.base_bit = 0;
   check_bsk_params(p);
@@ -236,9 +315,57 @@ mb200_bsk *lookup_bsk(Bootstrap_Key key) {
     }
   }
   mb200_bsk *b = bsk_from_host_array(p, flat.data(), -1);
-  std::lock_guard<std::mutex> lk(g_mu);
-  g_bsk_cache[(const void *)key->s] = b;
+  b->print = bsk_print(key);
   return b;
+}
+
+mb200_bsk *lookup_bsk(Bootstrap_Key key) {
+  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
+  MB_REQUIRE(key->unfolding == 1, "Bootstrap_Key with unfolding=%d has no Fourier-domain ->s", key->unfolding);
+  const unsigned long long print = bsk_print(key);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bsk_cache.find((const void *)key->s);
+    if (it != g_bsk_cache.end()) {
+      if (it->second->print == print || it->second->print == 0) return it->second;
+      free_bsk_obj(it->second);                       // same address, different key: the upload is stale
+      g_bsk_cache.erase(it);
+    }
+  }
+  mb200_bsk *b = upload_bsk(key);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto ins = g_bsk_cache.emplace((const void *)key->s, b);
+  if (!ins.second) { free_bsk_obj(b); return ins.first->second; }   // another thread uploaded the same key meanwhile
+  return b;
+}
+
+// A TRGSW_DFT array that may or may not be a registered key (blind_rotate, trgsw_mul_trlwe_DFT and the CMUX receive
+// ciphertexts there, mosfhet.h:344, 409): a registered key is served from the cache, anything else is uploaded for this
+// call only and never enters the cache (another thread could otherwise pick the entry up while this one frees it).
+struct BskRef {
+  mb200_bsk *b = nullptr;
+  bool temporary = false;
+  BskRef() = default;
+  BskRef(const BskRef &) = delete;
+  BskRef &operator=(const BskRef &) = delete;
+  ~BskRef() { if (temporary && b) free_bsk_obj(b); }
+  mb200_bsk *operator->() const { return b; }
+};
+void acquire_bsk_set(BskRef &ref, TRGSW_DFT *s, int n, int k, int N) {
+  MB_REQUIRE(s != nullptr && n >= 1 && s[0] != nullptr, "TRGSW_DFT array is NULL or empty");
+  struct _Bootstrap_Key tmp;
+  tmp.s = s; tmp.su = nullptr; tmp.n = n; tmp.k = k; tmp.N = N; tmp.Bg_bit = s[0]->Bg_bit; tmp.l = s[0]->l; tmp.unfolding = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bsk_cache.find((const void *)s);
+    if (it != g_bsk_cache.end() && it->second->p.n >= n && it->second->p.k == k && it->second->p.N == N) {
+      tmp.n = it->second->p.n;
+      if (it->second->print == 0 || it->second->print == bsk_print(&tmp)) { ref.b = it->second; ref.temporary = false; return; }
+      tmp.n = n;
+    }
+  }
+  ref.b = upload_bsk(&tmp);
+  ref.temporary = true;
 }
 
 mb200_ksk *ksk_from_host_array(const mb::Params &p, const u64 *h_ksk) {
@@ -255,10 +382,16 @@ mb200_ksk *ksk_from_host_array(const mb::Params &p, const u64 *h_ksk) {
 
 mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
   MB_REQUIRE(key != nullptr, "TLWE_KS_Key is NULL");
+  const unsigned long long print = ksk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_ksk_cache.find((const void *)key->s);
-    if (it != g_ksk_cache.end()) return it->second;
+    if (it != g_ksk_cache.end()) {
+      if (it->second->print == print) return it->second;
+      if (it->second->owned) cudaFree(it->second->d);
+      delete it->second;
+      g_ksk_cache.erase(it);
+    }
   }
   mb::Params p{};
   p.n = key->s[0][0][0]->n;
@@ -276,6 +409,7 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
         o += w;
       }
   mb200_ksk *k = ksk_from_host_array(p, flat.data());
+  k->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
   g_ksk_cache[(const void *)key->s] = k;
   (void)n_in_expected;
@@ -285,13 +419,20 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
 // Generic (TRLWE-row) key-switching key: u64 [n + include_b][t][2^base_bit-1][(k+1)*N]
 GkskDev *lookup_gksk(Generic_KS_Key key) {
   MB_REQUIRE(key != nullptr, "Generic_KS_Key is NULL");
+  const unsigned long long print = gksk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_gksk_cache.find((const void *)key->s);
-    if (it != g_gksk_cache.end()) return it->second;
+    if (it != g_gksk_cache.end()) {
+      if (it->second->print == print) return it->second;
+      cudaFree(it->second->d);
+      delete it->second;
+      g_gksk_cache.erase(it);
+    }
   }
   mb::ensure_init();
   GkskDev *g = new GkskDev();
+  g->print = print;
   TRLWE r0 = key->s[0][0][0];
   g->k = r0->k; g->N = r0->b->N; g->t = key->t; g->base_bit = key->base_bit; g->n_in = key->n; g->include_b = key->include_b;
   g->n_entries = key->n + key->include_b;
@@ -419,8 +560,10 @@ void pbs_dev_impl(mb200_bsk_t bsk, u64 *d_out, int extract, const u64 *d_tv, int
 // functional path for callers holding unfolding > 1 keys; the unfolding == 1 kernels are the fast ones.
 UbskDev *ubsk_upload(TRGSW *su, int n, int unfolding, int k, int N, int l, int Bg_bit) {
   mb::ensure_init();
-  MB_REQUIRE(unfolding >= 2 && unfolding <= 8 && n % unfolding == 0,
-             "unfolded bootstrap key: n=%d must be a multiple of unfolding=%d (2..8)", n, unfolding);
+  // The reference lays the key out as su[i * (2^u / u) + j], j < 2^u, for i = 0, u, 2u, ... (bootstrap.c:35-45): groups
+  // of 2^u samples only when u divides 2^u.  For u = 3, 5, 6, 7 its own groups overlap, so those values are refused.
+  MB_REQUIRE((unfolding == 2 || unfolding == 4 || unfolding == 8) && n % unfolding == 0,
+             "unfolded bootstrap key: unfolding=%d must be 2, 4 or 8 and divide n=%d", unfolding, n);
   UbskDev *U = new UbskDev();
   U->p = mb::Params{}; U->p.n = n; U->p.N = N; U->p.k = k; U->p.l = l; U->p.Bg_bit = Bg_bit;
   check_bsk_params(U->p);
@@ -444,12 +587,20 @@ UbskDev *ubsk_upload(TRGSW *su, int n, int unfolding, int k, int N, int l, int B
 }
 UbskDev *lookup_ubsk(Bootstrap_Key key) {
   MB_REQUIRE(key != nullptr && key->su != nullptr, "Bootstrap_Key (unfolding > 1) has no torus-domain key");
+  MB_REQUIRE(key->unfolding == 2 || key->unfolding == 4 || key->unfolding == 8, "Bootstrap_Key: unfolding=%d (2, 4 or 8)", key->unfolding);
+  const unsigned long long print = ubsk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_ubsk_cache.find((const void *)key->su);
-    if (it != g_ubsk_cache.end()) return it->second;
+    if (it != g_ubsk_cache.end()) {
+      if (it->second->print == print) return it->second;
+      cudaFree(it->second->d);
+      delete it->second;
+      g_ubsk_cache.erase(it);
+    }
   }
   UbskDev *U = ubsk_upload(key->su, key->n, key->unfolding, key->k, key->N, key->l, key->Bg_bit);
+  U->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
   g_ubsk_cache[(const void *)key->su] = U;
   return U;
@@ -510,6 +661,34 @@ void pbs_unfolded_core(UbskDev *U, u64 *d_out, int extract, const u64 *d_tv, int
     MB_CHECK(cudaMemsetAsync(d_idx, 0, sizeof(int), st));
     mb::launch_extract(d_out, d_acc, d_idx, 1, p.N, p.k, count, st);
   }
+}
+
+// A Bootstrap_Key of either kind (bootstrap.c:192-198 dispatches on key->unfolding): Fourier-domain ->s on the fused
+// kernels, or torus-domain ->su through the unfolded path above.
+struct AnyBsk {
+  mb200_bsk *bsk = nullptr;
+  UbskDev *U = nullptr;
+  AnyBsk() = default;
+  AnyBsk(mb200_bsk *b) : bsk(b) {}
+  const mb::Params &p() const { return U ? U->p : bsk->p; }
+};
+AnyBsk lookup_any_bsk(Bootstrap_Key key) {
+  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
+  AnyBsk k;
+  if (key->unfolding > 1) k.U = lookup_ubsk(key);
+  else k.bsk = lookup_bsk(key);
+  return k;
+}
+void pbs_any(const AnyBsk &k, u64 *d_out, int extract, const u64 *d_tv, int tv_count, const u64 *d_in, int torus_base,
+             int count, cudaStream_t st, int preprocess = 0, int kappa = 0, int theta = 0) {
+  if (!k.U) { pbs_dev_impl(k.bsk, d_out, extract, d_tv, tv_count, d_in, torus_base, count, st, preprocess, kappa, theta); return; }
+  const mb::Params &p = k.U->p;
+  if (preprocess) {                                   // programmable_bootstrap's input shaping (bootstrap.c:210-217), then :218
+    u64 *d_pre = (u64 *)t_scratch[S_PRE].dev(sizeof(u64) * (size_t)count * (p.n + 1));
+    mb::launch_pb_preprocess(d_pre, d_in, (size_t)count * (p.n + 1), kappa, theta, mb::ilog2i(p.N) + 1, st);
+    d_in = d_pre;
+  }
+  pbs_unfolded_core(k.U, d_out, extract, d_tv, tv_count, d_in, torus_base, count, st);
 }
 
 // ---- handle-tree gather / scatter -----------------------------------------------------------------
@@ -906,16 +1085,13 @@ void mb200_set_kernel_policy(int policy) { g_policy = policy; }
 void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
                                            int torus_base, int count) {
   if (count <= 0) return;
-  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
-  UbskDev *U = key->unfolding > 1 ? lookup_ubsk(key) : nullptr;
-  mb200_bsk *bsk = U ? nullptr : lookup_bsk(key);
-  const mb::Params &p = U ? U->p : bsk->p;
+  const AnyBsk bk = lookup_any_bsk(key);
+  const mb::Params &p = bk.p();
   cudaStream_t st = mb::default_stream();
   PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
   const size_t out_b = sizeof(u64) * (size_t)count * (p.k + 1) * p.N;
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  if (U) pbs_unfolded_core(U, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
-  else pbs_dev_impl(bsk, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
+  pbs_any(bk, d_out, 0, s.d_tv, tv_count, s.d_in, torus_base, count, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_trlwe(out, h_out, count, p.k, p.N);
@@ -924,17 +1100,13 @@ void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, 
 static void fb_batch_impl(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int torus_base, int count,
                           int preprocess, int kappa, int theta) {
   if (count <= 0) return;
-  MB_REQUIRE(key != nullptr, "Bootstrap_Key is NULL");
-  MB_REQUIRE(key->unfolding == 1 || !preprocess, "programmable_bootstrap: unfolding > 1 keys are not supported");
-  UbskDev *U = key->unfolding > 1 ? lookup_ubsk(key) : nullptr;
-  mb200_bsk *bsk = U ? nullptr : lookup_bsk(key);
-  const mb::Params &p = U ? U->p : bsk->p;
+  const AnyBsk bk = lookup_any_bsk(key);
+  const mb::Params &p = bk.p();
   cudaStream_t st = mb::default_stream();
   PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
   const size_t out_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  if (U) pbs_unfolded_core(U, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st);
-  else pbs_dev_impl(bsk, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st, preprocess, kappa, theta);
+  pbs_any(bk, d_out, 1, s.d_tv, tv_count, s.d_in, torus_base, count, st, preprocess, kappa, theta);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_tlwe(out, h_out, count, p.k * p.N);
@@ -990,21 +1162,9 @@ void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count)
   if (count <= 0 || size <= 0) return;
   // `s` is a bare TRGSW_DFT array (mosfhet.h:409): registered keys are found by pointer, anything
   // else (e.g. fresh encrypted selectors, vertical_packing.c:50) is uploaded for this call only.
-  mb200_bsk *bsk = nullptr;
-  bool temporary = false;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_bsk_cache.find((const void *)s);
-    if (it != g_bsk_cache.end()) bsk = it->second;
-  }
   const int k = tv[0]->k, N = tv[0]->b->N;
-  if (!bsk) {
-    struct _Bootstrap_Key tmp;
-    tmp.s = s; tmp.su = nullptr; tmp.n = size; tmp.k = k; tmp.N = N; tmp.Bg_bit = s[0]->Bg_bit; tmp.l = s[0]->l;
-    tmp.unfolding = 1;
-    bsk = lookup_bsk(&tmp);
-    temporary = true;
-  }
+  BskRef bsk;
+  acquire_bsk_set(bsk, s, size, k, N);
   MB_REQUIRE(size <= bsk->p.n, "blind_rotate: size %d exceeds key length %d", size, bsk->p.n);
   cudaStream_t st = mb::default_stream();
   const size_t a_b = sizeof(u64) * (size_t)count * size, acc_b = sizeof(u64) * (size_t)count * (k + 1) * N;
@@ -1014,16 +1174,10 @@ void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count)
   gather_trlwe(h_acc, tv, count, k, N);
   MB_CHECK(cudaMemcpyAsync(d_a, h_a, a_b, cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaMemcpyAsync(d_acc, h_acc, acc_b, cudaMemcpyHostToDevice, st));
-  mb200_blind_rotate_dev(bsk, (uint64_t *)d_acc, (const uint64_t *)d_a, size, size, count, st);
+  mb200_blind_rotate_dev(bsk.b, (uint64_t *)d_acc, (const uint64_t *)d_a, size, size, count, st);
   MB_CHECK(cudaMemcpyAsync(h_acc, d_acc, acc_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_trlwe(tv, h_acc, count, k, N);
-  if (temporary) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_bsk_cache.erase((const void *)s);
-    if (bsk->owned) cudaFree(bsk->d);
-    delete bsk;
-  }
 }
 
 void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int in2_count, int count) {
@@ -1031,16 +1185,8 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
   MB_REQUIRE(in2_count == 1 || in2_count == count, "trgsw_mul_trlwe_DFT_batch: in2_count must be 1 or count");
   const int k = in1[0]->k, N = in1[0]->b->N;
   MB_REQUIRE(k == in2[0]->samples[0]->k, "trgsw_mul_trlwe_DFT: k mismatch (trgsw.c:389)");
-  struct _Bootstrap_Key tmp;
-  tmp.s = in2; tmp.su = nullptr; tmp.n = in2_count; tmp.k = k; tmp.N = N; tmp.Bg_bit = in2[0]->Bg_bit; tmp.l = in2[0]->l;
-  tmp.unfolding = 1;
-  mb200_bsk *set;
-  bool cached;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    cached = g_bsk_cache.count((const void *)in2) != 0;
-  }
-  set = lookup_bsk(&tmp);
+  BskRef set;
+  acquire_bsk_set(set, in2, in2_count, k, N);
   cudaStream_t st = mb::default_stream();
   DftMaps maps = dft_maps_for(N);
   const size_t in_b = sizeof(u64) * (size_t)count * (k + 1) * N, out_b = sizeof(double) * (size_t)count * (k + 1) * N;
@@ -1052,7 +1198,7 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
   MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
   mb::BlindRotateLaunch a{};
-  a.bsk = set; a.tv = d_in; a.tv_count = count; a.size = 1; a.out = nullptr; a.count = count; a.direct = 1; a.sel = d_sel;
+  a.bsk = set.b; a.tv = d_in; a.tv_count = count; a.size = 1; a.out = nullptr; a.count = count; a.direct = 1; a.sel = d_sel;
   a.sel_const = -1;
   a.dft_out = d_out; a.dft_perm = maps.stored_to_host; a.dft_conj = maps.stored_conj;
   mb::launch_blind_rotate_generic(a, st);
@@ -1064,22 +1210,14 @@ void trgsw_mul_trlwe_DFT_batch(TRLWE_DFT *out, TRLWE *in1, TRGSW_DFT *in2, int i
     for (int q = 0; q < k; ++q) memcpy(out[i]->a[q]->coeffs, h_out + ((size_t)i * (k + 1) + q) * N, sizeof(double) * N);
     memcpy(out[i]->b->coeffs, h_out + ((size_t)i * (k + 1) + k) * N, sizeof(double) * N);
   }
-  if (!cached) {   // operand was not a registered key: do not keep it resident
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_bsk_cache.erase((const void *)in2);
-    if (set->owned) cudaFree(set->d);
-    delete set;
-  }
 }
 
 /* CMUX over arrays of handles with one selector (vertical_packing.c:24-33); out[i] may be in1[i] */
 void trgsw_cmux_batch(TRLWE *out, TRLWE *in1, TRLWE *in2, TRGSW_DFT selector, int count) {
   if (count <= 0) return;
   const int k = in1[0]->k, N = in1[0]->b->N;
-  struct _Bootstrap_Key tmp;
-  tmp.s = &selector; tmp.su = nullptr; tmp.n = 1; tmp.k = k; tmp.N = N; tmp.Bg_bit = selector->Bg_bit; tmp.l = selector->l;
-  tmp.unfolding = 1;
-  mb200_bsk *set = lookup_bsk(&tmp);
+  BskRef set;                                      // the selector is a ciphertext, not a key: uploaded for this call only
+  acquire_bsk_set(set, &selector, 1, k, N);
   cudaStream_t st = mb::default_stream();
   const size_t b = sizeof(u64) * (size_t)count * (k + 1) * N;
   u64 *h1 = (u64 *)t_scratch[S_TV].host(b), *d1 = (u64 *)t_scratch[S_TV].dev(b);
@@ -1088,14 +1226,10 @@ void trgsw_cmux_batch(TRLWE *out, TRLWE *in1, TRLWE *in2, TRGSW_DFT selector, in
   gather_trlwe(h2, in2, count, k, N);
   MB_CHECK(cudaMemcpyAsync(d1, h1, b, cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaMemcpyAsync(d2, h2, b, cudaMemcpyHostToDevice, st));
-  mb200_cmux_dev(set, 0, (uint64_t *)d1, (const uint64_t *)d1, (const uint64_t *)d2, count, st);
+  mb200_cmux_dev(set.b, 0, (uint64_t *)d1, (const uint64_t *)d1, (const uint64_t *)d2, count, st);
   MB_CHECK(cudaMemcpyAsync(h1, d1, b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_trlwe(out, h1, count, k, N);
-  std::lock_guard<std::mutex> lk(g_mu);          // the selector is a ciphertext, not a key: do not keep it resident
-  g_bsk_cache.erase((const void *)&selector);
-  if (set->owned) cudaFree(set->d);
-  delete set;
 }
 
 void trlwe_from_DFT_batch(TRLWE *out, TRLWE_DFT *in, int count) {
@@ -1138,8 +1272,8 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
                                        int torus_base, int n_luts, int count) {
   // bootstrap.c:222-230: one blind rotation with torus_base*n_luts, then n_luts extractions
   if (count <= 0) return;
-  mb200_bsk *bsk = lookup_bsk(key);
-  const mb::Params &p = bsk->p;
+  const AnyBsk bsk = lookup_any_bsk(key);
+  const mb::Params &p = bsk.p();
   cudaStream_t st = mb::default_stream();
   PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
   const int slot_size = p.N / (n_luts * torus_base);
@@ -1149,7 +1283,7 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
   const size_t out_b = sizeof(u64) * (size_t)count * n_luts * (p.k * p.N + 1);
   u64 *d_acc = (u64 *)t_scratch[S_MID].dev(acc_b);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  pbs_dev_impl(bsk, d_acc, 0, s.d_tv, tv_count, s.d_in, torus_base * n_luts, count, st);
+  pbs_any(bsk, d_acc, 0, s.d_tv, tv_count, s.d_in, torus_base * n_luts, count, st);
   mb200_extract_dev((uint64_t *)d_out, (const uint64_t *)d_acc, idx.data(), n_luts, p.N, p.k, count, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
@@ -1158,8 +1292,8 @@ void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE
 
 void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key, int torus_base, int count) {
   if (count <= 0) return;
-  mb200_bsk *bsk = lookup_bsk(key);
-  const mb::Params &p = bsk->p;
+  const AnyBsk bsk = lookup_any_bsk(key);
+  const mb::Params &p = bsk.p();
   cudaStream_t st = mb::default_stream();
   const size_t W = (size_t)(p.k + 1) * p.N;
   const size_t in_b = sizeof(u64) * (size_t)count * (p.n + 1), tv_b = sizeof(u64) * W;
@@ -1175,7 +1309,7 @@ void multivalue_bootstrap_phase1_batch(TRLWE **out, TLWE *in, Bootstrap_Key key,
   for (int i = 0; i < p.N; ++i) h_tv[(size_t)p.k * p.N + i] = cst;
   MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
-  pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, torus_base, count, st);
+  pbs_any(bsk, d_acc, 0, d_tv, 1, d_in, torus_base, count, st);
   mb::launch_mv_phase1_rotations(d_out, d_acc, p.N, p.k, torus_base, count, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
@@ -1250,24 +1384,36 @@ static mb200_bsk *rksk_build(TRLWE_KS_Key k0, TRLWE_KS_Key k1) {
 }
 static mb200_bsk *lookup_rksk(TRLWE_KS_Key key) {
   MB_REQUIRE(key != nullptr, "TRLWE_KS_Key is NULL");
+  const unsigned long long print = rksk_print(key, nullptr);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_rksk_cache.find((const void *)key->s);
-    if (it != g_rksk_cache.end()) return it->second;
+    if (it != g_rksk_cache.end()) {
+      if (it->second->print == print) return it->second;
+      free_bsk_obj(it->second);
+      g_rksk_cache.erase(it);
+    }
   }
   mb200_bsk *b = rksk_build(key, nullptr);
+  b->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
   g_rksk_cache[(const void *)key->s] = b;
   return b;
 }
 static mb200_bsk *lookup_rksk_pair(TRLWE_KS_Key *keys) {
   MB_REQUIRE(keys != nullptr && keys[0] != nullptr && keys[1] != nullptr, "TRLWE_KS_Key pair is NULL");
+  const unsigned long long print = rksk_print(keys[0], keys[1]);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_rksk_cache.find((const void *)keys);
-    if (it != g_rksk_cache.end()) return it->second;
+    if (it != g_rksk_cache.end()) {
+      if (it->second->print == print) return it->second;
+      free_bsk_obj(it->second);
+      g_rksk_cache.erase(it);
+    }
   }
   mb200_bsk *b = rksk_build(keys[0], keys[1]);
+  b->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
   g_rksk_cache[(const void *)keys] = b;
   return b;
@@ -1306,9 +1452,9 @@ void trlwe_priv_keyswitch_2_batch(TRLWE *out, TRLWE *in, TRLWE_KS_Key *ks_key, i
 //   variant 2  circuit_bootstrap_2  ONE blind rotation of the packed LUT (0,..,0, h_0,..,h_{l-1}), l extractions
 //   variant 3  circuit_bootstrap_3  as 2, but the private rows come from the FFT key switch of the packing rows
 // d_out: [count][2*l_out][Wo] (rows 0..l-1 private, l..2l-1 packing).
-static void circuit_bootstrap_core(int variant, mb200_bsk *bsk, GkskDev *ga, mb200_bsk *ga2, GkskDev *gb, u64 *d_out,
+static void circuit_bootstrap_core(int variant, const AnyBsk &bsk, GkskDev *ga, mb200_bsk *ga2, GkskDev *gb, u64 *d_out,
                                    const u64 *d_in, int lo, int Bgo, int count, cudaStream_t st) {
-  const mb::Params &p = bsk->p;
+  const mb::Params &p = bsk.p();
   MB_REQUIRE(p.k == 1, "circuit bootstrap: k = 1 only");
   MB_REQUIRE(variant == 1 || lo == p.l, "circuit_bootstrap_%d: needs out->l == key->l (the reference indexes the LUT with both)", variant);
   MB_REQUIRE(gb->n_in == p.k * p.N && (!ga || ga->n_in == p.k * p.N), "circuit bootstrap: key switch input dimension mismatch");
@@ -1329,7 +1475,7 @@ static void circuit_bootstrap_core(int variant, mb200_bsk *bsk, GkskDev *ga, mb2
       for (int c = p.N / 2; c < p.N; ++c) h_tv[(size_t)i * W + (size_t)p.k * p.N + c] = 1ull << (64 - (i + 1) * Bgo);
     MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
     for (int i = 0; i < lo; ++i)
-      pbs_dev_impl(bsk, d_tl + (size_t)i * count * tlw, 1, d_tv + (size_t)i * W, 1, d_in, 2, count, st);
+      pbs_any(bsk, d_tl + (size_t)i * count * tlw, 1, d_tv + (size_t)i * W, 1, d_in, 2, count, st);
   } else {
     const size_t tv_b = sizeof(u64) * W;
     u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
@@ -1342,7 +1488,7 @@ static void circuit_bootstrap_core(int variant, mb200_bsk *bsk, GkskDev *ga, mb2
     }
     MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
     u64 *d_acc = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * count * W);
-    pbs_dev_impl(bsk, d_acc, 0, d_tv, 1, d_in, 2 * p.l, count, st);
+    pbs_any(bsk, d_acc, 0, d_tv, 1, d_in, 2 * p.l, count, st);
     std::vector<int> idx(lo);
     for (int i = 0; i < lo; ++i) idx[i] = i * slot;
     mb200_extract_dev((uint64_t *)d_tl, (const uint64_t *)d_acc, idx.data(), lo, p.N, p.k, count, st);   // [count][l]
@@ -1368,10 +1514,10 @@ static void circuit_bootstrap_core(int variant, mb200_bsk *bsk, GkskDev *ga, mb2
 static void circuit_bootstrap_handles(int variant, TRGSW *out, TLWE *in, Bootstrap_Key key, Generic_KS_Key kska,
                                       TRLWE_KS_Key *kska2, Generic_KS_Key kskb, int count) {
   if (count <= 0) return;
-  mb200_bsk *bsk = lookup_bsk(key);
+  const AnyBsk bsk = lookup_any_bsk(key);
   GkskDev *ga = kska ? lookup_gksk(kska) : nullptr, *gb = lookup_gksk(kskb);
   mb200_bsk *ga2 = kska2 ? lookup_rksk_pair(kska2) : nullptr;
-  const mb::Params &p = bsk->p;
+  const mb::Params &p = bsk.p();
   const int lo = out[0]->l, Bgo = out[0]->Bg_bit;
   cudaStream_t st = mb::default_stream();
   const size_t Wo = (size_t)(gb->k + 1) * gb->N;
@@ -1468,14 +1614,8 @@ void multivalue_bootstrap_UBR_phase1(TRGSW_DFT *out, TLWE in, Bootstrap_Key key)
 void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa, Bootstrap_Key key, int torus_base) {
   MB_REQUIRE(key != nullptr && key->unfolding >= 1 && sa != nullptr, "multivalue_bootstrap_UBR_phase2: bad arguments");
   const int k = tv->k, N = tv->b->N, groups = key->n / key->unfolding;
-  struct _Bootstrap_Key tmp;
-  tmp.s = sa; tmp.su = nullptr; tmp.n = groups; tmp.k = k; tmp.N = N; tmp.Bg_bit = sa[0]->Bg_bit; tmp.l = sa[0]->l; tmp.unfolding = 1;
-  bool cached;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    cached = g_bsk_cache.count((const void *)sa) != 0;
-  }
-  mb200_bsk *set = lookup_bsk(&tmp);
+  BskRef set;
+  acquire_bsk_set(set, sa, groups, k, N);
   mb::Params p = set->p;
   p.n = key->n;
   MB_REQUIRE(in->n == p.n, "TLWE has dimension %d, expected %d", in->n, p.n);
@@ -1486,7 +1626,7 @@ void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa,
   initial_rotation_dev(p, d_acc, sg.d_tv, 1, sg.d_in, torus_base, 1, st);
   for (int i = 0; i < groups; ++i) {
     mb::BlindRotateLaunch a{};
-    a.bsk = set; a.tv = d_acc; a.tv_count = 1; a.size = 1; a.out = d_acc; a.count = 1; a.direct = 1; a.sel_const = i;
+    a.bsk = set.b; a.tv = d_acc; a.tv_count = 1; a.size = 1; a.out = d_acc; a.count = 1; a.direct = 1; a.sel_const = i;
     run_direct(a, st);
   }
   const size_t out_b = sizeof(u64) * (k * N + 1);
@@ -1497,12 +1637,6 @@ void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa,
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_tlwe(&out, h_out, 1, k * N);
-  if (!cached) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_bsk_cache.erase((const void *)sa);
-    if (set->owned) cudaFree(set->d);
-    delete set;
-  }
 }
 
 // ---- rank 4: TRGSW-accumulator bootstrap (bootstrap.c:267-306) ------------------------------------------------
@@ -1553,14 +1687,8 @@ void functional_bootstrap_trgsw_phase2_batch(TLWE *out, TRGSW_DFT *in, TRLWE *tv
   if (count <= 0) return;
   MB_REQUIRE(tv_count == 1 || tv_count == count, "functional_bootstrap_trgsw_phase2_batch: tv_count must be 1 or count");
   const int k = tv[0]->k, N = tv[0]->b->N;
-  struct _Bootstrap_Key tmp;
-  tmp.s = in; tmp.su = nullptr; tmp.n = count; tmp.k = k; tmp.N = N; tmp.Bg_bit = in[0]->Bg_bit; tmp.l = in[0]->l; tmp.unfolding = 1;
-  bool cached;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    cached = g_bsk_cache.count((const void *)in) != 0;
-  }
-  mb200_bsk *set = lookup_bsk(&tmp);
+  BskRef set;
+  acquire_bsk_set(set, in, count, k, N);
   cudaStream_t st = mb::default_stream();
   const size_t W = (size_t)(k + 1) * N, tv_b = sizeof(u64) * (size_t)tv_count * W, out_b = sizeof(u64) * (size_t)count * (k * N + 1);
   u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
@@ -1571,18 +1699,12 @@ void functional_bootstrap_trgsw_phase2_batch(TLWE *out, TRGSW_DFT *in, TRLWE *tv
   MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaMemcpyAsync(d_sel, h_sel, sizeof(int) * count, cudaMemcpyHostToDevice, st));
   mb::BlindRotateLaunch a{};
-  a.bsk = set; a.tv = d_tv; a.tv_count = tv_count; a.size = 1; a.out = d_out; a.extract = 1; a.count = count; a.direct = 1;
+  a.bsk = set.b; a.tv = d_tv; a.tv_count = tv_count; a.size = 1; a.out = d_out; a.extract = 1; a.count = count; a.direct = 1;
   a.sel = d_sel; a.sel_const = -1;
   run_direct(a, st);
   MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
   MB_CHECK(cudaStreamSynchronize(st));
   scatter_tlwe(out, h_out, count, k * N);
-  if (!cached) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_bsk_cache.erase((const void *)in);
-    if (set->owned) cudaFree(set->d);
-    delete set;
-  }
 }
 void functional_bootstrap_trgsw_phase2(TLWE out, TRGSW_DFT in, TRLWE tv) {
   functional_bootstrap_trgsw_phase2_batch(&out, &in, &tv, 1, 1);
@@ -1618,7 +1740,7 @@ void mb200_trlwe_ks_dev(mb200_gksk_t ksk, uint64_t *d_out, const uint64_t *d_in,
 void mb200_circuit_bootstrap_dev(mb200_bsk_t bsk, mb200_gksk_t kska, mb200_gksk_t kskb, uint64_t *d_out_trgsw,
                                  const uint64_t *d_in, int Bg_bit_out, int count, void *stream) {
   if (count <= 0) return;
-  circuit_bootstrap_core(2, bsk, kska, nullptr, kskb, (u64 *)d_out_trgsw, (const u64 *)d_in, bsk->p.l, Bg_bit_out, count,
+  circuit_bootstrap_core(2, AnyBsk(bsk), kska, nullptr, kskb, (u64 *)d_out_trgsw, (const u64 *)d_in, bsk->p.l, Bg_bit_out, count,
                          as_stream(stream));
 }
 
@@ -1674,7 +1796,7 @@ void mb200_circuit_bootstrap_variant_dev(int variant, mb200_bsk_t bsk, mb200_gks
   MB_REQUIRE(variant >= 1 && variant <= 3, "circuit bootstrap variant %d unknown", variant);
   MB_REQUIRE(variant == 3 ? kska_fft != nullptr : kska != nullptr, "circuit bootstrap variant %d: private key switch key missing", variant);
   if (count <= 0) return;
-  circuit_bootstrap_core(variant, bsk, variant == 3 ? nullptr : kska, variant == 3 ? kska_fft : nullptr, kskb,
+  circuit_bootstrap_core(variant, AnyBsk(bsk), variant == 3 ? nullptr : kska, variant == 3 ? kska_fft : nullptr, kskb,
                          (u64 *)d_out_trgsw, (const u64 *)d_in, l_out, Bg_bit_out, count, as_stream(stream));
 }
 void mb200_register_generic_ks_key(Generic_KS_Key key) { (void)lookup_gksk(key); }
@@ -1691,6 +1813,36 @@ void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int tor
 }
 void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base, int log_torus_base) {
   multivalue_bootstrap_phase2_batch(&out, &in, 1, &rotated_tv, torus_base, log_torus_base, 1);
+}
+
+// ---- the reference's key destructors, interposed (mosfhet.h:231, 376, 388, 417) -------------------------------------------
+// When this library sits in front of the reference (LD_PRELOAD, or earlier in the link order), freeing a key first drops
+// the resident copy made from it -- malloc will hand the address to the next key -- and then runs the reference's own
+// free_* (the next definition in lookup order).  Without a next definition the host tree is not ours to free.
+static void chain_free(const char *name, void *key) {
+  typedef void (*fn_t)(void *);
+  fn_t next = (fn_t)dlsym(RTLD_NEXT, name);
+  if (next) next(key);
+}
+void free_bootstrap_key(Bootstrap_Key key) {
+  if (!key) return;
+  mb200_release_bootstrap_key(key);
+  chain_free("free_bootstrap_key", key);
+}
+void free_tlwe_ks_key(TLWE_KS_Key key) {
+  if (!key) return;
+  mb200_release_ks_key(key);
+  chain_free("free_tlwe_ks_key", key);
+}
+void free_trlwe_generic_ks_key(Generic_KS_Key key) {
+  if (!key) return;
+  mb200_release_generic_ks_key(key);
+  chain_free("free_trlwe_generic_ks_key", key);
+}
+void free_trlwe_ks_key(TRLWE_KS_Key key) {
+  if (!key) return;
+  mb200_release_trlwe_ks_key(key);
+  chain_free("free_trlwe_ks_key", key);
 }
 
 }  // extern "C"

@@ -41,6 +41,39 @@ __device__ __forceinline__ u64 f64_to_torus_scaled(double x, double scale /* 2^-
   return (u64)__double2ll_rn(y);
 }
 
+// (cos, sin) of W_64^idx for a compile-time idx, from the 14 first-octant constants (see mul_w64)
+__device__ __forceinline__ void w64_cs(int idx, double &c, double &s) {
+  idx &= 63;
+  const double h = 0.70710678118654752440;
+  const int qd = idx >> 4, rem = idx & 15;
+  double c0, s0;
+  if (rem == 0) { c0 = 1.0; s0 = 0.0; }
+  else if (rem == 8) { c0 = h; s0 = h; }
+  else { c0 = rem < 8 ? CW64C[rem] : CW64S[16 - rem]; s0 = rem < 8 ? CW64S[rem] : CW64C[16 - rem]; }
+  if (qd == 0) { c = c0; s = s0; } else if (qd == 1) { c = -s0; s = c0; } else if (qd == 2) { c = -c0; s = -s0; } else { c = s0; s = -c0; }
+}
+
+// Tensor-memory loads issued early and waited for late: the 16 words become valid at tmem_wait, which takes them as
+// read-write operands so that no use can be scheduled ahead of it.
+struct TmemLd { unsigned w[16]; };
+__device__ __forceinline__ void tmem_issue(TmemLd &t, unsigned taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(t.w[0]), "=r"(t.w[1]), "=r"(t.w[2]), "=r"(t.w[3]), "=r"(t.w[4]), "=r"(t.w[5]), "=r"(t.w[6]), "=r"(t.w[7]), "=r"(t.w[8]),
+        "=r"(t.w[9]), "=r"(t.w[10]), "=r"(t.w[11]), "=r"(t.w[12]), "=r"(t.w[13]), "=r"(t.w[14]), "=r"(t.w[15])
+      : "r"(taddr)
+      : "memory");
+}
+#define MB_TMEM_RW(t) "+r"((t).w[0]), "+r"((t).w[1]), "+r"((t).w[2]), "+r"((t).w[3]), "+r"((t).w[4]), "+r"((t).w[5]), "+r"((t).w[6]), \
+                      "+r"((t).w[7]), "+r"((t).w[8]), "+r"((t).w[9]), "+r"((t).w[10]), "+r"((t).w[11]), "+r"((t).w[12]), "+r"((t).w[13]), \
+                      "+r"((t).w[14]), "+r"((t).w[15])
+__device__ __forceinline__ void tmem_wait(TmemLd &a) { asm volatile("tcgen05.wait::ld.sync.aligned;" : MB_TMEM_RW(a)::"memory"); }
+__device__ __forceinline__ void tmem_also(TmemLd &a) { asm volatile("" : MB_TMEM_RW(a)); }   // after a tmem_wait: same dependency, no instruction
+__device__ __forceinline__ double2 tmem_c(const TmemLd &t, int i) {
+  return make_double2(__hiloint2double((int)t.w[4 * i + 1], (int)t.w[4 * i]), __hiloint2double((int)t.w[4 * i + 3], (int)t.w[4 * i + 2]));
+}
+__device__ __forceinline__ u64 tmem_u(const TmemLd &t, int i) { return ((u64)t.w[2 * i + 1] << 32) | (u64)t.w[2 * i]; }
+
 // Kernel-uniform constants travel in the parameter block: FP64 and integer instructions take c[0][..] operands directly,
 // which keeps them out of the 128-register budget (at 128 registers every long-lived scalar counts).
 struct K1QArgs {
@@ -74,25 +107,32 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   const u64 *tv = A.tv + (size_t)(A.tv_count > 1 ? ct % A.tv_count : 0) * 2 * N;
   const int Bg_bit = A.Bg_bit;
 
-  // ---- thread roles ------------------------------------------------------------------------------------------
-  const int slot = tid >> 6, qA = tid & 63;           // pass A / A': row slot and in-block index
-  const int pA = slot & 1, lboA = slot >> 1;          // polynomial and level offset inside a round
-  // pass B / B' run PER WARP on the two blocks pos1 = 2*warp + {0, 1} whose positions the same warp's pass C / C' threads
-  // own, so that B -> C and C' -> B' need a warp barrier only: lane = (row of the batch, block bit, r)
-  const int warp = tid >> 5, lane = tid & 31;
-  const int rowB = lane >> 3, pos1B = 2 * warp + ((lane >> 2) & 1), rB = lane & 3;
-  // pass C / C': lanes 0..15 take the key columns c' = 16*warp + lane of the even position groups, lanes 16..31 of the odd
-  // ones: the 8 lanes of a quarter warp read 8 consecutive 16-byte key words, one 128-byte line per request (with c = tid
-  // a request straddles two lines and the key loads cost twice the L1 wavefronts: profiles/r2a)
-  const int cpC = 16 * warp + (lane & 15), halfC = lane >> 4;
-  const int cC = 2 * cpC + halfC, pos2C = cC & 15;
-  // swizzled offsets (elements): see the header
-  const int qs0 = qA ^ ((qA >> 3) & 7), qs1 = qs0 ^ 4;                // pass A: block pos1 even / odd
-  const int b4B = (pos1B & 1) << 2;                                    // pass B: bit 2 flips in odd blocks
-  const int cbase = 8 * cpC, cxor = (4 * halfC) ^ (cpC & 7) ^ (((cpC >> 3) & 1) << 2);   // pass C: element r at cbase + (r ^ cxor)
-
-  // element 4*e + rB of a block (e < 16), swizzled: bits 0-1 ^= (e >> 1) & 3, bit 2 ^= bit 2 of (e >> 1) and the block bit
-  auto swz_b = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4B) + (rB ^ ((e >> 1) & 3)); };
+  // ---- thread roles.  They are re-derived from the thread index inside the step loop (MB_K1Q_ROLES): as loop invariants
+  // the compiler keeps the dozen derived offsets live across the whole step in registers it does not have, spills them,
+  // and the reloads miss the 28 KB of L1 that is left (3 % of the kernel waiting on local loads, profiles/r2b)
+#define MB_K1Q_ROLES(t_)                                                                                                       \
+  const int slot = (t_) >> 6, qA = (t_) & 63;         /* pass A / A': row slot and in-block index */                           \
+  const int pA = slot & 1, lboA = slot >> 1;          /* polynomial and level offset inside a round */                         \
+  /* pass B / B' run PER WARP on the two blocks pos1 = 2*warp + {0, 1} whose positions the same warp's pass C / C' */        \
+  /* threads own, so that B -> C and C' -> B' need a warp barrier only: lane = (row of the batch, block bit, r) */            \
+  const int warp = (t_) >> 5, lane = (t_) & 31;                                                                                \
+  const int rowB = lane >> 3, pos1B = 2 * warp + ((lane >> 2) & 1), rB = lane & 3;                                             \
+  /* two-row phases: the 16 tasks of a warp are split over lane pairs (lane, lane + 16), see dif16_pair */                     \
+  const int hB = lane >> 4, rowB2 = (lane >> 3) & 1;                                                                           \
+  /* pass C / C': lanes 0..15 take the key columns c' = 16*warp + lane of the even position groups, lanes 16..31 of the */   \
+  /* odd ones: the 8 lanes of a quarter warp read 8 consecutive 16-byte key words, one 128-byte line per request (with */    \
+  /* c = tid a request straddles two lines and the key loads cost twice the L1 wavefronts: profiles/r2a) */                   \
+  const int cpC = 16 * warp + (lane & 15), halfC = lane >> 4;                                                                  \
+  const int cC = 2 * cpC + halfC, pos2C = cC & 15;                                                                             \
+  /* swizzled offsets (elements): see the header */                                                                            \
+  const int qs0 = qA ^ ((qA >> 3) & 7), qs1 = qs0 ^ 4;                /* pass A: block pos1 even / odd */                     \
+  const int b4B = (pos1B & 1) << 2;                                    /* pass B: bit 2 flips in odd blocks */                 \
+  const int cbase = 8 * cpC, cxor = (4 * halfC) ^ (cpC & 7) ^ (((cpC >> 3) & 1) << 2);   /* pass C: element r at cbase + (r ^ cxor) */ \
+  /* element 4*e + rB of a block (e < 16), swizzled: bits 0-1 ^= (e >> 1) & 3, bit 2 ^= bit 2 of (e >> 1) and the block bit */ \
+  auto swz_b = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4B) + (rB ^ ((e >> 1) & 3)); };                                \
+  /* the same for e = 8*hB + j, j < 8 (two-row phases) */                                                                      \
+  auto swz_b2 = [&](int j) { return 32 * hB + ((4 * j) ^ (4 * hB) ^ b4B) + (rB ^ ((j >> 1) & 3)); };                          \
+  (void)lboA; (void)rowB; (void)rowB2; (void)pos2C; (void)qs1; (void)cbase; (void)cxor; (void)swz_b; (void)swz_b2; (void)hB;
 
   // ---- tensor memory: per-thread constants and state ------------------------------------------------------------
   constexpr bool TMEM_ACC = (LOGM == 9);              // N = 2048: two warps share a lane quarter and pass-A threads are not the owners
@@ -120,6 +160,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   // lane field (bits 31:16) = 32 * (warp % 4); warps 4..7 (N = 2048) use the second half of the columns
   const unsigned taddr = tmem_base_s + ((unsigned)((tid >> 5) & 3) << 21) + (unsigned)((tid >> 7) * CPT);
   {
+    MB_K1Q_ROLES(tid)
     // pass-A twiddles w^q * W_M^(q k1), k1 = brev(pos1): A.tab[k1 * 64 + q]
 #pragma unroll
     for (int g4 = 0; g4 < RA / 4; ++g4) {
@@ -154,6 +195,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   }
   __syncthreads();
   if (TMEM_ACC) {                                     // park the accumulator words this thread owns: (j, j + M), j = q + 64 m
+    MB_K1Q_ROLES(tid)
     const u64 *ap0 = acc + pA * N;
 #pragma unroll
     for (int g4 = 0; g4 < RA / 4; ++g4) {
@@ -170,6 +212,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     const int a_i = rot[step];
     if (a_i == 0) continue;                           // bootstrap.c:114
     const double2 *__restrict__ key = A.bsk + (size_t)step * ROWS * 2 * M;
+    int t_ = tid;
+    asm volatile("" : "+r"(t_));                      // opaque copy of the thread index: the roles below are not loop invariants
+    MB_K1Q_ROLES(t_)
 
     double2 fa[2][4];                                 // Fourier accumulators: positions 4c..4c+3 of both outputs
 #pragma unroll
@@ -241,6 +286,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         const int lb = rd * LBO + lboA;
         if (LBO > 1 && lb >= NB) continue;           // warp-uniform (slot is a multiple of two warps)
         const int sh = FUSED ? 64 - (lev0 + lb + 1) * Bg_bit : ((PKALL ? (L - 1 - lev0) : (NB - 1)) - lb) * Bg_bit;
+        TmemLd ta0, ta1;                              // the first 8 twiddles fly under the digit conversion and the butterflies
+        tmem_issue(ta0, taddr + COL_TA);
+        tmem_issue(ta1, taddr + COL_TA + 16);
         double2 x[RA];
 #pragma unroll
         for (int m = 0; m < RA; ++m) {
@@ -258,15 +306,19 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         }
         reg_dif<RA>(x);
         double2 *row = buf + (pA * NB + lb) * M;
+        tmem_wait(ta0);
+        tmem_also(ta1);
 #pragma unroll
-        for (int g4 = 0; g4 < RA / 4; ++g4) {
-          double2 tw[4];
-          tmem_ld4(tw, taddr + COL_TA + 16 * g4);
+        for (int pos = 0; pos < 8; ++pos)
+          row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tmem_c(pos < 4 ? ta0 : ta1, pos & 3));
+        if (RA > 8) {
+          tmem_issue(ta0, taddr + COL_TA + 32);
+          tmem_issue(ta1, taddr + COL_TA + 48);
+          tmem_wait(ta0);
+          tmem_also(ta1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int pos = 4 * g4 + i;
-            row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tw[i]);
-          }
+          for (int pos = 8; pos < RA; ++pos)
+            row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tmem_c(pos < 12 ? ta0 : ta1, pos & 3));
         }
       }
       __syncthreads();
@@ -283,7 +335,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       double2 kv0[4], kv1[4];
       if (KPF) { load_half(kv0, 0, 0); load_half(kv1, 0, 1); }
       // ------------------------------- pass B: radix 16 in place, no twiddle --------------------------------------
-      if (rowB < RB) {
+      if constexpr (RB == 4) {
         double2 *blk = buf + rowB * M + pos1B * 64;
         double2 x[16];
 #pragma unroll
@@ -291,13 +343,46 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         reg_dif<16>(x);
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) blk[swz_b(pos)] = x[pos];
+      } else {
+        // Two rows = 16 radix-16 tasks per warp: each is split over the lane pair (lane, lane + 16) instead of leaving half
+        // the warp idle (idle lanes still occupy the FP64 pipe: +12 % FP64 instructions, profiles/r2b).  Both lanes read
+        // the 16 inputs; lane half h forms the first DIF stage for its half of the outputs branch-free,
+        //   y_i = (x_i + s x_{i+8}) * w_i,   (s, w_i) = (+1, 1) for h = 0 and (-1, W_16^i) for h = 1,
+        // finishes with a radix-8 DIF and writes outputs 8h .. 8h+7 (even / odd frequencies).
+        double2 *blk = buf + rowB2 * M + pos1B * 64;
+        double2 x[16], y[8];
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[swz_b(m2)];
+        const double sg = hB ? -1.0 : 1.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = make_double2(fma(sg, x[i + 8].x, x[i].x), fma(sg, x[i + 8].y, x[i].y));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+          double c, sn;
+          w64_cs(4 * i, c, sn);
+          const double cs = hB ? c : 1.0, ss = hB ? sn : 0.0;
+          y[i] = make_double2(fma(y[i].x, cs, -y[i].y * ss), fma(y[i].x, ss, y[i].y * cs));
+        }
+        reg_dif<8>(y);
+        __syncwarp();                                 // every lane has read its 16 inputs before any output lands on them
+#pragma unroll
+        for (int j = 0; j < 8; ++j) blk[swz_b2(j)] = y[j];
       }
       __syncwarp();                                   // pass C below reads only the blocks this warp just transformed
       // ------------------------------- pass C + MAC ----------------------------------------------------------------
       {
-        if (FA_PARK && lev0 > 0) { tmem_ld4(fa[0], taddr + COL_FA0); tmem_ld4(fa[1], taddr + COL_FA1); }
+        TmemLd tc, f0, f1;
+        tmem_issue(tc, taddr + COL_TC);
+        if (FA_PARK && lev0 > 0) { tmem_issue(f0, taddr + COL_FA0); tmem_issue(f1, taddr + COL_FA1); }
+        tmem_wait(tc);
+        if (FA_PARK && lev0 > 0) {
+          tmem_also(f0); tmem_also(f1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { fa[0][i] = tmem_c(f0, i); fa[1][i] = tmem_c(f1, i); }
+        }
         double2 twc[4];
-        tmem_ld4(twc, taddr + COL_TC);
+#pragma unroll
+        for (int r = 1; r < 4; ++r) twc[r] = tmem_c(tc, r);
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
           if (!KPF) { load_half(kv0, rb, 0); load_half(kv1, rb, 1); }
@@ -346,14 +431,27 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     }
     __syncwarp();
     // ---------------------------------- B' (per warp, own blocks) -----------------------------------------------------
-    if (rowB < 2) {
-      double2 *blk = buf + rowB * M + pos1B * 64;
-      double2 x[16];
+    {
+      // the mirror image of the split above: lane half h inverts the even (h = 0) / odd (h = 1) frequencies with a radix-8
+      // DIT, the odd half applies conj(W_16^j), the lane pair swaps its 8 values and lane h forms outputs j + 8h = E_j +- O_j
+      double2 *blk = buf + rowB2 * M + pos1B * 64;
+      double2 y[8];
 #pragma unroll
-      for (int pos = 0; pos < 16; ++pos) x[pos] = blk[swz_b(pos)];
-      reg_dit_inv<16>(x);
+      for (int j = 0; j < 8; ++j) y[j] = blk[swz_b2(j)];
+      reg_dit_inv<8>(y);
 #pragma unroll
-      for (int m2 = 0; m2 < 16; ++m2) blk[swz_b(m2)] = x[m2];
+      for (int j = 1; j < 8; ++j) {
+        double c, sn;
+        w64_cs(4 * j, c, sn);
+        const double cs = hB ? c : 1.0, ss = hB ? -sn : 0.0;        // conj(W_16^j)
+        y[j] = make_double2(fma(y[j].x, cs, -y[j].y * ss), fma(y[j].x, ss, y[j].y * cs));
+      }
+      const double sg = hB ? -1.0 : 1.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double rx = __shfl_xor_sync(0xffffffffu, y[j].x, 16), ry = __shfl_xor_sync(0xffffffffu, y[j].y, 16);
+        blk[swz_b2(j)] = make_double2(fma(sg, y[j].x, rx), fma(sg, y[j].y, ry));   // h = 0: E + O at j; h = 1: E - O at j + 8
+      }
     }
     __syncthreads();
     // ---------------------------------- A' + accumulate ----------------------------------------------------------------
@@ -361,14 +459,16 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       const double2 *row = buf + pA * M;
       double2 x[RA];
 #pragma unroll
-      for (int g4 = 0; g4 < RA / 4; ++g4) {
-        double2 tw[4];
-        tmem_ld4(tw, taddr + COL_TA + 16 * g4);
+      for (int g8 = 0; g8 < RA / 8; ++g8) {
+        TmemLd ta0, ta1;
+        tmem_issue(ta0, taddr + COL_TA + 32 * g8);
+        tmem_issue(ta1, taddr + COL_TA + 32 * g8 + 16);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pos = 4 * g4 + i;
-          x[pos] = cmul_conj(row[pos * 64 + ((pos & 1) ? qs1 : qs0)], tw[i]);
-        }
+        for (int i = 0; i < 8; ++i) x[8 * g8 + i] = row[(8 * g8 + i) * 64 + ((i & 1) ? qs1 : qs0)];
+        tmem_wait(ta0);
+        tmem_also(ta1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[8 * g8 + i] = cmul_conj(x[8 * g8 + i], tmem_c(i < 4 ? ta0 : ta1, i & 3));
       }
       reg_dit_inv<RA>(x);
       u64 *ap = acc + pA * N;

@@ -104,6 +104,7 @@ struct BlindRotateLaunch {
 void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st);
 void launch_unfold(u64 *out, const u64 *su, const u64 *a, int a_stride, int N, int npoly, int unfolding, int group0,
                    int n_groups, int count, cudaStream_t st);
+void launch_pb_preprocess(u64 *out, const u64 *in, size_t words, int kappa, int theta, int log_N2, cudaStream_t st);
 void launch_fill_sel(int *sel, int E, int size, int bit, int count, cudaStream_t st);
 void launch_rotate_trlwe(u64 *out, const u64 *in, int amount, int N, int polys, int count, cudaStream_t st);
 void launch_pos_to_host_order(double *out, const double *in, int N, size_t npolys, const int *perm, const int *conj,

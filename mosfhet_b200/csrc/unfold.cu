@@ -78,4 +78,16 @@ void launch_rotate_trlwe(u64 *out, const u64 *in, int amount, int N, int polys, 
   count_launch();
 }
 
+// programmable_bootstrap's input shaping (bootstrap.c:210-217) on a batch of TLWE words
+__global__ void pb_preprocess_kernel(u64 *out, const u64 *in, size_t words, int kappa, int theta, int log_N2) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < words; g += (size_t)gridDim.x * blockDim.x)
+    out[g] = pb_preprocess(in[g], kappa, theta, log_N2);
+}
+void launch_pb_preprocess(u64 *out, const u64 *in, size_t words, int kappa, int theta, int log_N2, cudaStream_t st) {
+  if (words == 0) return;
+  pb_preprocess_kernel<<<sm_count() * 4, 256, 0, st>>>(out, in, words, kappa, theta, log_N2);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
 }  // namespace mb

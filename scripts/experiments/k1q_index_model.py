@@ -151,3 +151,37 @@ for N in (512, 1024, 2048):
     assert np.abs(back - a).max() < 1e-9, N
     check_conflicts(M)
     print(f"N={N}: forward positions, inverse round trip and bank-conflict freedom OK")
+
+
+# ---- the lane-pair split of a radix-16 task (two-row phases of blind_rotate_k1q.cu) ---------------------------------------
+def dif16_pair(x):
+    out = np.zeros(16, complex)
+    for h in (0, 1):
+        sg = -1.0 if h else 1.0
+        y = np.array([x[i] + sg * x[i + 8] for i in range(8)])
+        if h:
+            y = y * np.exp(2j * np.pi * np.arange(8) / 16)
+        out[8 * h: 8 * h + 8] = dif(y)
+    return out
+
+
+def dit16_pair(xp):
+    halves = []
+    for h in (0, 1):
+        y = dit_inv(xp[8 * h: 8 * h + 8])
+        if h:
+            y = y * np.exp(-2j * np.pi * np.arange(8) / 16)
+        halves.append(y)
+    out = np.zeros(16, complex)
+    for h in (0, 1):
+        sg = -1.0 if h else 1.0
+        mine, recv = halves[h], halves[1 - h]
+        out[8 * h: 8 * h + 8] = recv + sg * mine if h else mine + recv
+    return out
+
+
+rng = np.random.default_rng(5)
+v = rng.normal(size=16) + 1j * rng.normal(size=16)
+assert np.abs(dif16_pair(v) - dif(v)).max() < 1e-12
+assert np.abs(dit16_pair(v) - dit_inv(v)).max() < 1e-12
+print("lane-pair split of the radix-16 task OK")
