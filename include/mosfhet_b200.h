@@ -103,9 +103,24 @@ void blind_rotate_unfolded(TRLWE tv, Torus *a, TRGSW *s, int size, int unfolding
 void multivalue_bootstrap_UBR_phase1(TRGSW_DFT *out, TLWE in, Bootstrap_Key key);                         /* mosfhet.h:431, bootstrap.c:151 */
 void multivalue_bootstrap_UBR_phase2(TLWE out, TRLWE tv, TLWE in, TRGSW_DFT *sa, Bootstrap_Key key,
                                      int torus_base);                                                     /* mosfhet.h:432, bootstrap.c:174 */
+/* extraction family of the multi-ciphertext caller (applications/multi-ciphertext-arith/src/integer.c:94-100): integer, bit-exact */
+void trlwe_extract_tlwe_addto(TLWE out, TRLWE in, int idx);                                               /* mosfhet.h:297, trlwe.c:554 */
+void trlwe_extract_tlwe_subto(TLWE out, TRLWE in, int idx);                                               /* mosfhet.h:298, trlwe.c:567 */
+void trlwe_mv_extract_tlwe(TLWE *out, TRLWE in, int amount);                                              /* mosfhet.h:279, trlwe.c:580 */
+void trlwe_mv_extract_tlwe_scaling(TLWE out, TRLWE in, int scale);                                        /* mosfhet.h:280, trlwe.c:591 */
+void trlwe_mv_extract_tlwe_scaling_addto(TLWE out, TRLWE in, int scale);                                  /* mosfhet.h:281, trlwe.c:602 */
+void trlwe_mv_extract_tlwe_scaling_subto(TLWE out, TRLWE in, int scale);                                  /* mosfhet.h:282, trlwe.c:612 */
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base);             /* mosfhet.h:413, bootstrap.c:232 */
 void multivalue_bootstrap_phase2(TLWE out, int *in, TRLWE *rotated_tv, int torus_base,
                                  int log_torus_base);                                                 /* mosfhet.h:414, bootstrap.c:245 */
+
+/* The reference's key destructors, interposed: they drop the resident copy of the key (malloc hands freed addresses to
+ * the next key) and then run the reference's own definition, found with dlsym(RTLD_NEXT).  Resident copies are also
+ * guarded by a fingerprint of the host tree, so a key regenerated in place is uploaded again. */
+void free_bootstrap_key(Bootstrap_Key key);                                                           /* mosfhet.h:417, bootstrap.c:51 */
+void free_tlwe_ks_key(TLWE_KS_Key key);                                                               /* mosfhet.h:231, tlwe.c:232 */
+void free_trlwe_generic_ks_key(Generic_KS_Key key);                                                   /* mosfhet.h:388, keyswitch.c:393 */
+void free_trlwe_ks_key(TRLWE_KS_Key key);                                                             /* mosfhet.h:376, keyswitch.c:109 */
 
 /* ------------------------------------------------------------------------------------------
  * (2) Batched variants over arrays of handles (new).  `count` independent ciphertexts per call.
@@ -131,6 +146,18 @@ void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count);
 void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in,
                                           Bootstrap_Key key, TLWE_KS_Key ks_key,
                                           int torus_base, int count);
+/* The extraction family over arrays: out[i] (op)= f(in[i]).  `mode`: 0 = plain (out is overwritten; scaling only),
+ * +1 = addto, -1 = subto.  trlwe_mv_extract_tlwe_batch: out[i] points to `amount` TLWEs. */
+void trlwe_extract_tlwe_acc_batch(TLWE *out, TRLWE *in, const int *idx, int idx_count /* 1 or count */, int mode, int count);
+void trlwe_mv_extract_tlwe_batch(TLWE **out, TRLWE *in, int amount, int count);
+void trlwe_mv_extract_tlwe_scaling_batch(TLWE *out, TRLWE *in, int scale, int mode, int count);
+/* One digit step of the multi-ciphertext arithmetic (integer.c:94-100) for `count` independent digits, nothing but the
+ * digits crossing PCIe:   tmp = tlwe_keyswitch(digit[i]);  acc = functional_bootstrap_wo_extract(tv, tmp, torus_base);
+ *   digit[i] -= trlwe_mv_extract_tlwe_scaling(acc, scale_digit)        (trlwe_mv_extract_tlwe_scaling_subto)
+ *   carry[i] += trlwe_mv_extract_tlwe_scaling(acc, scale_carry)        (trlwe_mv_extract_tlwe_scaling_addto; carry may be NULL)
+ * digit[i] and carry[i] have dimension k*N; the constant adjustments of b (integer.c:97, 99) stay with the caller. */
+void tlwe_keyswitch_bootstrap_mv_extract_batch(TLWE *digit, TLWE *carry, TRLWE *tv, int tv_count, TLWE_KS_Key ks_key,
+                                               Bootstrap_Key key, int torus_base, int scale_digit, int scale_carry, int count);
 void multivalue_bootstrap_CLOT21_batch(TLWE **out, TRLWE *tv, int tv_count, TLWE *in,
                                        Bootstrap_Key key, int torus_base, int n_luts, int count);
 /* out[c] points to torus_base+1 TRLWEs; lut[c] (lut_count == count) or lut[0] (lut_count == 1) holds

@@ -75,6 +75,21 @@ PROTOTYPES = {
     "trlwe_from_DFT_batch": (None, [_P(abi.TRLWE), _P(abi.TRLWE_DFT), C.c_int]),
     "trlwe_extract_tlwe_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), _P(C.c_int), C.c_int, C.c_int]),
     "tlwe_keyswitch_batch": (None, [_P(abi.TLWE), _P(abi.TLWE), abi.TLWE_KS_Key, C.c_int]),
+    "trlwe_extract_tlwe_addto": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
+    "trlwe_extract_tlwe_subto": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
+    "trlwe_mv_extract_tlwe": (None, [_P(abi.TLWE), abi.TRLWE, C.c_int]),
+    "trlwe_mv_extract_tlwe_scaling": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
+    "trlwe_mv_extract_tlwe_scaling_addto": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
+    "trlwe_mv_extract_tlwe_scaling_subto": (None, [abi.TLWE, abi.TRLWE, C.c_int]),
+    "trlwe_extract_tlwe_acc_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), _P(C.c_int), C.c_int, C.c_int, C.c_int]),
+    "trlwe_mv_extract_tlwe_batch": (None, [_P(_P(abi.TLWE)), _P(abi.TRLWE), C.c_int, C.c_int]),
+    "trlwe_mv_extract_tlwe_scaling_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, C.c_int, C.c_int]),
+    "tlwe_keyswitch_bootstrap_mv_extract_batch": (None, [_P(abi.TLWE), _P(abi.TLWE), _P(abi.TRLWE), C.c_int, abi.TLWE_KS_Key,
+                                                         abi.Bootstrap_Key, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "free_bootstrap_key": (None, [abi.Bootstrap_Key]),
+    "free_tlwe_ks_key": (None, [abi.TLWE_KS_Key]),
+    "free_trlwe_generic_ks_key": (None, [C.c_void_p]),
+    "free_trlwe_ks_key": (None, [C.c_void_p]),
     "functional_bootstrap_keyswitch_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, abi.TLWE_KS_Key, C.c_int, C.c_int]),
     "multivalue_bootstrap_CLOT21_batch": (None, [_P(_P(abi.TLWE)), _P(abi.TRLWE), C.c_int, _P(abi.TLWE), abi.Bootstrap_Key, C.c_int, C.c_int, C.c_int]),
     # runtime / keys

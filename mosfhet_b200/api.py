@@ -341,6 +341,51 @@ def trlwe_extract_tlwe_batch(out, in_, idx) -> None:
                                    idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx), len(in_))
 
 
+# extraction family of the multi-ciphertext caller (trlwe.c:554-620, integer.c:94-100)
+def trlwe_extract_tlwe_addto(out, in_, idx: int) -> None:
+    lib().trlwe_extract_tlwe_addto(_h(out), _h(in_), idx)
+
+
+def trlwe_extract_tlwe_subto(out, in_, idx: int) -> None:
+    lib().trlwe_extract_tlwe_subto(_h(out), _h(in_), idx)
+
+
+def trlwe_mv_extract_tlwe(outs, in_, amount: int) -> None:
+    lib().trlwe_mv_extract_tlwe(abi.handle_array(outs, abi.TLWE), _h(in_), amount)
+
+
+def trlwe_mv_extract_tlwe_scaling(out, in_, scale: int, mode: int = 0) -> None:
+    """mode 0: trlwe_mv_extract_tlwe_scaling, +1: _scaling_addto, -1: _scaling_subto."""
+    fn = {0: "trlwe_mv_extract_tlwe_scaling", 1: "trlwe_mv_extract_tlwe_scaling_addto", -1: "trlwe_mv_extract_tlwe_scaling_subto"}[mode]
+    getattr(lib(), fn)(_h(out), _h(in_), scale)
+
+
+def trlwe_extract_tlwe_acc_batch(outs, ins, idx, mode: int) -> None:
+    idx = np.ascontiguousarray(np.atleast_1d(idx), np.int32)
+    lib().trlwe_extract_tlwe_acc_batch(abi.handle_array(outs, abi.TLWE), abi.handle_array(ins, abi.TRLWE),
+                                       idx.ctypes.data_as(C.POINTER(C.c_int)), len(idx), mode, len(ins))
+
+
+def trlwe_mv_extract_tlwe_scaling_batch(outs, ins, scale: int, mode: int = 0) -> None:
+    lib().trlwe_mv_extract_tlwe_scaling_batch(abi.handle_array(outs, abi.TLWE), abi.handle_array(ins, abi.TRLWE), scale, mode, len(ins))
+
+
+def trlwe_mv_extract_tlwe_batch(out_lists, ins, amount: int) -> None:
+    arrs = [abi.handle_array(o, abi.TLWE) for o in out_lists]
+    ptrs = (C.POINTER(abi.TLWE) * len(arrs))(*[C.cast(a, C.POINTER(abi.TLWE)) for a in arrs])
+    lib().trlwe_mv_extract_tlwe_batch(ptrs, abi.handle_array(ins, abi.TRLWE), amount, len(ins))
+
+
+def tlwe_keyswitch_bootstrap_mv_extract_batch(digits, carries, tv, ks_key, key, torus_base: int, scale_digit: int,
+                                              scale_carry: int = 1) -> None:
+    """One digit step of integer.c:94-100 for a batch: digits[i] -= mv_scaling(PBS(KS(digits[i])), scale_digit) and
+    (carries given) carries[i] += mv_scaling(.., scale_carry)."""
+    tva, tvc = _tvs(tv)
+    lib().tlwe_keyswitch_bootstrap_mv_extract_batch(abi.handle_array(digits, abi.TLWE),
+                                                    abi.handle_array(carries, abi.TLWE) if carries is not None else None,
+                                                    tva, tvc, _h(ks_key), _h(key), torus_base, scale_digit, scale_carry, len(digits))
+
+
 # ---------------------------------------------------------------------------------------------
 # (3) flat calls: resident keys, host-buffer and device-resident batches
 # ---------------------------------------------------------------------------------------------

@@ -34,8 +34,8 @@ namespace {
 std::mutex g_mu;
 int g_host_layout = MB200_FFT_AUTO;
 int g_policy = 0;
-#ifndef MB200_K1Q_DEFAULT
-#define MB200_K1Q_DEFAULT false     // full batches: T = M/4 throughput kernel instead of the T = M/8 one
+#ifndef MB200_K1Q_N2048
+#define MB200_K1Q_N2048 false       // full batches at N = 2048: the T = M/4 kernel instead of the T = M/8 one
 #endif
 // name of the blind-rotation kernel this host thread dispatched last (entry points may be called from several threads)
 thread_local char t_last_kernel[96] = "none";
@@ -505,7 +505,8 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
     if (g_policy == 0) {
       const bool want_c = env_flag("MB200_K1C", 2 * a.count <= sms && p.N > 1024);
       const bool want_h = env_flag("MB200_K1H", a.count <= 2 * sms && p.N <= 1024);
-      const bool want_q = env_flag("MB200_K1Q", MB200_K1Q_DEFAULT);
+      // measured (profiles/r2c_k1q_timing.log, 4096 ciphertexts): N = 1024 k1q 40.6 ms vs k1 42.9 ms; N = 2048 see MB200_K1Q_N2048
+      const bool want_q = env_flag("MB200_K1Q", p.N == 1024 || MB200_K1Q_N2048);
       if (want_c && mb::k1c_supported(p)) pick = K1C;
       else if (want_h && mb::k1h_supported(p)) pick = K1H;
       else if (want_q && mb::k1q_supported(p)) pick = K1Q;
@@ -1338,6 +1339,125 @@ void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLW
   scatter_tlwe(out, h_out, count, k * N);
 }
 
+// ---- extraction family (trlwe.c:554-620): signed sums of extractions over two index ranges (multivalue.cu) ----------------
+// ranges for trlwe_mv_extract_tlwe_scaling (mode 0) and _scaling_addto / _subto (mode +-1)
+static void scaling_ranges(int N, int scale, int mode, int r[4]) {
+  const int amount = scale, half = amount / 2;
+  if (mode == 0) { r[0] = 0; r[1] = half; r[2] = N - (amount - half); r[3] = N - 2; }          // trlwe.c:593-599
+  else { r[0] = 0; r[1] = half - 1; r[2] = N - (amount - half); r[3] = N - 1; }               // trlwe.c:604-609, 614-619
+}
+static void mv_extract_dev(u64 *d_out, int out_stride, const u64 *d_in, const int *h_ranges, int outs_per_in, int N, int k,
+                           int sign, int acc, int count, cudaStream_t st) {
+  int *d_r = (int *)t_scratch[S_MISC2].dev(sizeof(int) * 4 * outs_per_in);
+  MB_CHECK(cudaMemcpyAsync(d_r, h_ranges, sizeof(int) * 4 * outs_per_in, cudaMemcpyHostToDevice, st));
+  mb::launch_mv_extract(d_out, out_stride, d_in, d_r, outs_per_in, N, k, sign, acc, count, st);
+}
+// out[i] (op)= f(in[i]) with one range quadruple for the whole batch (or one per element when `per_elem`)
+static void extract_family_batch(TLWE *out, TRLWE *in, const std::vector<int> &ranges, bool per_elem, int sign, int acc, int count) {
+  if (count <= 0) return;
+  const int k = in[0]->k, N = in[0]->b->N, W = k * N + 1;
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (k + 1) * N, out_b = sizeof(u64) * (size_t)count * W;
+  u64 *h_in = (u64 *)t_scratch[S_TV].host(in_b), *d_in = (u64 *)t_scratch[S_TV].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_trlwe(h_in, in, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  if (acc) {
+    gather_tlwe(h_out, out, count, k * N);
+    MB_CHECK(cudaMemcpyAsync(d_out, h_out, out_b, cudaMemcpyHostToDevice, st));
+  }
+  if (!per_elem) {
+    mv_extract_dev(d_out, W, d_in, ranges.data(), 1, N, k, sign, acc, count, st);
+  } else {                                           // one launch per element keeps the kernel's range table uniform
+    for (int i = 0; i < count; ++i)
+      mv_extract_dev(d_out + (size_t)i * W, W, d_in + (size_t)i * (k + 1) * N, &ranges[4 * i], 1, N, k, sign, acc, 1, st);
+  }
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(out, h_out, count, k * N);
+}
+void trlwe_extract_tlwe_acc_batch(TLWE *out, TRLWE *in, const int *idx, int idx_count, int mode, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(mode == 1 || mode == -1, "trlwe_extract_tlwe_acc_batch: mode must be +1 (addto) or -1 (subto)");
+  MB_REQUIRE(idx_count == 1 || idx_count == count, "trlwe_extract_tlwe_acc_batch: idx_count must be 1 or count");
+  const int N = in[0]->b->N;
+  std::vector<int> r((size_t)4 * idx_count);
+  for (int i = 0; i < idx_count; ++i) {
+    MB_REQUIRE(idx[i] >= 0 && idx[i] < N, "extract index %d out of range", idx[i]);
+    r[4 * i] = idx[i]; r[4 * i + 1] = idx[i]; r[4 * i + 2] = 1; r[4 * i + 3] = 0;
+  }
+  extract_family_batch(out, in, r, idx_count > 1, mode, 1, count);
+}
+void trlwe_mv_extract_tlwe_scaling_batch(TLWE *out, TRLWE *in, int scale, int mode, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(mode >= -1 && mode <= 1 && scale >= 1 && scale <= in[0]->b->N, "trlwe_mv_extract_tlwe_scaling: bad mode / scale");
+  std::vector<int> r(4);
+  scaling_ranges(in[0]->b->N, scale, mode, r.data());
+  extract_family_batch(out, in, r, false, mode < 0 ? -1 : 1, mode != 0, count);
+}
+void trlwe_mv_extract_tlwe_batch(TLWE **out, TRLWE *in, int amount, int count) {
+  if (count <= 0 || amount <= 0) return;
+  const int k = in[0]->k, N = in[0]->b->N, W = k * N + 1;
+  MB_REQUIRE(amount <= N, "trlwe_mv_extract_tlwe: amount %d exceeds N", amount);
+  std::vector<int> r((size_t)4 * amount);
+  for (int i = 0; i < amount; ++i) {                 // trlwe.c:582-588: +extract(i) below amount/2, -extract(N-1-(i-amount/2)) above
+    const bool neg = i >= amount / 2;
+    const int idx = neg ? N - 1 - (i - amount / 2) : i;
+    r[4 * i] = neg ? 1 : idx; r[4 * i + 1] = neg ? 0 : idx; r[4 * i + 2] = neg ? idx : 1; r[4 * i + 3] = neg ? idx : 0;
+  }
+  cudaStream_t st = mb::default_stream();
+  const size_t in_b = sizeof(u64) * (size_t)count * (k + 1) * N, out_b = sizeof(u64) * (size_t)count * amount * W;
+  u64 *h_in = (u64 *)t_scratch[S_TV].host(in_b), *d_in = (u64 *)t_scratch[S_TV].dev(in_b);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
+  gather_trlwe(h_in, in, count, k, N);
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  mv_extract_dev(d_out, W, d_in, r.data(), amount, N, k, +1, 0, count, st);
+  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  for (int c = 0; c < count; ++c) scatter_tlwe(out[c], h_out + (size_t)c * amount * W, amount, k * N);
+}
+
+/* integer.c:94-100 for `count` digits: key switch -> bootstrap without extraction -> the two scaled extractions */
+void tlwe_keyswitch_bootstrap_mv_extract_batch(TLWE *digit, TLWE *carry, TRLWE *tv, int tv_count, TLWE_KS_Key ks_key,
+                                               Bootstrap_Key key, int torus_base, int scale_digit, int scale_carry, int count) {
+  if (count <= 0) return;
+  MB_REQUIRE(tv_count == 1 || tv_count == count, "tv_count must be 1 or count");
+  const AnyBsk bk = lookup_any_bsk(key);
+  const mb::Params &p = bk.p();
+  mb200_ksk *ksk = lookup_ksk(ks_key, p.k * p.N);
+  MB_REQUIRE(ksk->p.k * ksk->p.N == p.k * p.N && ksk->p.n == p.n, "key switch (%d -> %d) does not feed the bootstrap (%d -> %d)",
+             ksk->p.k * ksk->p.N, ksk->p.n, p.n, p.k * p.N);
+  MB_REQUIRE(scale_digit >= 1 && scale_digit <= p.N && (!carry || (scale_carry >= 1 && scale_carry <= p.N)), "bad extraction scale");
+  cudaStream_t st = mb::default_stream();
+  const int nd = p.k * p.N, W = nd + 1;
+  const size_t dig_b = sizeof(u64) * (size_t)count * W, tv_b = sizeof(u64) * (size_t)tv_count * (p.k + 1) * p.N;
+  u64 *h_dig = (u64 *)t_scratch[S_MID].host(dig_b * (carry ? 2 : 1)), *d_dig = (u64 *)t_scratch[S_MID].dev(dig_b * (carry ? 2 : 1));
+  u64 *h_car = carry ? h_dig + (size_t)count * W : nullptr, *d_car = carry ? d_dig + (size_t)count * W : nullptr;
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  u64 *d_small = (u64 *)t_scratch[S_IN].dev(sizeof(u64) * (size_t)count * (p.n + 1));
+  u64 *d_acc = (u64 *)t_scratch[S_OUT].dev(sizeof(u64) * (size_t)count * (p.k + 1) * p.N);
+  gather_tlwe(h_dig, digit, count, nd);
+  if (carry) gather_tlwe(h_car, carry, count, nd);
+  gather_trlwe(h_tv, tv, tv_count, p.k, p.N);
+  MB_CHECK(cudaMemcpyAsync(d_dig, h_dig, dig_b * (carry ? 2 : 1), cudaMemcpyHostToDevice, st));
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  mb::launch_keyswitch(ksk, d_small, d_dig, count, st);                                              // integer.c:94
+  pbs_any(bk, d_acc, 0, d_tv, tv_count, d_small, torus_base, count, st);                            // :95
+  int r[4];
+  scaling_ranges(p.N, scale_digit, -1, r);
+  mv_extract_dev(d_dig, W, d_acc, r, 1, p.N, p.k, -1, 1, count, st);                                // :96 subto
+  if (carry) {
+    int *d_r2 = (int *)t_scratch[S_MISC].dev(sizeof(int) * 4);
+    scaling_ranges(p.N, scale_carry, +1, r);
+    MB_CHECK(cudaMemcpyAsync(d_r2, r, sizeof(int) * 4, cudaMemcpyHostToDevice, st));
+    mb::launch_mv_extract(d_car, W, d_acc, d_r2, 1, p.N, p.k, +1, 1, count, st);                    // :100 addto
+  }
+  MB_CHECK(cudaMemcpyAsync(h_dig, d_dig, dig_b * (carry ? 2 : 1), cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaStreamSynchronize(st));
+  scatter_tlwe(digit, h_dig, count, nd);
+  if (carry) scatter_tlwe(carry, h_car, count, nd);
+}
+
 static void trlwe_table_ks_batch(TRLWE *out, TLWE *in, Generic_KS_Key ks_key, int count, int mode) {
   if (count <= 0) return;
   GkskDev *g = lookup_gksk(ks_key);
@@ -1808,6 +1928,12 @@ void mb200_release_generic_ks_key(Generic_KS_Key key) {
   delete it->second;
   g_gksk_cache.erase(it);
 }
+void trlwe_extract_tlwe_addto(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_acc_batch(&out, &in, &idx, 1, +1, 1); }
+void trlwe_extract_tlwe_subto(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_acc_batch(&out, &in, &idx, 1, -1, 1); }
+void trlwe_mv_extract_tlwe(TLWE *out, TRLWE in, int amount) { trlwe_mv_extract_tlwe_batch(&out, &in, amount, 1); }
+void trlwe_mv_extract_tlwe_scaling(TLWE out, TRLWE in, int scale) { trlwe_mv_extract_tlwe_scaling_batch(&out, &in, scale, 0, 1); }
+void trlwe_mv_extract_tlwe_scaling_addto(TLWE out, TRLWE in, int scale) { trlwe_mv_extract_tlwe_scaling_batch(&out, &in, scale, +1, 1); }
+void trlwe_mv_extract_tlwe_scaling_subto(TLWE out, TRLWE in, int scale) { trlwe_mv_extract_tlwe_scaling_batch(&out, &in, scale, -1, 1); }
 void multivalue_bootstrap_phase1(TRLWE *out, TLWE in, Bootstrap_Key key, int torus_base) {
   multivalue_bootstrap_phase1_batch(&out, &in, key, torus_base, 1);
 }

@@ -239,6 +239,12 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     // digit is taken straight from the coefficient; otherwise the top lev_end*Bg_bit bits of every coefficient are packed
     // into one 32-bit word and serve the levels of the batch (PKALL: of the whole step)
     constexpr bool FUSED = !PKALL && (LBO >= LB);
+    // FUSED with exactly two batches (N = 2048, l = 4): the first batch also takes the digit of the thread's level in the
+    // SECOND batch from the same coefficient and parks the 16 digit pairs (one word per coefficient pair) in tensor memory;
+    // the second batch then needs no accumulator reads and no 64-bit arithmetic at all (they were a third of the kernel,
+    // profiles/r2c_level2: pass A at 34 % FP64 instructions)
+    constexpr bool DIG_PARK = FUSED && LOGM == 10 && L == 2 * LB && LBO == LB;
+    constexpr int COL_DG = 112;
     unsigned pk0[FUSED ? 1 : RA], pk1[FUSED ? 1 : RA];
     auto pack_digits = [&](int lev_end) {
       const int pk_shift = 64 - lev_end * Bg_bit;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       // ------------------------------- pass A -----------------------------------------------------------------
       // FUSED: every batch re-reads the coefficients; hide the common subexpressions (32 shared-memory addresses) from the
       // compiler, which otherwise keeps them across the batch in registers it does not have and spills them
-      if (FUSED) asm volatile("" : "+r"(base));
+      if (FUSED && !DIG_PARK) asm volatile("" : "+r"(base));
       if (!PKALL && !FUSED) pack_digits(lev0 + NB);
       if (PK_PARK && lev0 > 0) {
 #pragma unroll
@@ -290,19 +296,31 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         tmem_issue(ta0, taddr + COL_TA);
         tmem_issue(ta1, taddr + COL_TA + 16);
         double2 x[RA];
+        unsigned dg[16];
+        if constexpr (DIG_PARK) { if (lev0 > 0) tmem_ld_u32x16(dg, taddr + COL_DG); }
 #pragma unroll
         for (int m = 0; m < RA; ++m) {
           unsigned u0, u1;
-          if (FUSED) {
+          if (DIG_PARK && lev0 > 0) {
+            u0 = dg[m & 15] & Q.dmask; u1 = (dg[m & 15] >> 16) & Q.dmask;
+          } else if (FUSED) {
             u64 v0, v1;
             coef_pair(m, v0, v1);
             u0 = (unsigned)(v0 >> sh) & Q.dmask; u1 = (unsigned)(v1 >> sh) & Q.dmask;
+            if (DIG_PARK) {                           // the digits of level LB + lb, used by this thread in the second batch
+              const int sh1 = sh - LB * Bg_bit;
+              dg[m & 15] = ((unsigned)(v0 >> sh1) & Q.dmask) | (((unsigned)(v1 >> sh1) & Q.dmask) << 16);
+            }
           } else {
             u0 = (pk0[m] >> sh) & Q.dmask; u1 = (pk1[m] >> sh) & Q.dmask;
           }
           const double d0 = __hiloint2double(0x43300000, (int)u0) - Q.dbias;
           const double d1 = __hiloint2double(0x43300000, (int)u1) - Q.dbias;
           x[m] = mul_w64(make_double2(d0, d1), WQ * m, false);         // fold z = d0 + i d1, constant part of the twist
+        }
+        if constexpr (DIG_PARK) if (lev0 == 0) {
+          tmem_st_u32x16(taddr + COL_DG, dg);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         reg_dif<RA>(x);
         double2 *row = buf + (pA * NB + lb) * M;

@@ -139,6 +139,9 @@ void launch_mv_phase1_rotations(u64 *out, const u64 *src, int N, int k, int toru
 void launch_mv_phase2(u64 *out, const int *d_lut, int lut_count, const u64 *rot, int N, int k, int torus_base,
                       int log_torus_base, int count, cudaStream_t st);
 
+void launch_mv_extract(u64 *out, int out_stride, const u64 *in, const int *d_ranges, int outs_per_in, int N, int k, int sign,
+                       int acc, int count, cudaStream_t st);
+
 // keys.cu
 void import_bsk(BskDev *dst, const double *d_host_layout /* device copy of the host-form key */, const int32_t *h_exponents,
                 cudaStream_t st);

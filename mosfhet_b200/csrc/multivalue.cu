@@ -74,6 +74,46 @@ __global__ void mv_phase2_kernel(u64 *out, const int *lut, int lut_count, const 
   }
 }
 
+// ---- the extraction family of the multi-ciphertext caller (trlwe.c:554-620, integer.c:94-100) --------------------------------
+// Every member is a signed sum of sample extractions over two index ranges,
+//     out = [acc ? out : 0] + sign * ( sum_{idx in [p_lo, p_hi]} extract(in, idx) - sum_{idx in [q_lo, q_hi]} extract(in, idx) ),
+// with extract = trlwe_extract_tlwe (trlwe.c:540-552).  Pure u64 wrap-around arithmetic: bit-exact with the reference.
+//   trlwe_extract_tlwe_addto / _subto (idx)        P = [idx, idx], Q empty, sign = +1 / -1, acc
+//   trlwe_mv_extract_tlwe_scaling (s)              P = [0, s/2], Q = [N - (s - 1 - s/2), N - 1], no acc
+//   trlwe_mv_extract_tlwe_scaling_addto / _subto   P = [0, s/2 - 1], Q = [N - (s - s/2), N - 1], sign = +1 / -1, acc
+//   trlwe_mv_extract_tlwe (amount), output i       P = [i, i] (i < amount/2) or Q = [N-1-(i-amount/2)] (above), no acc
+// `outs_per_in` > 1 (trlwe_mv_extract_tlwe): output o of input ct uses the o-th range quadruple of `ranges`.
+struct MvExtractArgs {
+  u64 *out;            // [count * outs_per_in][out_stride]
+  const u64 *in;       // [count][(k+1)*N]
+  const int *ranges;   // device [outs_per_in][4] = p_lo, p_hi, q_lo, q_hi (empty range: lo > hi)
+  int N, k, out_stride, outs_per_in, sign, acc;
+};
+__global__ void mv_extract_kernel(MvExtractArgs A) {
+  const int v = blockIdx.x, ct = v / A.outs_per_in, oi = v - ct * A.outs_per_in;
+  const int N = A.N, k = A.k;
+  const u64 *tr = A.in + (size_t)ct * (k + 1) * N;
+  u64 *o = A.out + (size_t)v * A.out_stride;
+  const int p_lo = A.ranges[4 * oi], p_hi = A.ranges[4 * oi + 1], q_lo = A.ranges[4 * oi + 2], q_hi = A.ranges[4 * oi + 3];
+  for (int c = threadIdx.x; c <= k * N; c += blockDim.x) {
+    u64 sum = 0;
+    for (int idx = p_lo; idx <= p_hi; ++idx) sum += extract_word(tr, c, idx, N, k);
+    for (int idx = q_lo; idx <= q_hi; ++idx) sum -= extract_word(tr, c, idx, N, k);
+    const u64 base = A.acc ? o[c] : 0ull;
+    o[c] = A.sign > 0 ? base + sum : base - sum;
+  }
+}
+void launch_mv_extract(u64 *out, int out_stride, const u64 *in, const int *d_ranges, int outs_per_in, int N, int k, int sign,
+                       int acc, int count, cudaStream_t st) {
+  if (count <= 0 || outs_per_in <= 0) return;
+  MvExtractArgs A;
+  A.out = out; A.in = in; A.ranges = d_ranges; A.N = N; A.k = k; A.out_stride = out_stride; A.outs_per_in = outs_per_in;
+  A.sign = sign; A.acc = acc;
+  mv_extract_kernel<<<count * outs_per_in, 256, 0, st>>>(A);
+  MB_CHECK(cudaGetLastError());
+  count_launch();
+}
+
 void launch_mv_phase1_rotations(u64 *out, const u64 *src, int N, int k, int torus_base, int count, cudaStream_t st) {
   mv_phase1_rotations_kernel<<<count, 256, 0, st>>>(out, src, N, k, torus_base);
   MB_CHECK(cudaGetLastError());

@@ -433,6 +433,36 @@ static void extract_acc(Torus *out, const Torus *in, int N, int k, int idx, int 
   free(e);
 }
 
+/* trlwe.c:554-578 as exported entry points: out (+|-)= trlwe_extract_tlwe(in, idx) */
+void oracle_extract_tlwe_addto(Torus *out, const Torus *in, int N, int k, int idx) { extract_acc(out, in, N, k, idx, +1); }
+void oracle_extract_tlwe_subto(Torus *out, const Torus *in, int N, int k, int idx) { extract_acc(out, in, N, k, idx, -1); }
+
+/* trlwe.c:580-589  trlwe_mv_extract_tlwe: out[i] = extract(i) for i < amount/2, -extract(N-1-(i-amount/2)) above */
+void oracle_mv_extract_tlwe(Torus *outs, const Torus *in, int N, int k, int amount) {
+  const int W = k * N + 1;
+  for (int i = 0; i < amount / 2; i++) oracle_extract_tlwe(outs + (size_t)i * W, in, N, k, i);
+  for (int i = amount / 2; i < amount; i++) {
+    Torus *o = outs + (size_t)i * W;
+    oracle_extract_tlwe(o, in, N, k, N - 1 - (i - amount / 2));
+    for (int c = 0; c < W; c++) o[c] = 0 - o[c];                 /* tlwe_negate */
+  }
+}
+
+/* trlwe.c:591-600  trlwe_mv_extract_tlwe_scaling */
+void oracle_mv_extract_tlwe_scaling(Torus *out, const Torus *in, int N, int k, int scale) {
+  const int amount = scale;
+  oracle_extract_tlwe(out, in, N, k, amount / 2);
+  for (int i = amount / 2 + 1; i < amount; i++) extract_acc(out, in, N, k, N - 1 - (i - amount / 2), -1);
+  for (int i = 0; i < amount / 2; i++) extract_acc(out, in, N, k, i, +1);
+}
+
+/* trlwe.c:602-610 / 612-620  trlwe_mv_extract_tlwe_scaling_addto / _subto (sign = +1 / -1) */
+void oracle_mv_extract_tlwe_scaling_acc(Torus *out, const Torus *in, int N, int k, int scale, int sign) {
+  const int amount = scale;
+  for (int i = amount / 2; i < amount; i++) extract_acc(out, in, N, k, N - 1 - (i - amount / 2), -sign);
+  for (int i = 0; i < amount / 2; i++) extract_acc(out, in, N, k, i, sign);
+}
+
 /* bootstrap.c:245-265  multivalue_bootstrap_phase2 (+ trlwe_mv_extract_tlwe_scaling_addto, trlwe.c:602-610) */
 void oracle_multivalue_phase2(Torus *out_tlwe, const int *in, const Torus *rot, int N, int k, int torus_base,
                               int log_torus_base) {

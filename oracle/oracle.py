@@ -56,6 +56,11 @@ def lib():
             "oracle_blind_rotate": (None, [_u64p, _u64p, _f64p, _int, _int, _int, _int, _int, _int]),
             "oracle_functional_bootstrap_wo_extract": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 7),
             "oracle_extract_tlwe": (None, [_u64p, _u64p, _int, _int, _int]),
+            "oracle_extract_tlwe_addto": (None, [_u64p, _u64p, _int, _int, _int]),
+            "oracle_extract_tlwe_subto": (None, [_u64p, _u64p, _int, _int, _int]),
+            "oracle_mv_extract_tlwe": (None, [_u64p, _u64p, _int, _int, _int]),
+            "oracle_mv_extract_tlwe_scaling": (None, [_u64p, _u64p, _int, _int, _int]),
+            "oracle_mv_extract_tlwe_scaling_acc": (None, [_u64p, _u64p, _int, _int, _int, _int]),
             "oracle_functional_bootstrap": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 7),
             "oracle_programmable_preprocess": (None, [_u64p, _u64p, _int, _int, _int, _int]),
             "oracle_programmable_bootstrap": (None, [_u64p, _u64p, _u64p, _f64p] + [_int] * 9),
@@ -206,6 +211,37 @@ def extract_tlwe(trlwe, idx=0):
     out = np.empty(k * N + 1, np.uint64)
     lib().oracle_extract_tlwe(out, trlwe, N, k, idx)
     return out
+
+
+def extract_tlwe_acc(out, trlwe, idx, sign):
+    """trlwe_extract_tlwe_addto (sign = +1) / _subto (sign = -1), trlwe.c:554-578; returns the updated copy of ``out``."""
+    trlwe = _c(trlwe, np.uint64)
+    k, N = trlwe.shape[0] - 1, trlwe.shape[1]
+    out = _c(out, np.uint64).copy()
+    (lib().oracle_extract_tlwe_addto if sign > 0 else lib().oracle_extract_tlwe_subto)(out, trlwe, N, k, idx)
+    return out
+
+
+def mv_extract_tlwe(trlwe, amount):
+    """trlwe_mv_extract_tlwe (trlwe.c:580-589) -> [amount, k*N+1]."""
+    trlwe = _c(trlwe, np.uint64)
+    k, N = trlwe.shape[0] - 1, trlwe.shape[1]
+    out = np.empty((amount, k * N + 1), np.uint64)
+    lib().oracle_mv_extract_tlwe(out, trlwe, N, k, amount)
+    return out
+
+
+def mv_extract_tlwe_scaling(trlwe, scale, out=None, sign=0):
+    """trlwe_mv_extract_tlwe_scaling (sign = 0, trlwe.c:591-600), _scaling_addto (+1, :602-610), _scaling_subto (-1, :612-620)."""
+    trlwe = _c(trlwe, np.uint64)
+    k, N = trlwe.shape[0] - 1, trlwe.shape[1]
+    if sign == 0:
+        res = np.empty(k * N + 1, np.uint64)
+        lib().oracle_mv_extract_tlwe_scaling(res, trlwe, N, k, scale)
+        return res
+    res = _c(out, np.uint64).copy()
+    lib().oracle_mv_extract_tlwe_scaling_acc(res, trlwe, N, k, scale, sign)
+    return res
 
 
 def functional_bootstrap(tv, tlwe_in, bsk, l, Bg_bit, torus_base, mode=0):

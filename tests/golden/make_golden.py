@@ -372,7 +372,57 @@ def gen_r4(variant):
     return out
 
 
+def gen_mvx(variant):
+    """Integer extraction family of the multi-ciphertext caller (trlwe.c:554-620): recorded from the reference on random
+    TRLWE inputs for (k, N) = (1, 256) and (2, 128); every output is bit-exact by construction."""
+    R = reflib.load(variant)
+    for name, res, args in (("trlwe_extract_tlwe_addto", None, [abi.TLWE, abi.TRLWE, C.c_int]),
+                            ("trlwe_extract_tlwe_subto", None, [abi.TLWE, abi.TRLWE, C.c_int]),
+                            ("trlwe_mv_extract_tlwe", None, [C.POINTER(abi.TLWE), abi.TRLWE, C.c_int]),
+                            ("trlwe_mv_extract_tlwe_scaling", None, [abi.TLWE, abi.TRLWE, C.c_int]),
+                            ("trlwe_mv_extract_tlwe_scaling_addto", None, [abi.TLWE, abi.TRLWE, C.c_int]),
+                            ("trlwe_mv_extract_tlwe_scaling_subto", None, [abi.TLWE, abi.TRLWE, C.c_int])):
+        fn = getattr(R.lib, name)
+        fn.restype, fn.argtypes = res, args
+    out = dict(params=np.array([0, 0, 0, 0, 0, 0, 0], np.int32), layout=np.int32(R.layout))
+    shapes = [(1, 256), (2, 128)]
+    out["shapes"] = np.array(shapes, np.int32)
+    out["idx_list"] = np.array([0, 1, 17, 127], np.int32)
+    out["scales"] = np.array([1, 2, 4, 8, 16], np.int32)
+    out["amounts"] = np.array([2, 4, 8], np.int32)
+    for si, (k, N) in enumerate(shapes):
+        W = k * N + 1
+        tr = abi.HostTRLWE(rand_u64(R, (k + 1) * N).reshape(k + 1, N))
+        start = rand_u64(R, W)
+        out[f"s{si}_trlwe"] = tr.polys.copy()
+        out[f"s{si}_start"] = start.copy()
+        for idx in out["idx_list"]:
+            for nm, sign in (("addto", +1), ("subto", -1)):
+                o = abi.HostTLWE(start)
+                getattr(R.lib, f"trlwe_extract_tlwe_{nm}")(o.handle, tr.handle, int(idx))
+                out[f"s{si}_extract_{nm}_{int(idx)}"] = o.flat()
+        for amount in out["amounts"]:
+            outs = [abi.HostTLWE.zeros(k * N) for _ in range(int(amount))]
+            R.lib.trlwe_mv_extract_tlwe(abi.handle_array(outs, abi.TLWE), tr.handle, int(amount))
+            out[f"s{si}_mv_{int(amount)}"] = np.stack([o.flat() for o in outs])
+        for scale in out["scales"]:
+            o = abi.HostTLWE.zeros(k * N)
+            R.lib.trlwe_mv_extract_tlwe_scaling(o.handle, tr.handle, int(scale))
+            out[f"s{si}_scaling_{int(scale)}"] = o.flat()
+            for nm in ("addto", "subto"):
+                o = abi.HostTLWE(start)
+                getattr(R.lib, f"trlwe_mv_extract_tlwe_scaling_{nm}")(o.handle, tr.handle, int(scale))
+                out[f"s{si}_scaling_{nm}_{int(scale)}"] = o.flat()
+    return out
+
+
 def main():
+    if "--mvx-only" in sys.argv:
+        data = gen_mvx("avx512")
+        path = os.path.join(HERE, "tiny_mvx.npz")
+        np.savez_compressed(path, **data)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+        return
     if "--r4-only" in sys.argv:
         data = gen_r4("fma")
         path = os.path.join(HERE, "tiny_r4_spqlios.npz")

@@ -1115,3 +1115,145 @@ def test_next_rows_empty_batches_and_aborts(golden_cb):
         r = subprocess.run([sys.executable, "-c", code, which], capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "NOT REACHED" not in r.stdout, which
         assert "mosfhet_b200:" in r.stderr and word in r.stderr, r.stderr[-400:]
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: the extraction family of the multi-ciphertext caller (trlwe.c:554-620), the fused digit step of
+# integer.c:94-100, stale-key detection, and unfolded keys behind the remaining bootstrap entry points
+# ------------------------------------------------------------------------------------------------
+def test_mv_extract_family_bit_exact():
+    """Every exported member against the outputs recorded from the reference (tests/golden/tiny_mvx.npz): integer work,
+    bit for bit; the _batch forms equal the single calls."""
+    g = np.load(_os.path.join(TESTS_DIR, "golden", "tiny_mvx.npz"))
+    for si, (k, N) in enumerate(g["shapes"]):
+        tr = abi.HostTRLWE(g[f"s{si}_trlwe"])
+        start = g[f"s{si}_start"]
+        for idx in g["idx_list"]:
+            for nm, fn in (("addto", api.trlwe_extract_tlwe_addto), ("subto", api.trlwe_extract_tlwe_subto)):
+                o = abi.HostTLWE(start)
+                fn(o, tr, int(idx))
+                assert np.array_equal(o.flat(), g[f"s{si}_extract_{nm}_{int(idx)}"]), (si, nm, idx)
+        for amount in g["amounts"]:
+            outs = [abi.HostTLWE.zeros(k * N) for _ in range(int(amount))]
+            api.trlwe_mv_extract_tlwe(outs, tr, int(amount))
+            assert np.array_equal(np.stack([o.flat() for o in outs]), g[f"s{si}_mv_{int(amount)}"]), (si, amount)
+        for scale in g["scales"]:
+            o = abi.HostTLWE.zeros(k * N)
+            api.trlwe_mv_extract_tlwe_scaling(o, tr, int(scale), 0)
+            assert np.array_equal(o.flat(), g[f"s{si}_scaling_{int(scale)}"]), (si, scale)
+            for nm, mode in (("addto", 1), ("subto", -1)):
+                o = abi.HostTLWE(start)
+                api.trlwe_mv_extract_tlwe_scaling(o, tr, int(scale), mode)
+                assert np.array_equal(o.flat(), g[f"s{si}_scaling_{nm}_{int(scale)}"]), (si, nm, scale)
+        # batched forms: 5 copies with per-element indices / one scale
+        trs = [abi.HostTRLWE(np.roll(g[f"s{si}_trlwe"], 3 * i, axis=1)) for i in range(5)]
+        idxs = np.array([0, 5, N - 1, 17, 1], np.int32)
+        outs = [abi.HostTLWE(start) for _ in range(5)]
+        api.trlwe_extract_tlwe_acc_batch(outs, trs, idxs, -1)
+        for i in range(5):
+            assert np.array_equal(outs[i].flat(), O.extract_tlwe_acc(start, trs[i].polys, int(idxs[i]), -1)), i
+        outs = [abi.HostTLWE(start) for _ in range(5)]
+        api.trlwe_mv_extract_tlwe_scaling_batch(outs, trs, 8, 1)
+        for i in range(5):
+            assert np.array_equal(outs[i].flat(), O.mv_extract_tlwe_scaling(trs[i].polys, 8, start, +1)), i
+        lists = [[abi.HostTLWE.zeros(k * N) for _ in range(4)] for _ in range(5)]
+        api.trlwe_mv_extract_tlwe_batch(lists, trs, 4)
+        for i in range(5):
+            assert np.array_equal(np.stack([o.flat() for o in lists[i]]), O.mv_extract_tlwe(trs[i].polys, 4)), i
+
+
+def test_integer_digit_step_fused(golden):
+    """tlwe_keyswitch -> functional_bootstrap_wo_extract -> trlwe_mv_extract_tlwe_scaling_subto / _addto as ONE batched call
+    (integer.c:94-100) equals the same chain through the single drop-in calls, bit for bit (deterministic kernels), and
+    the integer stages of that chain equal the oracle's on the GPU's own bootstrap output."""
+    g, P = golden, golden["P"]
+    k, N, n = P["k"], P["N"], P["n"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, P["l"], P["Bg_bit"])
+    hksk = abi.HostKSKey(g["ksk"], P["base_bit"])
+    tv = abi.HostTRLWE(g["tv"])
+    B = g["ks_out"].shape[0]
+    big = g["fb_out"]                                   # dimension k*N TLWEs (the reference's bootstrap outputs) as digits
+    start_carry = g["fb_out"][::-1].copy()
+    digits = [abi.HostTLWE(big[b]) for b in range(B)]
+    carries = [abi.HostTLWE(start_carry[b]) for b in range(B)]
+    api.tlwe_keyswitch_bootstrap_mv_extract_batch(digits, carries, tv, hksk, hbsk, 4, 4, 1)
+    for b in range(B):
+        small = abi.HostTLWE.zeros(n)
+        api.tlwe_keyswitch(small, abi.HostTLWE(big[b]), hksk)
+        assert np.array_equal(small.flat(), O.tlwe_keyswitch(big[b], g["ksk"], P["base_bit"]))
+        acc = abi.HostTRLWE.zeros(k, N)
+        api.functional_bootstrap_wo_extract(acc, tv, small, hbsk, 4)
+        d = abi.HostTLWE(big[b])
+        api.trlwe_mv_extract_tlwe_scaling(d, acc, 4, -1)
+        c = abi.HostTLWE(start_carry[b])
+        api.trlwe_mv_extract_tlwe_scaling(c, acc, 1, 1)
+        assert np.array_equal(digits[b].flat(), d.flat()), b
+        assert np.array_equal(carries[b].flat(), c.flat()), b
+        assert np.array_equal(d.flat(), O.mv_extract_tlwe_scaling(acc.polys, 4, big[b], -1))
+        assert np.array_equal(c.flat(), O.mv_extract_tlwe_scaling(acc.polys, 1, start_carry[b], +1))
+    # without a carry output
+    digits2 = [abi.HostTLWE(big[b]) for b in range(B)]
+    api.tlwe_keyswitch_bootstrap_mv_extract_batch(digits2, None, tv, hksk, hbsk, 4, 4)
+    for b in range(B):
+        assert np.array_equal(digits2[b].flat(), digits[b].flat())
+    api.release_bootstrap_key(hbsk)
+    api.release_ks_key(hksk)
+
+
+def test_stale_key_is_detected(golden):
+    """A key regenerated IN PLACE (same host addresses, new contents) must not be served from the resident copy of the old
+    one: the fingerprint taken at upload no longer matches and the key is uploaded again."""
+    g, P = golden, golden["P"]
+    k, N = P["k"], P["N"]
+    api.set_host_fft_layout(g["layout"])
+    hbsk = abi.HostBootstrapKey(g["bsk_host"], k, P["l"], P["Bg_bit"])
+    hksk = abi.HostKSKey(g["ksk"], P["base_bit"])
+    tv, cin = abi.HostTRLWE(g["tv"]), abi.HostTLWE(g["tlwe_in"][0])
+    out1 = abi.HostTLWE.zeros(k * N)
+    api.functional_bootstrap(out1, tv, cin, hbsk, 4)
+    ks1 = abi.HostTLWE.zeros(P["n"])
+    api.tlwe_keyswitch(ks1, abi.HostTLWE(g["fb_out"][0]), hksk)
+    # overwrite the host trees in place with a different (here: negated) key
+    for trg in hbsk.trgsw:
+        for row in trg.rows:
+            row.polys *= -1.0
+    neg_ksk = np.uint64(0) - g["ksk"]
+    n_in, t_, bm1, w_ = g["ksk"].shape
+    for i in range(n_in):
+        for j in range(t_):
+            for d_ in range(bm1):
+                r = hksk.rows[i][j][d_]
+                r._a[: r.n] = neg_ksk[i, j, d_, : r.n]
+                r.struct.b = int(neg_ksk[i, j, d_, r.n])
+    out2 = abi.HostTLWE.zeros(k * N)
+    api.functional_bootstrap(out2, tv, cin, hbsk, 4)
+    assert not np.array_equal(out1.flat(), out2.flat()), "bootstrap served from the stale resident key"
+    ks2 = abi.HostTLWE.zeros(P["n"])
+    api.tlwe_keyswitch(ks2, abi.HostTLWE(g["fb_out"][0]), hksk)
+    want = O.tlwe_keyswitch(g["fb_out"][0], neg_ksk, P["base_bit"])
+    assert np.array_equal(ks2.flat(), want) and not np.array_equal(ks1.flat(), ks2.flat())
+    api.release_bootstrap_key(hbsk)
+    api.release_ks_key(hksk)
+
+
+def test_programmable_bootstrap_with_unfolded_key(golden_r4):
+    """programmable_bootstrap reaches the unfolded loop through functional_bootstrap (bootstrap.c:218 -> 192-198): the GPU
+    result must equal functional_bootstrap of the shaped input through the same key, bit for bit, and decrypt to the LUT."""
+    g, P = golden_r4, golden_r4["P"]
+    n, N, k, l, Bg_bit, u = P["n"], P["N"], P["k"], P["l"], P["Bg_bit"], golden_r4["unfolding"]
+    api.set_host_fft_layout(g["layout"])
+    key = abi.HostUnfoldedBootstrapKey(g["su"], n, u, k, l, Bg_bit)
+    tv = abi.HostTRLWE(g["tv"])
+    precision, kappa, theta = 3, 0, 1
+    for c in range(g["r4_in"].shape[0]):
+        cin = abi.HostTLWE(g["r4_in"][c])
+        out = abi.HostTLWE.zeros(k * N)
+        api.programmable_bootstrap(out, tv, cin, key, precision, kappa, theta)
+        shaped = O.programmable_preprocess(g["r4_in"][c], N, kappa, theta)
+        ref = abi.HostTLWE.zeros(k * N)
+        api.functional_bootstrap(ref, tv, abi.HostTLWE(shaped), key, 1 << (precision - 1))
+        assert np.array_equal(out.flat(), ref.flat()), c
+        ph = O.tlwe_phase(out.flat(), g["ext_key"])
+        assert sdiff(np.uint64(ph), g["lut"][g["msgs"][c]]) <= TOL_TEST
+    api.release_bootstrap_key(key)

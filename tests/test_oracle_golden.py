@@ -1,6 +1,8 @@
 """Pins the CPU oracle (oracle/oracle.c) against golden vectors produced by the UNMODIFIED reference
 library (tests/golden/make_golden.py).  Integer stages must be bit-exact; floating-point stages are
 held to the tolerances of SURVEY.md section 8(c), written next to each assertion."""
+import os
+
 import numpy as np
 import pytest
 
@@ -271,3 +273,19 @@ def test_unfolded_blind_rotation(golden_r4):
         ph_ref = O.tlwe_phase(g["ubr_p2"][c], g["ext_key"])
         assert abs(int(np.int64(np.uint64((ph - ph_ref) % 2**64)))) <= tol
         assert abs(int(np.int64(np.uint64((ph - int(g["lut"][g["msgs"][c]])) % 2**64)))) <= (1 << 58)
+
+
+# ---- extraction family of the multi-ciphertext caller (trlwe.c:554-620), fixture recorded by make_golden.py --mvx-only ----
+def test_mv_extract_family_vs_reference():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_mvx.npz"))
+    for si, (k, N) in enumerate(g["shapes"]):
+        tr, start = g[f"s{si}_trlwe"], g[f"s{si}_start"]
+        for idx in g["idx_list"]:
+            assert np.array_equal(O.extract_tlwe_acc(start, tr, int(idx), +1), g[f"s{si}_extract_addto_{int(idx)}"])
+            assert np.array_equal(O.extract_tlwe_acc(start, tr, int(idx), -1), g[f"s{si}_extract_subto_{int(idx)}"])
+        for amount in g["amounts"]:
+            assert np.array_equal(O.mv_extract_tlwe(tr, int(amount)), g[f"s{si}_mv_{int(amount)}"])
+        for scale in g["scales"]:
+            assert np.array_equal(O.mv_extract_tlwe_scaling(tr, int(scale)), g[f"s{si}_scaling_{int(scale)}"])
+            assert np.array_equal(O.mv_extract_tlwe_scaling(tr, int(scale), start, +1), g[f"s{si}_scaling_addto_{int(scale)}"])
+            assert np.array_equal(O.mv_extract_tlwe_scaling(tr, int(scale), start, -1), g[f"s{si}_scaling_subto_{int(scale)}"])
