@@ -4,7 +4,10 @@
 #include <dlfcn.h>
 
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -34,9 +37,6 @@ namespace {
 std::mutex g_mu;
 int g_host_layout = MB200_FFT_AUTO;
 int g_policy = 0;
-#ifndef MB200_K1Q_N2048
-#define MB200_K1Q_N2048 false       // full batches at N = 2048: the T = M/4 kernel instead of the T = M/8 one
-#endif
 // name of the blind-rotation kernel this host thread dispatched last (entry points may be called from several threads)
 thread_local char t_last_kernel[96] = "none";
 void set_last_kernel(const char *name) { snprintf(t_last_kernel, sizeof(t_last_kernel), "%s", name); }
@@ -505,8 +505,8 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
     if (g_policy == 0) {
       const bool want_c = env_flag("MB200_K1C", 2 * a.count <= sms && p.N > 1024);
       const bool want_h = env_flag("MB200_K1H", a.count <= 2 * sms && p.N <= 1024);
-      // measured (profiles/r2c_k1q_timing.log, 4096 ciphertexts): N = 1024 k1q 40.6 ms vs k1 42.9 ms; N = 2048 see MB200_K1Q_N2048
-      const bool want_q = env_flag("MB200_K1Q", p.N == 1024 || MB200_K1Q_N2048);
+      // measured (profiles/r2d_k1q_timing.log, 4096 ciphertexts): N = 1024 k1q 40.6 ms vs k1 42.9 ms; N = 2048 120.3 vs 126.4 ms
+      const bool want_q = env_flag("MB200_K1Q", true);
       if (want_c && mb::k1c_supported(p)) pick = K1C;
       else if (want_h && mb::k1h_supported(p)) pick = K1H;
       else if (want_q && mb::k1q_supported(p)) pick = K1Q;
@@ -695,21 +695,68 @@ void pbs_any(const AnyBsk &k, u64 *d_out, int extract, const u64 *d_tv, int tv_c
 // ---- handle-tree gather / scatter -----------------------------------------------------------------
 // The handle trees are thousands of separately allocated host blocks (mosfhet.h:22-60): flattening a large batch is
 // split over a few host threads (measured: functional_bootstrap_keyswitch_batch 56.5 -> 53.7 ms per 4096 Level-1 ciphertexts, scripts/handle_overhead.py).
+// A small persistent pool of host workers (created on first use): flattening a batch of handle trees is memcpy-bound and
+// scales over a few cores, and the pipelined entry points below hand it gather / scatter jobs while the GPU works.
+class HostPool {
+ public:
+  static HostPool &get() { static HostPool *p = new HostPool(); return *p; }     // leaked at exit on purpose (threads may outlive statics)
+  int workers() const { return (int)th_.size(); }
+  // a group of jobs whose completion can be awaited
+  struct Group { std::mutex m; std::condition_variable cv; int pending = 0; };
+  void submit(Group &g, std::function<void()> job) {
+    { std::lock_guard<std::mutex> lk(g.m); ++g.pending; }
+    { std::lock_guard<std::mutex> lk(mu_); q_.push_back(Item{&g, std::move(job)}); }
+    cv_.notify_one();
+  }
+  void wait(Group &g) {
+    std::unique_lock<std::mutex> lk(g.m);
+    g.cv.wait(lk, [&] { return g.pending == 0; });
+  }
+ private:
+  struct Item { Group *g; std::function<void()> job; };
+  HostPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? (hw < 12 ? hw : 12) : 4) - 1;
+    if (nt < 1) nt = 1;
+    for (int i = 0; i < nt; ++i) th_.emplace_back([this] { run(); });
+    for (auto &t : th_) t.detach();
+  }
+  void run() {
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !q_.empty(); });
+        it = std::move(q_.front());
+        q_.pop_front();
+      }
+      it.job();
+      // notify under the lock: the waiter may destroy the group as soon as it sees pending == 0 and owns the mutex
+      { std::lock_guard<std::mutex> lk(it.g->m); --it.g->pending; it.g->cv.notify_all(); }
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Item> q_;
+  std::vector<std::thread> th_;
+};
+
+// body(begin, end) over [0, count) in slices of at least 256 elements, the calling thread taking one slice itself
 template <class F>
 void parallel_for(int count, F body) {
-  const int min_chunk = 512;
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)(hw ? (hw < 8 ? hw : 8) : 4);
-  if (count < 2 * min_chunk || nt <= 1) { body(0, count); return; }
-  if (nt > count / min_chunk) nt = count / min_chunk;
-  std::vector<std::thread> th;
-  const int per = (count + nt - 1) / nt;
-  for (int i = 1; i < nt; ++i) {
+  const int min_chunk = 256;
+  HostPool &pool = HostPool::get();
+  int parts = count / min_chunk;
+  if (parts > pool.workers() + 1) parts = pool.workers() + 1;
+  if (parts <= 1) { body(0, count); return; }
+  HostPool::Group g;
+  const int per = (count + parts - 1) / parts;
+  for (int i = 1; i < parts; ++i) {
     const int b = i * per, e = b + per < count ? b + per : count;
-    if (b < e) th.emplace_back([=] { body(b, e); });
+    if (b < e) pool.submit(g, [=] { body(b, e); });
   }
   body(0, per < count ? per : count);
-  for (auto &x : th) x.join();
+  pool.wait(g);
 }
 
 void gather_tlwe(u64 *dst, TLWE *in, int count, int n) {
@@ -1141,22 +1188,78 @@ void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count) {
   scatter_tlwe(out, h_out, count, p.n);
 }
 
+// The metric's unit of work over handle arrays, pipelined: the batch is cut into chunks of whole GPU waves; host workers
+// flatten chunk c + 1 while chunk c is copied and bootstrapped, ONE key switch sweeps the table for the whole batch
+// (a chunked key switch would re-read the table per chunk), and the results are copied back and scattered chunk by chunk.
 void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
                                           TLWE_KS_Key ks_key, int torus_base, int count) {
   if (count <= 0) return;
+  MB_REQUIRE(tv_count == 1 || tv_count == count, "tv_count must be 1 or count");
   mb200_bsk *bsk = lookup_bsk(key);
   mb200_ksk *ksk = lookup_ksk(ks_key, bsk->p.k * bsk->p.N);
   const mb::Params &p = bsk->p;
+  MB_REQUIRE(ksk->p.k * ksk->p.N == p.k * p.N && ksk->p.n == p.n, "pbs_ks: key switch (%d -> %d) does not chain with the bootstrap (%d -> %d)",
+             ksk->p.k * ksk->p.N, ksk->p.n, p.n, p.k * p.N);
+  for (int i = 0; i < count; ++i) {
+    MB_REQUIRE(in[i]->n == p.n, "TLWE %d has dimension %d, expected %d", i, in[i]->n, p.n);
+    MB_REQUIRE(out[i]->n == p.n, "output TLWE %d has dimension %d, expected %d", i, out[i]->n, p.n);      // tlwe.c:293
+  }
   cudaStream_t st = mb::default_stream();
-  PbsStaged s = stage_pbs_inputs(tv, tv_count, in, p, count, st);
-  const size_t mid_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1), out_b = sizeof(u64) * (size_t)count * (p.n + 1);
-  u64 *d_mid = (u64 *)t_scratch[S_MID].dev(mid_b);
-  u64 *h_out = (u64 *)t_scratch[S_OUT].host(out_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  mb200_pbs_ks_dev(bsk, ksk, (uint64_t *)d_out, (const uint64_t *)s.d_tv, tv_count, (const uint64_t *)s.d_in,
-                   (uint64_t *)d_mid, torus_base, count, st);
-  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
-  MB_CHECK(cudaStreamSynchronize(st));
-  scatter_tlwe(out, h_out, count, p.n);
+  const int w_in = p.n + 1, w_mid = p.k * p.N + 1, W = (p.k + 1) * p.N;
+  const size_t in_b = sizeof(u64) * (size_t)count * w_in, tv_b = sizeof(u64) * (size_t)tv_count * W;
+  u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
+  u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
+  u64 *d_mid = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * (size_t)count * w_mid);
+  u64 *h_out = (u64 *)t_scratch[S_OUT].host(in_b), *d_out = (u64 *)t_scratch[S_OUT].dev(in_b);
+  // chunks of whole waves (a wave = resident CTAs of the blind rotation: 4 per SM at N <= 1024, 2 at N = 2048), about 4 per batch
+  const int wave = mb::sm_count() * (p.N <= 1024 ? 4 : (p.N <= 2048 ? 2 : 1));
+  int per = ((count + 3) / 4 + wave - 1) / wave * wave;
+  if (count < 2 * wave || tv_count != 1) per = count;           // small batches / per-input test vectors: one chunk
+  const int nchunks = (count + per - 1) / per;
+  HostPool &pool = HostPool::get();
+  std::vector<HostPool::Group> gathered(nchunks);
+  const int sub = 256;                                          // gather / scatter job size (ciphertexts)
+  auto gather_job = [=](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      memcpy(h_in + (size_t)i * w_in, in[i]->a, sizeof(u64) * (w_in - 1));
+      h_in[(size_t)i * w_in + w_in - 1] = in[i]->b;
+    }
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * per, c1 = c0 + per < count ? c0 + per : count;
+    for (int b = c0; b < c1; b += sub) pool.submit(gathered[c], [=] { gather_job(b, b + sub < c1 ? b + sub : c1); });
+  }
+  gather_trlwe(h_tv, tv, tv_count, p.k, p.N);
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
+    pool.wait(gathered[c]);
+    MB_CHECK(cudaMemcpyAsync(d_in + (size_t)c0 * w_in, h_in + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyHostToDevice, st));
+    pbs_dev_impl(bsk, d_mid + (size_t)c0 * w_mid, 1, d_tv + (tv_count > 1 ? (size_t)c0 * W : 0), tv_count > 1 ? cc : 1,
+                 d_in + (size_t)c0 * w_in, torus_base, cc, st);
+  }
+  mb::launch_keyswitch(ksk, d_out, d_mid, count, st);
+  std::vector<cudaEvent_t> done(nchunks);
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
+    MB_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * w_in, d_out + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyDeviceToHost, st));
+    MB_CHECK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+    MB_CHECK(cudaEventRecord(done[c], st));
+  }
+  HostPool::Group scattered;
+  auto scatter_job = [=](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      memcpy(out[i]->a, h_out + (size_t)i * w_in, sizeof(u64) * (w_in - 1));
+      out[i]->b = h_out[(size_t)i * w_in + w_in - 1];
+    }
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * per, c1 = c0 + per < count ? c0 + per : count;
+    MB_CHECK(cudaEventSynchronize(done[c]));
+    MB_CHECK(cudaEventDestroy(done[c]));
+    for (int b = c0; b < c1; b += sub) pool.submit(scattered, [=] { scatter_job(b, b + sub < c1 ? b + sub : c1); });
+  }
+  pool.wait(scattered);
 }
 
 void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count) {
