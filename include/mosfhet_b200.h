@@ -182,6 +182,12 @@ void multivalue_bootstrap_phase2_batch(TLWE *out, int **lut, int lut_count, TRLW
 int  mb200_init(int device);            /* select device, create context; <0 only if device==-2 probe and none present */
 void mb200_shutdown(void);              /* free cached keys, staging buffers, streams */
 int  mb200_device_count(void);          /* number of visible CUDA devices (0 without a GPU; no abort) */
+/* Multi-GPU inside the library: after mb200_init_multi(ndev) the batched drop-in entry points
+ * (functional_bootstrap[_wo_extract|_keyswitch]_batch, programmable_bootstrap_batch, tlwe_keyswitch_batch) cut their batch
+ * into contiguous shards over devices 0..ndev-1 (ndev <= 0: all), one host worker thread, stream and staging area per
+ * device; registered keys are replicated to every device over NVLink (cudaMemcpyPeer).  Returns the devices in use. */
+int  mb200_init_multi(int ndev);
+int  mb200_multi_device_count(void);
 const char *mb200_version(void);
 void mb200_device_synchronize(void);
 

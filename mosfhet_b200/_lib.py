@@ -86,6 +86,8 @@ PROTOTYPES = {
     "trlwe_mv_extract_tlwe_scaling_batch": (None, [_P(abi.TLWE), _P(abi.TRLWE), C.c_int, C.c_int, C.c_int]),
     "tlwe_keyswitch_bootstrap_mv_extract_batch": (None, [_P(abi.TLWE), _P(abi.TLWE), _P(abi.TRLWE), C.c_int, abi.TLWE_KS_Key,
                                                          abi.Bootstrap_Key, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mb200_init_multi": (C.c_int, [C.c_int]),
+    "mb200_multi_device_count": (C.c_int, []),
     "free_bootstrap_key": (None, [abi.Bootstrap_Key]),
     "free_tlwe_ks_key": (None, [abi.TLWE_KS_Key]),
     "free_trlwe_generic_ks_key": (None, [C.c_void_p]),

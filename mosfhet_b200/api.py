@@ -41,6 +41,11 @@ def init(device: int = 0) -> None:
     lib().mb200_init(device)
 
 
+def init_multi(ndev: int = 0) -> int:
+    """Multi-GPU mode inside the library: batched drop-in calls shard over ``ndev`` devices (0 = all); returns the count."""
+    return int(lib().mb200_init_multi(ndev))
+
+
 def require_gpu() -> None:
     if device_count() < 1:
         raise RuntimeError("mosfhet_b200: no CUDA device visible and there is no CPU fallback")

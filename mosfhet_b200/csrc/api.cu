@@ -40,16 +40,20 @@ int g_policy = 0;
 // name of the blind-rotation kernel this host thread dispatched last (entry points may be called from several threads)
 thread_local char t_last_kernel[96] = "none";
 void set_last_kernel(const char *name) { snprintf(t_last_kernel, sizeof(t_last_kernel), "%s", name); }
-std::map<const void *, mb200_bsk *> g_bsk_cache;   // keyed by Bootstrap_Key->s (the TRGSW_DFT array)
-std::map<const void *, mb200_ksk *> g_ksk_cache;   // keyed by TLWE_KS_Key->s
+// resident keys: (host pointer, device) -> upload.  The host pointer is Bootstrap_Key->s (the TRGSW_DFT array),
+// TLWE_KS_Key->s, ...; every device of the multi-GPU mode holds its own replica.
+typedef std::pair<const void *, int> CKey;
+inline CKey ck(const void *p) { return CKey(p, mb::current_device()); }
+std::map<CKey, mb200_bsk *> g_bsk_cache;
+std::map<CKey, mb200_ksk *> g_ksk_cache;
 struct GkskDev { u64 *d; int n_entries, t, base_bit, k, N, n_in, include_b; unsigned long long print = 0; };
 }  // namespace
 struct mb200_gksk : GkskDev {};
 namespace {
-std::map<const void *, GkskDev *> g_gksk_cache;    // keyed by Generic_KS_Key->s
+std::map<CKey, GkskDev *> g_gksk_cache;            // keyed by Generic_KS_Key->s
 struct UbskDev { u64 *d; mb::Params p; int unfolding; unsigned long long print = 0; };   // torus-domain key of bootstrap.c:23-48, p.n = LWE dimension
-std::map<const void *, UbskDev *> g_ubsk_cache;    // keyed by Bootstrap_Key->su
-std::map<const void *, mb200_bsk *> g_rksk_cache;  // keyed by TRLWE_KS_Key->s, or by the TRLWE_KS_Key[2] array
+std::map<CKey, UbskDev *> g_ubsk_cache;            // keyed by Bootstrap_Key->su
+std::map<CKey, mb200_bsk *> g_rksk_cache;          // keyed by TRLWE_KS_Key->s, or by the TRLWE_KS_Key[2] array
 
 // ---- resident keys are cached by host pointer; a fingerprint guards the pointer ---------------------------------------
 // The reference's callers free keys and generate new ones (its tests do), and malloc readily hands the same address
@@ -223,11 +227,11 @@ void host_exponents(int N, std::vector<int32_t> &e, int layout_override = -1) {
 
 // device-side maps for the DFT boundary ops (trgsw_mul_trlwe_DFT out, trlwe_from_DFT in)
 struct DftMaps { int *stored_to_host, *stored_conj, *pos_to_host, *pos_conj; };
-std::map<std::pair<int, int>, DftMaps> g_dft_maps;   // (N, layout)
+std::map<std::pair<long long, int>, DftMaps> g_dft_maps;   // ((device, N), layout)
 
 DftMaps dft_maps_for(int N) {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto key = std::make_pair(N, g_host_layout);
+  auto key = std::make_pair(mb::dev_key(N), g_host_layout);
   auto it = g_dft_maps.find(key);
   if (it != g_dft_maps.end()) return it->second;
   const int M = N / 2;
@@ -325,16 +329,32 @@ mb200_bsk *lookup_bsk(Bootstrap_Key key) {
   const unsigned long long print = bsk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_bsk_cache.find((const void *)key->s);
+    auto it = g_bsk_cache.find(ck((const void *)key->s));
     if (it != g_bsk_cache.end()) {
       if (it->second->print == print || it->second->print == 0) return it->second;
       free_bsk_obj(it->second);                       // same address, different key: the upload is stale
       g_bsk_cache.erase(it);
     }
   }
-  mb200_bsk *b = upload_bsk(key);
+  mb200_bsk *b = nullptr;
+  if (mb::current_device() != mb::primary_device()) {           // replica of the primary's upload, over NVLink
+    mb200_bsk *src = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      auto it = g_bsk_cache.find(CKey((const void *)key->s, mb::primary_device()));
+      if (it != g_bsk_cache.end() && it->second->print == print) src = it->second;
+    }
+    if (src) {
+      b = bsk_alloc(src->p);
+      b->print = print;
+      cudaStream_t st = mb::default_stream();
+      MB_CHECK(cudaMemcpyPeerAsync(b->d, mb::current_device(), src->d, mb::primary_device(), sizeof(double2) * bsk_elems(src->p), st));
+      MB_CHECK(cudaStreamSynchronize(st));
+    }
+  }
+  if (!b) b = upload_bsk(key);
   std::lock_guard<std::mutex> lk(g_mu);
-  auto ins = g_bsk_cache.emplace((const void *)key->s, b);
+  auto ins = g_bsk_cache.emplace(ck((const void *)key->s), b);
   if (!ins.second) { free_bsk_obj(b); return ins.first->second; }   // another thread uploaded the same key meanwhile
   return b;
 }
@@ -357,7 +377,7 @@ void acquire_bsk_set(BskRef &ref, TRGSW_DFT *s, int n, int k, int N) {
   tmp.s = s; tmp.su = nullptr; tmp.n = n; tmp.k = k; tmp.N = N; tmp.Bg_bit = s[0]->Bg_bit; tmp.l = s[0]->l; tmp.unfolding = 1;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_bsk_cache.find((const void *)s);
+    auto it = g_bsk_cache.find(ck((const void *)s));
     if (it != g_bsk_cache.end() && it->second->p.n >= n && it->second->p.k == k && it->second->p.N == N) {
       tmp.n = it->second->p.n;
       if (it->second->print == 0 || it->second->print == bsk_print(&tmp)) { ref.b = it->second; ref.temporary = false; return; }
@@ -385,12 +405,31 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
   const unsigned long long print = ksk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ksk_cache.find((const void *)key->s);
+    auto it = g_ksk_cache.find(ck((const void *)key->s));
     if (it != g_ksk_cache.end()) {
       if (it->second->print == print) return it->second;
       if (it->second->owned) cudaFree(it->second->d);
       delete it->second;
       g_ksk_cache.erase(it);
+    }
+  }
+  if (mb::current_device() != mb::primary_device()) {           // replica of the primary's upload, over NVLink
+    mb200_ksk *src = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      auto it = g_ksk_cache.find(CKey((const void *)key->s, mb::primary_device()));
+      if (it != g_ksk_cache.end() && it->second->print == print) src = it->second;
+    }
+    if (src) {
+      mb200_ksk *k = ksk_alloc(src->p);
+      k->print = print;
+      cudaStream_t st = mb::default_stream();
+      MB_CHECK(cudaMemcpyPeerAsync(k->d, mb::current_device(), src->d, mb::primary_device(),
+                                   sizeof(u64) * ksk_rows(src->p) * src->row_stride, st));
+      MB_CHECK(cudaStreamSynchronize(st));
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_ksk_cache[ck((const void *)key->s)] = k;
+      return k;
     }
   }
   mb::Params p{};
@@ -411,7 +450,7 @@ mb200_ksk *lookup_ksk(TLWE_KS_Key key, int n_in_expected) {
   mb200_ksk *k = ksk_from_host_array(p, flat.data());
   k->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_ksk_cache[(const void *)key->s] = k;
+  g_ksk_cache[ck((const void *)key->s)] = k;
   (void)n_in_expected;
   return k;
 }
@@ -422,7 +461,7 @@ GkskDev *lookup_gksk(Generic_KS_Key key) {
   const unsigned long long print = gksk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_gksk_cache.find((const void *)key->s);
+    auto it = g_gksk_cache.find(ck((const void *)key->s));
     if (it != g_gksk_cache.end()) {
       if (it->second->print == print) return it->second;
       cudaFree(it->second->d);
@@ -477,7 +516,7 @@ GkskDev *lookup_gksk(Generic_KS_Key key) {
   MB_CHECK(cudaMemcpyAsync(g->d, flat.data(), sizeof(u64) * flat.size(), cudaMemcpyHostToDevice, st));
   MB_CHECK(cudaStreamSynchronize(st));
   std::lock_guard<std::mutex> lk(g_mu);
-  g_gksk_cache[(const void *)key->s] = g;
+  g_gksk_cache[ck((const void *)key->s)] = g;
   return g;
 }
 
@@ -592,7 +631,7 @@ UbskDev *lookup_ubsk(Bootstrap_Key key) {
   const unsigned long long print = ubsk_print(key);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ubsk_cache.find((const void *)key->su);
+    auto it = g_ubsk_cache.find(ck((const void *)key->su));
     if (it != g_ubsk_cache.end()) {
       if (it->second->print == print) return it->second;
       cudaFree(it->second->d);
@@ -603,7 +642,7 @@ UbskDev *lookup_ubsk(Bootstrap_Key key) {
   UbskDev *U = ubsk_upload(key->su, key->n, key->unfolding, key->k, key->N, key->l, key->Bg_bit);
   U->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_ubsk_cache[(const void *)key->su] = U;
+  g_ubsk_cache[ck((const void *)key->su)] = U;
   return U;
 }
 
@@ -759,6 +798,70 @@ void parallel_for(int count, F body) {
   pool.wait(g);
 }
 
+// ---- multi-GPU mode inside the library ------------------------------------------------------------------------
+// mb200_init_multi(ndev) starts one host worker thread per device, each bound to its device with its own stream and
+// staging buffers (all per-thread state above is per worker).  The batched drop-in entry points then cut a batch into
+// contiguous shards -- the first count % ndev devices get one ciphertext more, as sharding.shard_bounds on the Python side --
+// and every worker runs the single-device path on its shard.  Keys are uploaded once on the primary device and replicated
+// to the others over NVLink with cudaMemcpyPeer; there is no communication in the steady state.
+struct DevWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+};
+int g_ndev = 1;
+std::vector<DevWorker *> g_workers;
+thread_local bool t_in_worker = false;
+
+void worker_loop(DevWorker *w, int dev) {
+  mb::bind_thread_to_device(dev);
+  t_in_worker = true;
+  (void)mb::default_stream();
+  for (;;) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> lk(w->m);
+      w->cv.wait(lk, [&] { return !w->q.empty(); });
+      job = std::move(w->q.front());
+      w->q.pop_front();
+    }
+    job();
+  }
+}
+bool multi_active(int count) { return g_ndev > 1 && !t_in_worker && count >= 2 * g_ndev; }
+// body(lo, hi) on every device's worker over its contiguous shard of [0, count)
+template <class F>
+void run_sharded(int count, F body) {
+  HostPool::Group g;
+  const int base = count / g_ndev, extra = count % g_ndev;
+  int b = 0;
+  for (int d = 0; d < g_ndev; ++d) {
+    const int e = b + base + (d < extra ? 1 : 0);
+    if (e > b) {
+      { std::lock_guard<std::mutex> lk(g.m); ++g.pending; }
+      DevWorker *w = g_workers[d];
+      const int lo = b, hi = e;
+      {
+        std::lock_guard<std::mutex> lk(w->m);
+        w->q.push_back([=, &g] {
+          body(lo, hi);
+          std::lock_guard<std::mutex> lk2(g.m);
+          --g.pending;
+          g.cv.notify_all();
+        });
+      }
+      w->cv.notify_one();
+    }
+    b = e;
+  }
+  std::unique_lock<std::mutex> lk(g.m);
+  g.cv.wait(lk, [&] { return g.pending == 0; });
+}
+// f() on every device's worker (key replication, shutdown)
+template <class F>
+void run_on_all_devices(F f) { run_sharded(g_ndev, [=](int, int) { f(); }); }
+
 void gather_tlwe(u64 *dst, TLWE *in, int count, int n) {
   for (int i = 0; i < count; ++i)
     MB_REQUIRE(in[i]->n == n, "TLWE %d has dimension %d, expected %d", i, in[i]->n, n);
@@ -818,6 +921,16 @@ PbsStaged stage_pbs_inputs(TRLWE *tv, int tv_count, TLWE *in, const mb::Params &
   return PbsStaged{d_in, d_tv};
 }
 
+// releases the resident copies on EVERY device
+template <class Map, class Free>
+static void erase_all_devices(Map &cache, const void *ptr, Free free_entry) {
+  for (int d = 0; d < mb::MB_MAX_DEV; ++d) {
+    auto it = cache.find(CKey(ptr, d));
+    if (it == cache.end()) continue;
+    free_entry(it->second);
+    cache.erase(it);
+  }
+}
 }  // namespace
 
 // ===================================================================================================
@@ -832,7 +945,43 @@ int mb200_init(int device) {
   return 0;
 }
 
-void mb200_device_synchronize(void) { mb::ensure_init(); MB_CHECK(cudaDeviceSynchronize()); }
+void mb200_device_synchronize(void) {
+  if (g_ndev > 1 && !t_in_worker) { run_on_all_devices([] { MB_CHECK(cudaDeviceSynchronize()); }); return; }
+  mb::ensure_init();
+  MB_CHECK(cudaDeviceSynchronize());
+}
+
+/* Multi-GPU mode: the batched drop-in entry points shard their batch over devices 0 .. ndev-1 (ndev <= 0: all visible).
+ * One host worker thread per device; keys are replicated at mb200_register_* (or on first use).  Returns the number of
+ * devices in use.  Call once, before the first batched call. */
+int mb200_init_multi(int ndev) {
+  const int avail = mb::device_count_noabort();
+  MB_REQUIRE(avail > 0, "no CUDA device visible: this library has no CPU fallback (B200 / sm_100a required)");
+  if (ndev <= 0 || ndev > avail) ndev = avail;
+  if (ndev > mb::MB_MAX_DEV) ndev = mb::MB_MAX_DEV;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_workers.empty()) return g_ndev;                       // already started
+  mb::init_device(0);
+  for (int a = 0; a < ndev; ++a) {                             // NVLink peer access for the key replication
+    MB_CHECK(cudaSetDevice(a));
+    for (int b = 0; b < ndev; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      MB_CHECK(cudaDeviceCanAccessPeer(&can, a, b));
+      if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(b, 0); if (e != cudaSuccess) cudaGetLastError(); }
+    }
+  }
+  MB_CHECK(cudaSetDevice(0));
+  for (int d = 0; d < ndev; ++d) {
+    DevWorker *w = new DevWorker();
+    w->th = std::thread(worker_loop, w, d);
+    w->th.detach();
+    g_workers.push_back(w);
+  }
+  g_ndev = ndev;
+  return g_ndev;
+}
+int mb200_multi_device_count(void) { return g_ndev; }
 
 void mb200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -864,33 +1013,25 @@ void mb200_host_slot_exponents(int layout, int N, int32_t *e_out) {
 }
 
 void mb200_register_bootstrap_key(Bootstrap_Key key) {
-  if (key && key->unfolding > 1) (void)lookup_ubsk(key);
-  else (void)lookup_bsk(key);
+  if (key && key->unfolding > 1) { (void)lookup_ubsk(key); return; }
+  (void)lookup_bsk(key);
+  // multi-GPU mode: replicate to every device now (NVLink peer copies from the primary's upload)
+  if (g_ndev > 1 && !t_in_worker) run_on_all_devices([=] { (void)lookup_bsk(key); });
 }
 void mb200_release_bootstrap_key(Bootstrap_Key key) {
+  if (!key) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  if (key->unfolding > 1) {
-    auto iu = g_ubsk_cache.find((const void *)key->su);
-    if (iu == g_ubsk_cache.end()) return;
-    cudaFree(iu->second->d);
-    delete iu->second;
-    g_ubsk_cache.erase(iu);
-    return;
-  }
-  auto it = g_bsk_cache.find((const void *)key->s);
-  if (it == g_bsk_cache.end()) return;
-  if (it->second->owned) cudaFree(it->second->d);
-  delete it->second;
-  g_bsk_cache.erase(it);
+  if (key->unfolding > 1) erase_all_devices(g_ubsk_cache, (const void *)key->su, [](UbskDev *u) { cudaFree(u->d); delete u; });
+  else erase_all_devices(g_bsk_cache, (const void *)key->s, [](mb200_bsk *b) { free_bsk_obj(b); });
 }
-void mb200_register_ks_key(TLWE_KS_Key key) { (void)lookup_ksk(key, 0); }
+void mb200_register_ks_key(TLWE_KS_Key key) {
+  (void)lookup_ksk(key, 0);
+  if (g_ndev > 1 && !t_in_worker) run_on_all_devices([=] { (void)lookup_ksk(key, 0); });
+}
 void mb200_release_ks_key(TLWE_KS_Key key) {
+  if (!key) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_ksk_cache.find((const void *)key->s);
-  if (it == g_ksk_cache.end()) return;
-  if (it->second->owned) cudaFree(it->second->d);
-  delete it->second;
-  g_ksk_cache.erase(it);
+  erase_all_devices(g_ksk_cache, (const void *)key->s, [](mb200_ksk *k) { if (k->owned) cudaFree(k->d); delete k; });
 }
 
 // ---- flat API --------------------------------------------------------------------------------------
@@ -1133,6 +1274,13 @@ void mb200_set_kernel_policy(int policy) { g_policy = policy; }
 void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key,
                                            int torus_base, int count) {
   if (count <= 0) return;
+  if (multi_active(count)) {
+    if (key && key->unfolding == 1) (void)lookup_bsk(key);
+    run_sharded(count, [=](int lo, int hi) {
+      functional_bootstrap_wo_extract_batch(out + lo, tv_count > 1 ? tv + lo : tv, tv_count > 1 ? hi - lo : 1, in + lo, key, torus_base, hi - lo);
+    });
+    return;
+  }
   const AnyBsk bk = lookup_any_bsk(key);
   const mb::Params &p = bk.p();
   cudaStream_t st = mb::default_stream();
@@ -1148,6 +1296,13 @@ void functional_bootstrap_wo_extract_batch(TRLWE *out, TRLWE *tv, int tv_count, 
 static void fb_batch_impl(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, Bootstrap_Key key, int torus_base, int count,
                           int preprocess, int kappa, int theta) {
   if (count <= 0) return;
+  if (multi_active(count)) {
+    if (key && key->unfolding == 1) (void)lookup_bsk(key);
+    run_sharded(count, [=](int lo, int hi) {
+      fb_batch_impl(out + lo, tv_count > 1 ? tv + lo : tv, tv_count > 1 ? hi - lo : 1, in + lo, key, torus_base, hi - lo, preprocess, kappa, theta);
+    });
+    return;
+  }
   const AnyBsk bk = lookup_any_bsk(key);
   const mb::Params &p = bk.p();
   cudaStream_t st = mb::default_stream();
@@ -1173,6 +1328,11 @@ void programmable_bootstrap_batch(TLWE *out, TRLWE *tv, int tv_count, TLWE *in, 
 
 void tlwe_keyswitch_batch(TLWE *out, TLWE *in, TLWE_KS_Key ks_key, int count) {
   if (count <= 0) return;
+  if (multi_active(count)) {
+    (void)lookup_ksk(ks_key, 0);
+    run_sharded(count, [=](int lo, int hi) { tlwe_keyswitch_batch(out + lo, in + lo, ks_key, hi - lo); });
+    return;
+  }
   mb200_ksk *ksk = lookup_ksk(ks_key, in[0]->n);
   const mb::Params &p = ksk->p;
   const int n_in = p.k * p.N;
@@ -1195,6 +1355,15 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
                                           TLWE_KS_Key ks_key, int torus_base, int count) {
   if (count <= 0) return;
   MB_REQUIRE(tv_count == 1 || tv_count == count, "tv_count must be 1 or count");
+  if (multi_active(count)) {                                    // contiguous shards, one device worker each
+    if (key && key->unfolding == 1) (void)lookup_bsk(key);      // the primary's upload first: the others copy it over NVLink
+    (void)lookup_ksk(ks_key, 0);
+    run_sharded(count, [=](int lo, int hi) {
+      functional_bootstrap_keyswitch_batch(out + lo, tv_count > 1 ? tv + lo : tv, tv_count > 1 ? hi - lo : 1, in + lo, key, ks_key,
+                                           torus_base, hi - lo);
+    });
+    return;
+  }
   mb200_bsk *bsk = lookup_bsk(key);
   mb200_ksk *ksk = lookup_ksk(ks_key, bsk->p.k * bsk->p.N);
   const mb::Params &p = bsk->p;
@@ -1610,7 +1779,7 @@ static mb200_bsk *lookup_rksk(TRLWE_KS_Key key) {
   const unsigned long long print = rksk_print(key, nullptr);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_rksk_cache.find((const void *)key->s);
+    auto it = g_rksk_cache.find(ck((const void *)key->s));
     if (it != g_rksk_cache.end()) {
       if (it->second->print == print) return it->second;
       free_bsk_obj(it->second);
@@ -1620,7 +1789,7 @@ static mb200_bsk *lookup_rksk(TRLWE_KS_Key key) {
   mb200_bsk *b = rksk_build(key, nullptr);
   b->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_rksk_cache[(const void *)key->s] = b;
+  g_rksk_cache[ck((const void *)key->s)] = b;
   return b;
 }
 static mb200_bsk *lookup_rksk_pair(TRLWE_KS_Key *keys) {
@@ -1628,7 +1797,7 @@ static mb200_bsk *lookup_rksk_pair(TRLWE_KS_Key *keys) {
   const unsigned long long print = rksk_print(keys[0], keys[1]);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_rksk_cache.find((const void *)keys);
+    auto it = g_rksk_cache.find(ck((const void *)keys));
     if (it != g_rksk_cache.end()) {
       if (it->second->print == print) return it->second;
       free_bsk_obj(it->second);
@@ -1638,7 +1807,7 @@ static mb200_bsk *lookup_rksk_pair(TRLWE_KS_Key *keys) {
   mb200_bsk *b = rksk_build(keys[0], keys[1]);
   b->print = print;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_rksk_cache[(const void *)keys] = b;
+  g_rksk_cache[ck((const void *)keys)] = b;
   return b;
 }
 // mode 1: trlwe_keyswitch, mode 2: trlwe_priv_keyswitch_2; d_out may alias d_in
@@ -1773,7 +1942,7 @@ void blind_rotate_unfolded_batch(TRLWE *tv, Torus **a, TRGSW *s, int size, int u
   bool temporary = false;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ubsk_cache.find((const void *)s);
+    auto it = g_ubsk_cache.find(ck((const void *)s));
     if (it != g_ubsk_cache.end()) U = it->second;
   }
   if (!U) { U = ubsk_upload(s, size, unfolding, k, N, s[0]->l, s[0]->Bg_bit); temporary = true; }
@@ -2002,10 +2171,7 @@ void mb200_register_trlwe_ks_key(TRLWE_KS_Key key) { (void)lookup_rksk(key); }
 void mb200_register_trlwe_priv_ks_key(TRLWE_KS_Key *keys) { (void)lookup_rksk_pair(keys); }
 static void release_rksk(const void *cache_key) {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_rksk_cache.find(cache_key);
-  if (it == g_rksk_cache.end()) return;
-  mb200_bsk_free(it->second);
-  g_rksk_cache.erase(it);
+  erase_all_devices(g_rksk_cache, cache_key, [](mb200_bsk *b) { free_bsk_obj(b); });
 }
 void mb200_release_trlwe_ks_key(TRLWE_KS_Key key) { if (key) release_rksk((const void *)key->s); }
 void mb200_release_trlwe_priv_ks_key(TRLWE_KS_Key *keys) { release_rksk((const void *)keys); }
@@ -2024,12 +2190,9 @@ void mb200_circuit_bootstrap_variant_dev(int variant, mb200_bsk_t bsk, mb200_gks
 }
 void mb200_register_generic_ks_key(Generic_KS_Key key) { (void)lookup_gksk(key); }
 void mb200_release_generic_ks_key(Generic_KS_Key key) {
+  if (!key) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_gksk_cache.find((const void *)key->s);
-  if (it == g_gksk_cache.end()) return;
-  cudaFree(it->second->d);
-  delete it->second;
-  g_gksk_cache.erase(it);
+  erase_all_devices(g_gksk_cache, (const void *)key->s, [](GkskDev *g) { cudaFree(g->d); delete g; });
 }
 void trlwe_extract_tlwe_addto(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_acc_batch(&out, &in, &idx, 1, +1, 1); }
 void trlwe_extract_tlwe_subto(TLWE out, TRLWE in, int idx) { trlwe_extract_tlwe_acc_batch(&out, &in, &idx, 1, -1, 1); }

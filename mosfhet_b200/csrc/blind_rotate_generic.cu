@@ -247,7 +247,8 @@ void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st) {
   const size_t smem = generic_smem_bytes(p.N, p.k, rb);
   MB_REQUIRE(smem <= limit, "generic blind rotate: (k+1)*N = %d does not fit in shared memory (%zu B needed)",
              (p.k + 1) * p.N, smem);
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -33,12 +33,12 @@ namespace mb {
 
 // ---- per-N tables ------------------------------------------------------------------------------
 static std::mutex g_k1_mu;
-static std::map<int, double2 *> g_k1_tab;
+static std::map<long long, double2 *> g_k1_tab;     // (device, N) -> table
 
 const double2 *k1_tables_for(int N) {
   ensure_init();
   std::lock_guard<std::mutex> lk(g_k1_mu);
-  auto it = g_k1_tab.find(N);
+  auto it = g_k1_tab.find(dev_key(N));
   if (it != g_k1_tab.end()) return it->second;
   const int M = N / 2, S = M / 16, R2 = M / 128;
   std::vector<double2> h((size_t)16 * S + (size_t)R2 * 8);
@@ -58,7 +58,7 @@ const double2 *k1_tables_for(int N) {
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * h.size()));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
   MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
-  g_k1_tab[N] = d;
+  g_k1_tab[dev_key(N)] = d;
   return d;
 }
 
@@ -110,7 +110,8 @@ template <int LOGM, int L, int LB, int MINB, bool PKALL, int PF>
 static void launch_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1 kernel: %zu B of shared memory needed (blind rotation too long)", smem);
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, MINB, PKALL, PF>,

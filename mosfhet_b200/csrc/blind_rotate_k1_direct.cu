@@ -19,7 +19,8 @@ template <int LOGM, int L, int LB, bool PKALL>
 static void launch_direct_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + 16;
-  static bool configured = false;
+  static bool configured_dev[MB_MAX_DEV] = {false};        // function attributes are per device
+  bool &configured = configured_dev[current_device()];
   if (!configured) {
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1_kernel<LOGM, L, LB, 1, PKALL, 0, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

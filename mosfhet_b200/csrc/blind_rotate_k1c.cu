@@ -307,7 +307,8 @@ template <int LOGM, int L>
 static void launch_k1c_one(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * M * 8 + (size_t)L * M * 16 + (size_t)2 * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1c kernel: %zu B of shared memory needed (blind rotation too long)", smem);
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1c_kernel<LOGM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -253,12 +253,12 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, MINB) blind_rotate_k1h_kernel
 
 // ---- tables: TA[8][S] then TB[R2][8], S = M/8 -------------------------------------------------------
 static std::mutex g_k1h_mu;
-static std::map<int, double2 *> g_k1h_tab;
+static std::map<long long, double2 *> g_k1h_tab;     // (device, N) -> table
 
 static const double2 *k1h_tables_for(int N) {
   ensure_init();
   std::lock_guard<std::mutex> lk(g_k1h_mu);
-  auto it = g_k1h_tab.find(N);
+  auto it = g_k1h_tab.find(dev_key(N));
   if (it != g_k1h_tab.end()) return it->second;
   const int M = N / 2, S = M / 8, R2 = M / 64;
   std::vector<double2> h((size_t)8 * S + (size_t)R2 * 8);
@@ -276,7 +276,7 @@ static const double2 *k1h_tables_for(int N) {
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * h.size()));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
   MB_CHECK(cudaDeviceSynchronize());
-  g_k1h_tab[N] = d;
+  g_k1h_tab[dev_key(N)] = d;
   return d;
 }
 
@@ -284,7 +284,8 @@ template <int LOGM, int L, int LB, int MINB>
 static void launch_h(const K1Args &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.size * 2 + 15) & ~(size_t)15);
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1h kernel: %zu B of shared memory needed", smem);
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1h_kernel<LOGM, L, LB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -531,12 +531,12 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
 
 // ---- tables: TA[RA][64] then TC[16][4] -----------------------------------------------------------------------------
 static std::mutex g_k1q_mu;
-static std::map<int, double2 *> g_k1q_tab;
+static std::map<long long, double2 *> g_k1q_tab;     // (device, N) -> table
 
 static const double2 *k1q_tables_for(int N) {
   ensure_init();
   std::lock_guard<std::mutex> lk(g_k1q_mu);
-  auto it = g_k1q_tab.find(N);
+  auto it = g_k1q_tab.find(dev_key(N));
   if (it != g_k1q_tab.end()) return it->second;
   const int M = N / 2, RA = M / 64;
   std::vector<double2> h((size_t)RA * 64 + 64);
@@ -555,7 +555,7 @@ static const double2 *k1q_tables_for(int N) {
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * h.size()));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
   MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
-  g_k1q_tab[N] = d;
+  g_k1q_tab[dev_key(N)] = d;
   return d;
 }
 
@@ -563,7 +563,8 @@ template <int LOGM, int L, int LB, bool PKALL, bool KPF>
 static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.a.size * 2 + 15) & ~(size_t)15);
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1q kernel: %zu B of shared memory needed (blind rotation too long)", smem);
     MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, KPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -65,9 +65,15 @@ const double2 *k1_tables_for(int N);
 void count_launch(int n = 1);
 
 // ---- context ----------------------------------------------------------------------------------
-void ensure_init();
-cudaStream_t default_stream();
+constexpr int MB_MAX_DEV = 16;
+void ensure_init();                 // cudaSetDevice(device of this host thread)
+cudaStream_t default_stream();      // this host thread's stream on its device
 int sm_count();
+int current_device();               // device of this host thread (the primary unless bound elsewhere)
+int primary_device();
+void bind_thread_to_device(int device);
+// key of per-device caches: (device, n)
+inline long long dev_key(int n) { return ((long long)current_device() << 32) | (long long)(unsigned)n; }
 
 // ---- kernels' host-side launchers ---------------------------------------------------------------
 struct BlindRotateLaunch {

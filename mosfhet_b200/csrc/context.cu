@@ -10,10 +10,15 @@
 namespace mb {
 
 static std::mutex g_mu;
-static int g_device = -1;
-static int g_sm_count = 0;
+// Devices.  mb200_init selects the PRIMARY device; a host thread works on the primary unless it has been bound to another
+// one (the per-device workers of the multi-GPU mode, api.cu).  Everything that lives on a device -- streams, twiddle
+// tables, kernel attributes, resident keys -- is kept per device.
+static int g_primary = -1;
+static thread_local int t_device = -1;
+static int g_sm_count[MB_MAX_DEV] = {0};
+static bool g_dev_ready[MB_MAX_DEV] = {false};
 static std::atomic<unsigned long long> g_launches{0};
-static std::map<int, double2 *> g_tw;
+static std::map<long long, double2 *> g_tw;            // (device << 32 | N) -> table
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 unsigned long long launches() { return g_launches.load(); }
@@ -26,49 +31,59 @@ int device_count_noabort() {
   return n;
 }
 
-void init_device(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+static void prepare_device(int device) {               // g_mu held
   const int n = device_count_noabort();
   MB_REQUIRE(n > 0, "no CUDA device visible: this library has no CPU fallback (B200 / sm_100a required)");
-  if (device < 0) device = 0;
-  MB_REQUIRE(device < n, "device %d requested but only %d visible", device, n);
+  MB_REQUIRE(device >= 0 && device < n && device < MB_MAX_DEV, "device %d requested but only %d visible", device, n);
   MB_CHECK(cudaSetDevice(device));
+  if (g_dev_ready[device]) return;
   cudaDeviceProp prop;
   MB_CHECK(cudaGetDeviceProperties(&prop, device));
   MB_REQUIRE(prop.major >= 10, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
-  if (g_device != device) {
-    // tables live on one device; switching devices drops them
-    for (auto &kv : g_tw) cudaFree(kv.second);
-    g_tw.clear();
-  }
-  g_device = device;
-  g_sm_count = prop.multiProcessorCount;
+  g_sm_count[device] = prop.multiProcessorCount;
+  g_dev_ready[device] = true;
 }
 
+void init_device(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device < 0) device = 0;
+  prepare_device(device);
+  g_primary = device;
+}
+
+// binds the calling host thread to `device` (>= 0) or back to the primary (-1)
+void bind_thread_to_device(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device >= 0) prepare_device(device);
+  t_device = device;
+}
+
+int current_device() { return t_device >= 0 ? t_device : g_primary; }
+int primary_device() { return g_primary; }
+
 void ensure_init() {
-  if (g_device >= 0) { MB_CHECK(cudaSetDevice(g_device)); return; }
+  const int d = current_device();
+  if (d >= 0) { MB_CHECK(cudaSetDevice(d)); return; }
   init_device(0);
 }
 
-int current_device() { return g_device; }
-int sm_count() { ensure_init(); return g_sm_count; }
+int sm_count() { ensure_init(); return g_sm_count[current_device()]; }
 
-struct ThreadStream {
-  cudaStream_t s = nullptr;
-  ~ThreadStream() { /* leaked deliberately at thread exit: the context may already be gone */ }
-};
-static thread_local ThreadStream t_stream;
+// one stream per (host thread, device), leaked deliberately at thread exit: the context may already be gone
+static thread_local cudaStream_t t_stream[MB_MAX_DEV] = {nullptr};
 
 cudaStream_t default_stream() {
   ensure_init();
-  if (!t_stream.s) MB_CHECK(cudaStreamCreateWithFlags(&t_stream.s, cudaStreamNonBlocking));
-  return t_stream.s;
+  cudaStream_t &s = t_stream[current_device()];
+  if (!s) MB_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
 }
 
 const double2 *twiddles_for(int N) {
   ensure_init();
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_tw.find(N);
+  const long long key = ((long long)current_device() << 32) | (long long)N;
+  auto it = g_tw.find(key);
   if (it != g_tw.end()) return it->second;
   std::vector<double2> h(N);
   for (int j = 0; j < N; ++j) {
@@ -80,7 +95,7 @@ const double2 *twiddles_for(int N) {
   MB_CHECK(cudaMalloc(&d, sizeof(double2) * N));
   MB_CHECK(cudaMemcpy(d, h.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
   MB_CHECK(cudaDeviceSynchronize());   // pageable H2D + non-blocking compute streams: fence once
-  g_tw[N] = d;
+  g_tw[key] = d;
   return d;
 }
 

@@ -10,7 +10,8 @@ namespace mb {
 // folded 64-bit immediates cost two UMOV each time they are rematerialised (ncu: 184 UMOV per step).
 static __constant__ double CW64C[64], CW64S[64];   // one copy per translation unit
 static void upload_w64() {
-  static bool done = false;
+  static bool done_dev[MB_MAX_DEV] = {false};          // __constant__ memory is per device
+  bool &done = done_dev[current_device()];
   if (done) return;
   MB_CHECK(cudaMemcpyToSymbol(CW64C, W64C_HOST, sizeof(double) * 64));
   MB_CHECK(cudaMemcpyToSymbol(CW64S, W64S_HOST, sizeof(double) * 64));

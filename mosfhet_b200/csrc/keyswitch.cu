@@ -138,7 +138,8 @@ static void launch_ks_nv(TableKsArgs A, cudaStream_t st) {
   if (per > KS_MAX_WARPS) per = KS_MAX_WARPS;
   A.per_cta = per;
   const int grid = (vcount + per - 1) / per;
-  static bool configured = false;
+  static bool configured_dev[MB_MAX_DEV] = {false};        // function attributes are per device
+  bool &configured = configured_dev[current_device()];
   if (!configured) {
     // no shared memory needed: give the whole unified array to L1, which is what shares rows between warps
     MB_CHECK(cudaFuncSetAttribute(keyswitch_warp_kernel<NV, CHUNKED>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));

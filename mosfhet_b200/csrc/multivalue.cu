@@ -125,7 +125,8 @@ void launch_mv_phase2(u64 *out, const int *d_lut, int lut_count, const u64 *rot,
   const int threads = 1024;
   MB_REQUIRE(k * N + 1 <= threads * 8, "multivalue phase 2: k*N = %d too large", k * N);
   const size_t smem = sizeof(u64) * (k + 1) * N;
-  static size_t configured = 0;
+  static size_t configured_dev[MB_MAX_DEV] = {0};          // function attributes are per device
+  size_t &configured = configured_dev[current_device()];
   if (smem > 48 * 1024 && smem > configured) {
     MB_CHECK(cudaFuncSetAttribute(mv_phase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -59,4 +59,14 @@ for v in avx512 fma portable; do
     fi
   fi
 done
+# The reference's own benchmark build (Makefile.def:2-6: -O3 -fwhole-program -flto, all sources in one program) as a second
+# CPU variant of the timing driver, with the same explicit ISA level instead of -march=native.
+exe="$OUT/ref_bench_avx512_lto"
+if [ -f "$HERE/ref_bench.c" ] && { [ ! -f "$exe" ] || [ "$HERE/ref_bench.c" -nt "$exe" ] || [ "$0" -nt "$exe" ]; }; then
+  echo "build_ref: $exe"
+  gcc -O3 -fwhole-program -flto -g0 -w -funroll-all-loops -I"$REF/include" \
+    -march=x86-64-v4 -mvaes -maes -mrdrnd -mpclmul -DUSE_SPQLIOS -DAVX512_OPT -DUSE_COMPRESSED_TRLWE -DVAES_OPT \
+    $COMMON_SRC $S/trlwe_compressed_vaes.c $S/rnd/aes_rng.c $SPQ/spqlios-fft-avx512.s $SPQ/spqlios-ifft-avx512.s \
+    $SPQ/spqlios-fft-impl-avx512.c $SPQ/fft_processor_spqlios.c "$HERE/ref_bench.c" -lpthread -lm -o "$exe"
+fi
 echo "build_ref: done"
