@@ -3,6 +3,7 @@
 // Host-side logic only: handle-tree gather/scatter, staging, dispatch.  No CPU compute path.
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -1374,6 +1375,13 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
     MB_REQUIRE(out[i]->n == p.n, "output TLWE %d has dimension %d, expected %d", i, out[i]->n, p.n);      // tlwe.c:293
   }
   cudaStream_t st = mb::default_stream();
+  static const bool trace = getenv("MB200_TRACE") != nullptr;   // host-side timeline of this call on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what, int c) {
+    if (!trace) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(stderr, "[mb200 trace] %8.3f ms  %s %d\n", ms, what, c);
+  };
   const int w_in = p.n + 1, w_mid = p.k * p.N + 1, W = (p.k + 1) * p.N;
   const size_t in_b = sizeof(u64) * (size_t)count * w_in, tv_b = sizeof(u64) * (size_t)tv_count * W;
   u64 *h_in = (u64 *)t_scratch[S_IN].host(in_b), *d_in = (u64 *)t_scratch[S_IN].dev(in_b);
@@ -1403,11 +1411,13 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   for (int c = 0; c < nchunks; ++c) {
     const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
     pool.wait(gathered[c]);
+    mark("gathered chunk", c);
     MB_CHECK(cudaMemcpyAsync(d_in + (size_t)c0 * w_in, h_in + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyHostToDevice, st));
     pbs_dev_impl(bsk, d_mid + (size_t)c0 * w_mid, 1, d_tv + (tv_count > 1 ? (size_t)c0 * W : 0), tv_count > 1 ? cc : 1,
                  d_in + (size_t)c0 * w_in, torus_base, cc, st);
   }
   mb::launch_keyswitch(ksk, d_out, d_mid, count, st);
+  mark("all launches queued", nchunks);
   std::vector<cudaEvent_t> done(nchunks);
   for (int c = 0; c < nchunks; ++c) {
     const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
@@ -1425,10 +1435,12 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   for (int c = 0; c < nchunks; ++c) {
     const int c0 = c * per, c1 = c0 + per < count ? c0 + per : count;
     MB_CHECK(cudaEventSynchronize(done[c]));
+    mark("results on the host, chunk", c);
     MB_CHECK(cudaEventDestroy(done[c]));
     for (int b = c0; b < c1; b += sub) pool.submit(scattered, [=] { scatter_job(b, b + sub < c1 ? b + sub : c1); });
   }
   pool.wait(scattered);
+  mark("scattered", count);
 }
 
 void blind_rotate_batch(TRLWE *tv, Torus **a, TRGSW_DFT *s, int size, int count) {
