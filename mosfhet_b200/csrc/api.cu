@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 namespace mb {
+cudaStream_t second_stream();
 void init_device(int device);
 int device_count_noabort();
 int current_device();
@@ -1388,11 +1389,15 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
   u64 *d_mid = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * (size_t)count * w_mid);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(in_b), *d_out = (u64 *)t_scratch[S_OUT].dev(in_b);
-  // chunks of whole waves (a wave = resident CTAs of the blind rotation: 4 per SM at N <= 1024, 2 at N = 2048), about 4 per batch
+  // Two chunks on two streams: the first wave of ciphertexts (resident CTAs of the blind rotation: 4 per SM at N <= 1024,
+  // 2 at N = 2048) is flattened, copied and launched at once; the rest is flattened meanwhile and launched on a second
+  // stream, so that its CTAs fill the SMs as the first launch drains.  (Measured with MB200_TRACE, profiles/r2f: flattening
+  // 4096 inputs takes 0.9 ms on the worker pool; four back-to-back launches on ONE stream cost 2.4 ms in drained tails.)
   const int wave = mb::sm_count() * (p.N <= 1024 ? 4 : (p.N <= 2048 ? 2 : 1));
-  int per = ((count + 3) / 4 + wave - 1) / wave * wave;
-  if (count < 2 * wave || tv_count != 1) per = count;           // small batches / per-input test vectors: one chunk
-  const int nchunks = (count + per - 1) / per;
+  int per = wave;
+  if (count < 3 * wave || tv_count != 1) per = count;           // small batches / per-input test vectors: one chunk
+  const int nchunks = per < count ? 2 : 1;
+  cudaStream_t st2 = nchunks > 1 ? mb::second_stream() : st;
   HostPool &pool = HostPool::get();
   std::vector<HostPool::Group> gathered(nchunks);
   const int sub = 256;                                          // gather / scatter job size (ciphertexts)
@@ -1403,24 +1408,38 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
     }
   };
   for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, c1 = c0 + per < count ? c0 + per : count;
+    const int c0 = c * per, c1 = c == nchunks - 1 ? count : c0 + per;
     for (int b = c0; b < c1; b += sub) pool.submit(gathered[c], [=] { gather_job(b, b + sub < c1 ? b + sub : c1); });
   }
   gather_trlwe(h_tv, tv, tv_count, p.k, p.N);
   MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+  cudaEvent_t tv_ready = nullptr, second_done = nullptr;
+  if (nchunks > 1) {
+    MB_CHECK(cudaEventCreateWithFlags(&tv_ready, cudaEventDisableTiming));
+    MB_CHECK(cudaEventCreateWithFlags(&second_done, cudaEventDisableTiming));
+    MB_CHECK(cudaEventRecord(tv_ready, st));
+    MB_CHECK(cudaStreamWaitEvent(st2, tv_ready, 0));
+  }
   for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
+    const int c0 = c * per, cc = (c == nchunks - 1 ? count : c0 + per) - c0;
+    cudaStream_t sc = c == 0 ? st : st2;
     pool.wait(gathered[c]);
     mark("gathered chunk", c);
-    MB_CHECK(cudaMemcpyAsync(d_in + (size_t)c0 * w_in, h_in + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyHostToDevice, st));
+    MB_CHECK(cudaMemcpyAsync(d_in + (size_t)c0 * w_in, h_in + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyHostToDevice, sc));
     pbs_dev_impl(bsk, d_mid + (size_t)c0 * w_mid, 1, d_tv + (tv_count > 1 ? (size_t)c0 * W : 0), tv_count > 1 ? cc : 1,
-                 d_in + (size_t)c0 * w_in, torus_base, cc, st);
+                 d_in + (size_t)c0 * w_in, torus_base, cc, sc);
+  }
+  if (nchunks > 1) {
+    MB_CHECK(cudaEventRecord(second_done, st2));
+    MB_CHECK(cudaStreamWaitEvent(st, second_done, 0));
   }
   mb::launch_keyswitch(ksk, d_out, d_mid, count, st);
   mark("all launches queued", nchunks);
-  std::vector<cudaEvent_t> done(nchunks);
-  for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, cc = (c0 + per < count ? c0 + per : count) - c0;
+  // results come back in a few chunks so that the host scatter of one overlaps the copy of the next
+  const int ochunks = count >= 2048 ? 4 : 1, oper = (count + ochunks - 1) / ochunks;
+  std::vector<cudaEvent_t> done(ochunks);
+  for (int c = 0; c < ochunks; ++c) {
+    const int c0 = c * oper, cc = (c0 + oper < count ? c0 + oper : count) - c0;
     MB_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * w_in, d_out + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyDeviceToHost, st));
     MB_CHECK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
     MB_CHECK(cudaEventRecord(done[c], st));
@@ -1432,13 +1451,14 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
       out[i]->b = h_out[(size_t)i * w_in + w_in - 1];
     }
   };
-  for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, c1 = c0 + per < count ? c0 + per : count;
+  for (int c = 0; c < ochunks; ++c) {
+    const int c0 = c * oper, c1 = c0 + oper < count ? c0 + oper : count;
     MB_CHECK(cudaEventSynchronize(done[c]));
     mark("results on the host, chunk", c);
     MB_CHECK(cudaEventDestroy(done[c]));
     for (int b = c0; b < c1; b += sub) pool.submit(scattered, [=] { scatter_job(b, b + sub < c1 ? b + sub : c1); });
   }
+  if (tv_ready) { MB_CHECK(cudaEventDestroy(tv_ready)); MB_CHECK(cudaEventDestroy(second_done)); }
   pool.wait(scattered);
   mark("scattered", count);
 }

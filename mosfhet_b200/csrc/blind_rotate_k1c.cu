@@ -279,6 +279,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((1 << LOGM) / 8, 1) 
     __syncthreads();
   }
 
+  // every thread is past its last tensor-memory access before the columns are released -- also when every step was
+  // skipped and no step barrier ran
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base_s) : "memory");
   // ---- epilogue: extraction at index 0 (a part from polynomial 0, b from coefficient 0 of polynomial 1) or raw ----
   if (A.extract) {

@@ -79,6 +79,15 @@ cudaStream_t default_stream() {
   return s;
 }
 
+// a second stream of this host thread on its device (overlapping launches of the pipelined entry points)
+static thread_local cudaStream_t t_stream2[MB_MAX_DEV] = {nullptr};
+cudaStream_t second_stream() {
+  ensure_init();
+  cudaStream_t &s = t_stream2[current_device()];
+  if (!s) MB_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
+}
+
 const double2 *twiddles_for(int N) {
   ensure_init();
   std::lock_guard<std::mutex> lk(g_mu);
