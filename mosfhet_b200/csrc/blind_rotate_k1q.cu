@@ -84,9 +84,12 @@ struct K1QArgs {
   unsigned dmask;     // Bg - 1
 };
 
-template <int LOGM, int L, int LB, bool PKALL, bool KPF>
+template <int LOGM, int L, int LB, bool PKALL, int VAR>
 __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blind_rotate_k1q_kernel(const __grid_constant__ K1QArgs Q) {
   const K1Args &A = Q.a;
+  // VAR bit 0 (KPF): pass-C key values pipelined one half row ahead; bit 1 (HYB): two-row phases of pass B mapped to two of
+  // the warps (full radix-16 tasks, block barriers) instead of lane pairs in every warp -- see the two-row branches below
+  constexpr bool KPF = (VAR & 1) != 0, HYB = (VAR & 2) != 0;
   constexpr int M = 1 << LOGM, N = 2 * M, T = M / 4, RA = M / 64, LOGRA = LOGM - 6;
   constexpr int SLOTS = T / 64;                       // pass-A rows in flight: 2 (N = 1024), 4 (N = 2048)
   constexpr int LBO = SLOTS / 2;                      // gadget levels per pass-A round
@@ -361,6 +364,22 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         reg_dif<16>(x);
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) blk[swz_b(pos)] = x[pos];
+      } else if constexpr (HYB) {
+        // Two rows = 2 x M/16 full radix-16 tasks: the first M/64 warps take them (row = task / (M/16)), the others wait at
+        // the block barrier.  No redundant loads and no half-filled FP64 instructions, at the price of two block barriers.
+        __syncwarp();
+        if (t_ < M / 8) {
+          const int rowH = t_ / (M / 16), trH = t_ - rowH * (M / 16), pos1H = trH >> 2, rH = trH & 3, b4H = (pos1H & 1) << 2;
+          auto swz_h = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4H) + (rH ^ ((e >> 1) & 3)); };
+          double2 *blk = buf + rowH * M + pos1H * 64;
+          double2 x[16];
+#pragma unroll
+          for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[swz_h(m2)];
+          reg_dif<16>(x);
+#pragma unroll
+          for (int pos = 0; pos < 16; ++pos) blk[swz_h(pos)] = x[pos];
+        }
+        __syncthreads();
       } else {
         // Two rows = 16 radix-16 tasks per warp: each is split over the lane pair (lane, lane + 16) instead of leaving half
         // the warp idle (idle lanes still occupy the FP64 pipe: +12 % FP64 instructions, profiles/r2b).  Both lanes read
@@ -447,9 +466,25 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         for (int r = 1; r < 4; ++r) row[r ^ cxor] = cmul_conj(fa[o][r], twc[r]);
       }
     }
+    if constexpr (HYB) {
+      // the LAST M/64 warps take the 2 x M/16 inverse tasks (the first ones took the forward two-row phase)
+      __syncthreads();
+      if (t_ >= T - M / 8) {
+        const int th = t_ - (T - M / 8);
+        const int rowH = th / (M / 16), trH = th - rowH * (M / 16), pos1H = trH >> 2, rH = trH & 3, b4H = (pos1H & 1) << 2;
+        auto swz_h = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4H) + (rH ^ ((e >> 1) & 3)); };
+        double2 *blk = buf + rowH * M + pos1H * 64;
+        double2 x[16];
+#pragma unroll
+        for (int pos = 0; pos < 16; ++pos) x[pos] = blk[swz_h(pos)];
+        reg_dit_inv<16>(x);
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) blk[swz_h(m2)] = x[m2];
+      }
+    }
     __syncwarp();
     // ---------------------------------- B' (per warp, own blocks) -----------------------------------------------------
-    {
+    if constexpr (!HYB) {
       // the mirror image of the split above: lane half h inverts the even (h = 0) / odd (h = 1) frequencies with a radix-8
       // DIT, the odd half applies conj(W_16^j), the lane pair swaps its 8 values and lane h forms outputs j + 8h = E_j +- O_j
       double2 *blk = buf + rowB2 * M + pos1B * 64;
@@ -559,7 +594,7 @@ static const double2 *k1q_tables_for(int N) {
   return d;
 }
 
-template <int LOGM, int L, int LB, bool PKALL, bool KPF>
+template <int LOGM, int L, int LB, bool PKALL, int VAR>
 static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   constexpr int M = 1 << LOGM;
   const size_t smem = (size_t)2 * 2 * M * 8 + (size_t)2 * LB * M * 16 + (((size_t)a.a.size * 2 + 15) & ~(size_t)15);
@@ -567,15 +602,15 @@ static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   size_t &configured = configured_dev[current_device()];
   if (smem > configured) {
     MB_REQUIRE(smem <= 227 * 1024, "k1q kernel: %zu B of shared memory needed (blind rotation too long)", smem);
-    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, KPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CHECK(cudaFuncSetAttribute(blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, KPF><<<count, M / 4, smem, st>>>(a);
+  blind_rotate_k1q_kernel<LOGM, L, LB, PKALL, VAR><<<count, M / 4, smem, st>>>(a);
   MB_CHECK(cudaGetLastError());
   count_launch();
 }
 
-constexpr bool K1Q_KPF = true;    // default pass-C key schedule (see the kernel)
+constexpr int K1Q_VAR = 1;    // default variant bits (see the kernel): key pipelining on, lane-pair split of the two-row phases
 
 // levels per shared-memory batch: 2 when two levels' digits fit the 32-bit packed word, else 1
 static int k1q_lb(int l, int Bg_bit) { return (l >= 2 && 2 * Bg_bit <= 32) ? 2 : 1; }
@@ -606,15 +641,18 @@ void launch_blind_rotate_k1q(const BlindRotateLaunch &b, cudaStream_t st) {
   a.Bg_bit = p.Bg_bit; a.count = b.count;
   const int logm = ilog2i(p.N) - 1, lb = k1q_lb(p.l, p.Bg_bit);
   const bool pkall = p.l * p.Bg_bit <= 32;
-  // experiment knob (benchmark shapes only): MB200_K1Q_KPF=0/1 selects the pass-C key schedule
-  if (const char *e = getenv("MB200_K1Q_KPF")) {
-    const bool kpf = e[0] == '1';
-    if (kpf != K1Q_KPF && logm == 9 && p.l == 3 && lb == 2 && pkall) { launch_q<9, 3, 2, true, !K1Q_KPF>(qa, b.count, st); return; }
-    if (kpf != K1Q_KPF && logm == 10 && p.l == 4 && lb == 2 && !pkall) { launch_q<10, 4, 2, false, !K1Q_KPF>(qa, b.count, st); return; }
+  // experiment knob (benchmark shapes only): MB200_K1Q_VAR = variant bits
+  if (const char *e = getenv("MB200_K1Q_VAR")) {
+    const int var = atoi(e);
+#define MB_K1Q_VARCASE(V_) \
+    if (var == V_ && var != K1Q_VAR && logm == 9 && p.l == 3 && lb == 2 && pkall) { launch_q<9, 3, 2, true, V_>(qa, b.count, st); return; } \
+    if (var == V_ && var != K1Q_VAR && logm == 10 && p.l == 4 && lb == 2 && !pkall) { launch_q<10, 4, 2, false, V_>(qa, b.count, st); return; }
+    MB_K1Q_VARCASE(0) MB_K1Q_VARCASE(1) MB_K1Q_VARCASE(2) MB_K1Q_VARCASE(3)
+#undef MB_K1Q_VARCASE
   }
 #define MB_K1Q_CASE(LM, LL, LBB) \
   if (logm == LM && p.l == LL && lb == LBB) { \
-    if (pkall) launch_q<LM, LL, LBB, true, K1Q_KPF>(qa, b.count, st); else launch_q<LM, LL, LBB, false, K1Q_KPF>(qa, b.count, st); \
+    if (pkall) launch_q<LM, LL, LBB, true, K1Q_VAR>(qa, b.count, st); else launch_q<LM, LL, LBB, false, K1Q_VAR>(qa, b.count, st); \
     return; }
   MB_K1Q_CASE(9, 1, 1) MB_K1Q_CASE(9, 2, 2) MB_K1Q_CASE(9, 2, 1) MB_K1Q_CASE(9, 3, 2) MB_K1Q_CASE(9, 3, 1) MB_K1Q_CASE(9, 4, 2) MB_K1Q_CASE(9, 4, 1)
   MB_K1Q_CASE(10, 1, 1) MB_K1Q_CASE(10, 2, 2) MB_K1Q_CASE(10, 2, 1) MB_K1Q_CASE(10, 3, 2) MB_K1Q_CASE(10, 3, 1) MB_K1Q_CASE(10, 4, 2) MB_K1Q_CASE(10, 4, 1)
