@@ -89,7 +89,8 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   const K1Args &A = Q.a;
   // VAR bit 0 (KPF): pass-C key values pipelined one half row ahead; bit 1 (HYB): two-row phases of pass B mapped to two of
   // the warps (full radix-16 tasks, block barriers) instead of lane pairs in every warp -- see the two-row branches below
-  constexpr bool KPF = (VAR & 1) != 0, HYB = (VAR & 2) != 0;
+  // bit 2 (FOLD): butterflies with the twiddle folded in (k1_common.cuh), the pass-A twist absorbed into them
+  constexpr bool KPF = (VAR & 1) != 0, HYB = (VAR & 2) != 0, FOLD = (VAR & 4) != 0;
   constexpr int M = 1 << LOGM, N = 2 * M, T = M / 4, RA = M / 64, LOGRA = LOGM - 6;
   constexpr int SLOTS = T / 64;                       // pass-A rows in flight: 2 (N = 1024), 4 (N = 2048)
   constexpr int LBO = SLOTS / 2;                      // gadget levels per pass-A round
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         double2 x[16];
 #pragma unroll
         for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[swz_b(m2)];
-        reg_dif<16>(x);
+        if constexpr (FOLD) reg_dft_fma<16, 0>(x); else reg_dif<16>(x);
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) blk[swz_b(pos)] = x[pos];
       } else if constexpr (HYB) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
           double2 x[16];
 #pragma unroll
           for (int m2 = 0; m2 < 16; ++m2) x[m2] = blk[swz_h(m2)];
-          reg_dif<16>(x);
+          if constexpr (FOLD) reg_dft_fma<16, 0>(x); else reg_dif<16>(x);
 #pragma unroll
           for (int pos = 0; pos < 16; ++pos) blk[swz_h(pos)] = x[pos];
         }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
           const double cs = hB ? c : 1.0, ss = hB ? sn : 0.0;
           y[i] = make_double2(fma(y[i].x, cs, -y[i].y * ss), fma(y[i].x, ss, y[i].y * cs));
         }
-        reg_dif<8>(y);
+        if constexpr (FOLD) reg_dft_fma<8, 0>(y); else reg_dif<8>(y);
         __syncwarp();                                 // every lane has read its 16 inputs before any output lands on them
 #pragma unroll
         for (int j = 0; j < 8; ++j) blk[swz_b2(j)] = y[j];
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         double2 x[16];
 #pragma unroll
         for (int pos = 0; pos < 16; ++pos) x[pos] = blk[swz_h(pos)];
-        reg_dit_inv<16>(x);
+        if constexpr (FOLD) reg_dit_inv_fma<16>(x); else reg_dit_inv<16>(x);
 #pragma unroll
         for (int m2 = 0; m2 < 16; ++m2) blk[swz_h(m2)] = x[m2];
       }
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       double2 y[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = blk[swz_b2(j)];
-      reg_dit_inv<8>(y);
+      if constexpr (FOLD) reg_dit_inv_fma<8>(y); else reg_dit_inv<8>(y);
 #pragma unroll
       for (int j = 1; j < 8; ++j) {
         double c, sn;
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[8 * g8 + i] = cmul_conj(x[8 * g8 + i], tmem_c(i < 4 ? ta0 : ta1, i & 3));
       }
-      reg_dit_inv<RA>(x);
+      if constexpr (FOLD) reg_dit_inv_fma<RA>(x); else reg_dit_inv<RA>(x);
       u64 *ap = acc + pA * N;
       u64 ownA[8];
 #pragma unroll
@@ -647,7 +648,7 @@ void launch_blind_rotate_k1q(const BlindRotateLaunch &b, cudaStream_t st) {
 #define MB_K1Q_VARCASE(V_) \
     if (var == V_ && var != K1Q_VAR && logm == 9 && p.l == 3 && lb == 2 && pkall) { launch_q<9, 3, 2, true, V_>(qa, b.count, st); return; } \
     if (var == V_ && var != K1Q_VAR && logm == 10 && p.l == 4 && lb == 2 && !pkall) { launch_q<10, 4, 2, false, V_>(qa, b.count, st); return; }
-    MB_K1Q_VARCASE(0) MB_K1Q_VARCASE(1) MB_K1Q_VARCASE(2) MB_K1Q_VARCASE(3)
+    MB_K1Q_VARCASE(0) MB_K1Q_VARCASE(1) MB_K1Q_VARCASE(3) MB_K1Q_VARCASE(5) MB_K1Q_VARCASE(7)
 #undef MB_K1Q_VARCASE
   }
 #define MB_K1Q_CASE(LM, LL, LBB) \

@@ -9,12 +9,14 @@ namespace mb {
 // W_64 powers in constant memory: FP64 instructions take c[bank][offset] operands directly, whereas
 // folded 64-bit immediates cost two UMOV each time they are rematerialised (ncu: 184 UMOV per step).
 static __constant__ double CW64C[64], CW64S[64];   // one copy per translation unit
+static __constant__ double CW64T[9];               // tan(2 pi m / 64), m = 0..8 (folded-twiddle butterflies)
 static void upload_w64() {
   static bool done_dev[MB_MAX_DEV] = {false};          // __constant__ memory is per device
   bool &done = done_dev[current_device()];
   if (done) return;
   MB_CHECK(cudaMemcpyToSymbol(CW64C, W64C_HOST, sizeof(double) * 64));
   MB_CHECK(cudaMemcpyToSymbol(CW64S, W64S_HOST, sizeof(double) * 64));
+  MB_CHECK(cudaMemcpyToSymbol(CW64T, W64T_HOST, sizeof(double) * 9));
   MB_CHECK(cudaDeviceSynchronize());
   done = true;
 }
@@ -78,6 +80,65 @@ __device__ __forceinline__ void reg_dit_inv(double2 (&x)[R]) {
       const double2 u = x[i0], v = mul_w64(x[i1], j * (32 / h), true);
       x[i0] = cadd(u, v);
       x[i1] = csub(u, v);
+    }
+  }
+}
+
+// ---- butterflies with the twiddle folded in (compile-time powers of W_64) ---------------------------------------------------
+// (u, v) <- (u + w v, u - w v), w = W_64^idx (or its conjugate), in SIX FP64 instructions instead of 4 + 4: with
+// w = i^qd * g * (1 + i tau) -- g = cos or sin of the first-octant angle, |tau| <= 1 its tangent (or the cotangent form
+// w = i^qd * g * (tau + i)) -- the product is g * (p, q) with p, q one FMA each, and g rides in the FMAs that add it to u.
+// Trivial powers cost the 4 additions, the eighth roots 2 additions + 4 FMAs.
+__device__ __forceinline__ void bfly_w64(double2 &u, double2 &v, int idx, bool conj) {
+  idx &= 63;
+  if (conj) idx = (64 - idx) & 63;
+  const int qd = idx >> 4, rem = idx & 15;
+  double p, q, g;                                      // w v = i^qd * g * (p + i q)
+  if (rem == 0) { p = v.x; q = v.y; g = 1.0; }
+  else if (rem == 8) { p = v.x - v.y; q = v.x + v.y; g = 0.70710678118654752440; }
+  else if (rem < 8) { const double t = CW64T[rem]; p = fma(-t, v.y, v.x); q = fma(t, v.x, v.y); g = CW64C[rem]; }          // g (1 + i t)
+  else { const double t = CW64T[16 - rem]; p = fma(t, v.x, -v.y); q = fma(t, v.y, v.x); g = CW64C[16 - rem]; }            // g (t + i)
+  // rotate by i^qd: (p, q) -> (-q, p) -> (-p, -q) -> (q, -p)
+  const double a = (qd == 0) ? p : (qd == 1) ? -q : (qd == 2) ? -p : q;
+  const double b = (qd == 0) ? q : (qd == 1) ? p : (qd == 2) ? -q : -p;
+  const double2 u0 = u;
+  if (rem == 0) { u = make_double2(u0.x + a, u0.y + b); v = make_double2(u0.x - a, u0.y - b); }
+  else { u = make_double2(fma(g, a, u0.x), fma(g, b, u0.y)); v = make_double2(fma(-g, a, u0.x), fma(-g, b, u0.y)); }
+}
+
+// In-register radix-R DFT of TWISTED input, X_k = sum_m x_m (t W_R^k)^m with t = W_64^TW (TW = 0: the plain DFT of
+// reg_dif), as a decimation-in-time network of folded butterflies: the twist t^m is absorbed into the butterfly twiddles
+// (stage of block size 2h: t^(R/2h) W_2h^j), so pass A pays nothing for it.  Natural-order input; on return
+// x[pos] = X[brev(pos)] like reg_dif.
+template <int R, int TW>
+__device__ __forceinline__ void reg_dft_fma(double2 (&x)[R]) {
+  constexpr int LOGR = clog2(R);
+  double2 a[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[i] = x[brev(i, LOGR)];
+#pragma unroll
+  for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+    for (int b = 0; b < R / 2; ++b) {
+      const int j = b & (h - 1);
+      const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
+      bfly_w64(a[i0], a[i1], TW * (R / (2 * h)) + j * (32 / h), false);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) x[i] = a[brev(i, LOGR)];
+}
+
+// reg_dit_inv with folded butterflies: input x[pos] = X[brev(pos)], output x[m] = sum_k X_k W_R^(-mk)
+template <int R>
+__device__ __forceinline__ void reg_dit_inv_fma(double2 (&x)[R]) {
+#pragma unroll
+  for (int h = 1; h < R; h <<= 1) {
+#pragma unroll
+    for (int b = 0; b < R / 2; ++b) {
+      const int j = b & (h - 1);
+      const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
+      bfly_w64(x[i0], x[i1], j * (32 / h), true);
     }
   }
 }

@@ -185,3 +185,38 @@ v = rng.normal(size=16) + 1j * rng.normal(size=16)
 assert np.abs(dif16_pair(v) - dif(v)).max() < 1e-12
 assert np.abs(dit16_pair(v) - dit_inv(v)).max() < 1e-12
 print("lane-pair split of the radix-16 task OK")
+
+
+# ---- the folded decimation-in-time networks of k1_common.cuh (reg_dft_fma / reg_dit_inv_fma): index algebra only ----------
+def w64(idx):
+    return np.exp(2j * np.pi * (idx % 64) / 64)
+
+
+def reg_dft_fma(x, TW):
+    R = len(x)
+    lg = R.bit_length() - 1
+    a = np.array([x[brev(i, lg)] for i in range(R)], complex)
+    h = 1
+    while h < R:
+        for b in range(R // 2):
+            j = b & (h - 1)
+            i0 = ((b - j) << 1) + j
+            i1 = i0 + h
+            w = w64(TW * (R // (2 * h)) + j * (32 // h))
+            a[i0], a[i1] = a[i0] + w * a[i1], a[i0] - w * a[i1]
+        h <<= 1
+    return np.array([a[brev(i, lg)] for i in range(R)])
+
+
+for R, TW in ((4, 0), (8, 0), (16, 0), (8, 2), (16, 1), (8, 5)):
+    lg = R.bit_length() - 1
+    v = rng.normal(size=R) + 1j * rng.normal(size=R)
+    got = reg_dft_fma(v, TW)
+    t = w64(TW)
+    for pos in range(R):
+        k = brev(pos, lg)
+        want = sum(v[m] * (t * np.exp(2j * np.pi * k / R)) ** m for m in range(R))
+        assert abs(got[pos] - want) < 1e-12, (R, TW, pos)
+    if TW == 0:
+        assert np.abs(got - dif(v)).max() < 1e-12
+print("folded DIT networks (twist absorbed) OK")
