@@ -611,7 +611,11 @@ static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   count_launch();
 }
 
-constexpr int K1Q_VAR = 1;    // default variant bits (see the kernel): key pipelining on, lane-pair split of the two-row phases
+// default variant bits (see the kernel): key pipelining + hybrid two-row pass B.  Measured on B200, 4096 ciphertexts
+// (profiles/r2g_k1q_variants.log, r2h_k1q_variants.log): level 1 var 0 / 1 / 3 / 7 = 41.1 / 40.6 / 39.0 / 38.8 ms, level 2 = 124.4 / 120.2 /
+// 119.0-119.5 / 120.8 ms: the folded butterflies (bit 2) remove 7 % of the FP64 instructions and change nothing -- the kernel is bound by
+// the L1 / shared-memory data pipe and by barrier skew, not by the FP64 pipe -- so they stay an option.
+constexpr int K1Q_VAR = 3;
 
 // levels per shared-memory batch: 2 when two levels' digits fit the 32-bit packed word, else 1
 static int k1q_lb(int l, int Bg_bit) { return (l >= 2 && 2 * Bg_bit <= 32) ? 2 : 1; }
