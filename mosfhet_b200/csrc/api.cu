@@ -185,7 +185,7 @@ struct Scratch {
     h = d = nullptr; hcap = dcap = 0;
   }
 };
-enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_UX, S_UD, S_US, S_PRE, S_COUNT };
+enum { S_IN = 0, S_TV, S_OUT, S_MID, S_MISC, S_MISC2, S_KS, S_UX, S_UD, S_US, S_PRE, S_SEG, S_COUNT };
 thread_local Scratch t_scratch[S_COUNT];
 
 // ---- host FFT slot order ----------------------------------------------------------------------
@@ -556,6 +556,32 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
     else if (g_policy == 3 && mb::k1h_supported(p)) pick = K1H;
     else if (g_policy == 4 && mb::k1c_supported(p)) pick = K1C;
     else if (g_policy == 5 && mb::k1q_supported(p)) pick = K1Q;
+  }
+  // Key larger than L2 (Level 2: 166 MB against 126 MB): every wave of CTAs sweeps it from HBM again and CTAs drifting apart
+  // widen the window (4.6 GB of DRAM reads per 4096 bootstraps, profiles/r2d).  The steps are then cut into segments whose
+  // key rows fit L2, one launch per segment over ALL ciphertexts, the accumulators parked in HBM in between (2 x 134 MB).
+  if (pick == K1Q && a.init_rotate && a.size == p.n && a.in_div <= 1 && a.b_index == 0 && !getenv("MB200_NO_SEGMENTS")) {
+    const size_t key_bytes = sizeof(double2) * bsk_elems(p), budget = (size_t)88 << 20;
+    const int wave = sms * (p.N <= 1024 ? 4 : 2);
+    if (key_bytes > ((size_t)110 << 20) && a.count >= 2 * wave) {
+      const int segs = (int)((key_bytes + budget - 1) / budget);
+      const size_t W = (size_t)(p.k + 1) * p.N;
+      u64 *d_acc = (u64 *)t_scratch[S_SEG].dev(sizeof(u64) * (size_t)a.count * W);
+      const size_t row_elems = (size_t)(p.k + 1) * p.l * (p.k + 1) * (p.N / 2);
+      for (int s = 0; s < segs; ++s) {
+        const int s0 = (int)((long long)p.n * s / segs), s1 = (int)((long long)p.n * (s + 1) / segs);
+        mb200_bsk part;
+        part.p = p; part.p.n = s1 - s0; part.d = a.bsk->d + (size_t)s0 * row_elems; part.owned = false;
+        mb::BlindRotateLaunch b = a;
+        b.bsk = &part; b.in = a.in + s0; b.size = s1 - s0; b.b_index = p.n - s0;
+        b.init_rotate = s == 0;
+        if (s > 0) { b.tv = d_acc; b.tv_count = a.count > 1 ? a.count : 1; }
+        if (s + 1 < segs) { b.out = d_acc; b.extract = 0; }
+        mb::launch_blind_rotate_k1q(b, st);
+      }
+      mb::k1q_variant_name(p, t_last_kernel, sizeof(t_last_kernel));
+      return;
+    }
   }
   switch (pick) {
     case K1C: mb::launch_blind_rotate_k1c(a, st); mb::k1c_variant_name(p, t_last_kernel, sizeof(t_last_kernel)); break;

@@ -238,6 +238,7 @@ static size_t generic_smem_bytes(int N, int k, int rows_batch) {
 }
 
 void launch_blind_rotate_generic(const BlindRotateLaunch &a, cudaStream_t st) {
+  MB_REQUIRE(a.b_index == 0 || a.b_index == a.size, "segmented launches exist for the k1q kernel only");
   const Params &p = a.bsk->p;
   MB_REQUIRE(p.N >= 16 && (p.N & (p.N - 1)) == 0, "generic blind rotate: N=%d must be a power of two >= 16", p.N);
   const int rows = (p.k + 1) * p.l;

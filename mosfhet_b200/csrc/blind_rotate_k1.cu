@@ -131,6 +131,7 @@ static void launch_pk(const K1Args &a, int count, cudaStream_t st) {
 }
 
 void launch_blind_rotate_k1(const BlindRotateLaunch &b, cudaStream_t st) {
+  MB_REQUIRE(b.b_index == 0 || b.b_index == b.size, "segmented launches exist for the k1q kernel only");
   const Params &p = b.bsk->p;
   MB_REQUIRE(k1_supported(p) && !b.direct, "k1 kernel: unsupported parameters");
   upload_w64();

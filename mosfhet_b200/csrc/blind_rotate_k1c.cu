@@ -325,6 +325,7 @@ static void launch_k1c_one(const K1Args &a, int count, cudaStream_t st) {
 }
 
 void launch_blind_rotate_k1c(const BlindRotateLaunch &b, cudaStream_t st) {
+  MB_REQUIRE(b.b_index == 0 || b.b_index == b.size, "segmented launches exist for the k1q kernel only");
   const Params &p = b.bsk->p;
   MB_REQUIRE(k1c_supported(p) && !b.direct, "k1c kernel: unsupported parameters");
   upload_w64();

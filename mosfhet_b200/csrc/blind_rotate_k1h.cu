@@ -317,6 +317,7 @@ void k1h_variant_name(const Params &p, char *dst, size_t cap) {
 }
 
 void launch_blind_rotate_k1h(const BlindRotateLaunch &b, cudaStream_t st) {
+  MB_REQUIRE(b.b_index == 0 || b.b_index == b.size, "segmented launches exist for the k1q kernel only");
   const Params &p = b.bsk->p;
   MB_REQUIRE(k1h_supported(p) && !b.direct, "k1h kernel: unsupported parameters");
   upload_w64();

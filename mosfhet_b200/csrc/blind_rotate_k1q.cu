@@ -82,6 +82,7 @@ struct K1QArgs {
   double dbias;       // 2^52 + Bg/2: digit u in [0, Bg) -> double(u - Bg/2) = hiloint2double(0x43300000, u) - dbias, exact
   double out_scale;   // 2^-64 / M
   unsigned dmask;     // Bg - 1
+  int b_index;        // index of b in the input row (init_rotate)
 };
 
 template <int LOGM, int L, int LB, bool PKALL, int VAR>
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   // ---- initial accumulator: tv * X^(2N - round((b + 1/(4*torus_base)) * 2N))  (bootstrap.c:194-195) ----------------
   int rot0 = 0;
   if (A.init_rotate) {
-    u64 b = in[A.size];
+    u64 b = in[Q.b_index];
     if (A.preprocess) b = pb_preprocess(b, A.kappa, A.theta, log_N2);
     rot0 = (2 * N - (int)torus2int(b + A.prec_offset, log_N2)) & (2 * N - 1);
   }
@@ -640,6 +641,7 @@ void launch_blind_rotate_k1q(const BlindRotateLaunch &b, cudaStream_t st) {
   qa.dbias = 4503599627370496.0 + (double)(1ull << (p.Bg_bit - 1));
   qa.out_scale = 5.42101086242752217e-20 / (double)(p.N / 2);
   qa.dmask = (unsigned)((1ull << p.Bg_bit) - 1ull);
+  qa.b_index = b.b_index > 0 ? b.b_index : b.size;
   a.bsk = b.bsk->d; a.tab = k1q_tables_for(p.N); a.tv = b.tv; a.tv_count = b.tv_count; a.in = b.in;
   a.in_stride = b.in_stride; a.in_div = b.in_div > 0 ? b.in_div : 1; a.size = b.size; a.out = b.out; a.extract = b.extract;
   a.init_rotate = b.init_rotate; a.prec_offset = b.prec_offset; a.preprocess = b.preprocess; a.kappa = b.kappa; a.theta = b.theta;

@@ -84,6 +84,7 @@ struct BlindRotateLaunch {
   int in_stride;
   int in_div;           // 0/1: one input per ciphertext; r > 1: ciphertext ct reads input ct / r (and tv ct % tv_count)
   int size;             // number of blind-rotation steps (= n for a bootstrap)
+  int b_index;          // index of b in an input row when init_rotate (0: `size`); set when a launch covers a SEGMENT of the steps
   u64 *out;             // mode 0: [count][(k+1)*N] accumulator; mode 1: [count][k*N+1] TLWE (extract idx 0)
   int extract;          // 0 / 1
   int init_rotate;      // 1: acc = tv * X^(2N - round((b+prec_offset)*2N)) (bootstrap.c:194-195); 0: acc = tv

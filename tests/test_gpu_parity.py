@@ -1257,3 +1257,26 @@ def test_programmable_bootstrap_with_unfolded_key(golden_r4):
         ph = O.tlwe_phase(out.flat(), g["ext_key"])
         assert sdiff(np.uint64(ph), g["lut"][g["msgs"][c]]) <= TOL_TEST
     api.release_bootstrap_key(key)
+
+
+def test_segmented_blind_rotation_is_identical():
+    """Level 2's key (166 MB) exceeds L2, so full batches run the steps in segments with the accumulators parked in HBM
+    (api.cu:run_blind_rotate).  Same arithmetic in the same order: the result must equal the single launch bit for bit."""
+    import os
+    P, count = LEVEL2, 640
+    lwe_key, rlwe_key = syn.binary_key(P.n, 201), syn.binary_key(P.k * P.N, 202)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=17)
+    msgs = (np.arange(count) * 5 + 1) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, P.lwe_sigma, seed=19)
+    lut = syn.encode((np.arange(4) * 3 + 1) % 4, 4)
+    tv = syn.test_vector(lut, P.N, P.k)
+    seg = api.pbs_host(bsk, tv, cts, 4).copy()
+    assert api.last_blind_rotate_kernel().startswith("k1q<")
+    os.environ["MB200_NO_SEGMENTS"] = "1"
+    try:
+        one = api.pbs_host(bsk, tv, cts, 4).copy()
+    finally:
+        del os.environ["MB200_NO_SEGMENTS"]
+    assert np.array_equal(seg, one)
+    assert syn.torus_distance(syn.tlwe_phase(seg, rlwe_key), lut[msgs]).max() <= TOL_TEST
+    bsk.free()
