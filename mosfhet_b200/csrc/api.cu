@@ -561,9 +561,13 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   // widen the window (4.6 GB of DRAM reads per 4096 bootstraps, profiles/r2d).  The steps are then cut into segments whose
   // key rows fit L2, one launch per segment over ALL ciphertexts, the accumulators parked in HBM in between (2 x 134 MB).
   if (pick == K1Q && a.init_rotate && a.size == p.n && a.in_div <= 1 && a.b_index == 0 && !getenv("MB200_NO_SEGMENTS")) {
-    const size_t key_bytes = sizeof(double2) * bsk_elems(p), budget = (size_t)88 << 20;
+    // measured (profiles/r2j_segment_sweep.log, level 2): one launch 119.7 ms, 2 segments 115.9, 3 segments 112.3, 4-8 the same;
+    // the 62 MB level-1 key gains nothing from being cut
+    size_t budget = (size_t)56 << 20;
+    if (const char *e = getenv("MB200_SEG_BUDGET_MB")) budget = (size_t)atoi(e) << 20;     // experiment knob
+    const size_t key_bytes = sizeof(double2) * bsk_elems(p);
     const int wave = sms * (p.N <= 1024 ? 4 : 2);
-    if (key_bytes > ((size_t)110 << 20) && a.count >= 2 * wave) {
+    if (key_bytes > budget + budget / 4 && a.count >= 2 * wave) {
       const int segs = (int)((key_bytes + budget - 1) / budget);
       const size_t W = (size_t)(p.k + 1) * p.N;
       u64 *d_acc = (u64 *)t_scratch[S_SEG].dev(sizeof(u64) * (size_t)a.count * W);
