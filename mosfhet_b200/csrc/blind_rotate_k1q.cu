@@ -526,16 +526,23 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       // (h = 1) frequencies with a radix-8 DIT, the odd half applies conj(W_16^j), the pair swaps its 8 values and half h
       // forms outputs m = j + 8h, untwists them and accumulates their 8 coefficient pairs.
       const double2 *row = buf + pA * M;
-      TmemLd ta0, ta1;
-      tmem_issue(ta0, taddr + COL_TA + 32 * hA);
-      tmem_issue(ta1, taddr + COL_TA + 32 * hA + 16);
+      // tensor-memory addresses are warp-uniform (LDTM takes a uniform register): both halves' twiddles are loaded and the
+      // lane's eight are selected afterwards
+      TmemLd ta0, ta1, ta2, ta3;
+      tmem_issue(ta0, taddr + COL_TA);
+      tmem_issue(ta1, taddr + COL_TA + 16);
+      tmem_issue(ta2, taddr + COL_TA + 32);
+      tmem_issue(ta3, taddr + COL_TA + 48);
       double2 y[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = row[(8 * hA + j) * 64 + ((j & 1) ? qs1 : qs0)];
       tmem_wait(ta0);
-      tmem_also(ta1);
+      tmem_also(ta1); tmem_also(ta2); tmem_also(ta3);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = cmul_conj(y[j], tmem_c(j < 4 ? ta0 : ta1, j & 3));
+      for (int j = 0; j < 8; ++j) {
+        const double2 t0 = tmem_c(j < 4 ? ta0 : ta1, j & 3), t1 = tmem_c(j < 4 ? ta2 : ta3, j & 3);
+        y[j] = cmul_conj(y[j], make_double2(hA ? t1.x : t0.x, hA ? t1.y : t0.y));
+      }
       if constexpr (FOLD) reg_dit_inv_fma<8>(y); else reg_dit_inv<8>(y);
 #pragma unroll
       for (int j = 1; j < 8; ++j) {
