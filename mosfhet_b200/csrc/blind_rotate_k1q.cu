@@ -116,12 +116,8 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   // the compiler keeps the dozen derived offsets live across the whole step in registers it does not have, spills them,
   // and the reloads miss the 28 KB of L1 that is left (3 % of the kernel waiting on local loads, profiles/r2b)
 #define MB_K1Q_ROLES(t_)                                                                                                       \
-  /* pass A / A'.  N = 1024: thread (polynomial pA, in-block index qA), one level per round.  N = 2048: the two lanes   */   \
-  /* (lane, lane ^ 16) share (pA, qA) and differ in hA = the level of the batch they transform in pass A and the half   */   \
-  /* of the outputs they produce in A' -- so all 256 threads work in A', and the pass-A twiddles of a q serve both.     */   \
-  const int pA = (LOGM == 9) ? (t_) >> 6 : (t_) >> 7;                                                                          \
-  const int qA = (LOGM == 9) ? (t_) & 63 : 16 * (((t_) >> 5) & 3) + ((t_) & 15);                                               \
-  const int lboA = (LOGM == 9) ? 0 : ((t_) >> 4) & 1, hA = lboA;                                                               \
+  const int slot = (t_) >> 6, qA = (t_) & 63;         /* pass A / A': row slot and in-block index */                           \
+  const int pA = slot & 1, lboA = slot >> 1;          /* polynomial and level offset inside a round */                         \
   /* pass B / B' run PER WARP on the two blocks pos1 = 2*warp + {0, 1} whose positions the same warp's pass C / C' */        \
   /* threads own, so that B -> C and C' -> B' need a warp barrier only: lane = (row of the batch, block bit, r) */            \
   const int warp = (t_) >> 5, lane = (t_) & 31;                                                                                \
@@ -141,7 +137,7 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
   auto swz_b = [&](int e) { return ((4 * e) ^ ((e >> 1) & 4) ^ b4B) + (rB ^ ((e >> 1) & 3)); };                                \
   /* the same for e = 8*hB + j, j < 8 (two-row phases) */                                                                      \
   auto swz_b2 = [&](int j) { return 32 * hB + ((4 * j) ^ (4 * hB) ^ b4B) + (rB ^ ((j >> 1) & 3)); };                          \
-  (void)lboA; (void)hA; (void)rowB; (void)rowB2; (void)pos2C; (void)qs1; (void)cbase; (void)cxor; (void)swz_b; (void)swz_b2; (void)hB;
+  (void)lboA; (void)rowB; (void)rowB2; (void)pos2C; (void)qs1; (void)cbase; (void)cxor; (void)swz_b; (void)swz_b2; (void)hB;
 
   // ---- tensor memory: per-thread constants and state ------------------------------------------------------------
   constexpr bool TMEM_ACC = (LOGM == 9);              // N = 2048: two warps share a lane quarter and pass-A threads are not the owners
@@ -298,10 +294,8 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
       constexpr int ROUNDS = (NB + LBO - 1) / LBO;
 #pragma unroll
       for (int rd = 0; rd < ROUNDS; ++rd) {
-        // N = 2048 with an odd level left over: the h = 1 lanes have no row in this round.  They still run the round (the
-        // tensor-memory loads are warp-aligned instructions) on level 0 of the batch and skip the stores.
-        const bool activeA = !(LBO > 1 && rd * LBO + lboA >= NB);
-        const int lb = activeA ? rd * LBO + lboA : 0;
+        const int lb = rd * LBO + lboA;
+        if (LBO > 1 && lb >= NB) continue;           // warp-uniform (a slot is two whole warps)
         const int sh = FUSED ? 64 - (lev0 + lb + 1) * Bg_bit : ((PKALL ? (L - 1 - lev0) : (NB - 1)) - lb) * Bg_bit;
         TmemLd ta0, ta1;                              // the first 8 twiddles fly under the digit conversion and the butterflies
         tmem_issue(ta0, taddr + COL_TA);
@@ -339,20 +333,16 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
         tmem_wait(ta0);
         tmem_also(ta1);
 #pragma unroll
-        for (int pos = 0; pos < 8; ++pos) {
-          const double2 v = cmul(x[pos], tmem_c(pos < 4 ? ta0 : ta1, pos & 3));
-          if (activeA) row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = v;
-        }
+        for (int pos = 0; pos < 8; ++pos)
+          row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tmem_c(pos < 4 ? ta0 : ta1, pos & 3));
         if (RA > 8) {
           tmem_issue(ta0, taddr + COL_TA + 32);
           tmem_issue(ta1, taddr + COL_TA + 48);
           tmem_wait(ta0);
           tmem_also(ta1);
 #pragma unroll
-          for (int pos = 8; pos < RA; ++pos) {
-            const double2 v = cmul(x[pos], tmem_c(pos < 12 ? ta0 : ta1, pos & 3));
-            if (activeA) row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = v;
-          }
+          for (int pos = 8; pos < RA; ++pos)
+            row[pos * 64 + ((pos & 1) ? qs1 : qs0)] = cmul(x[pos], tmem_c(pos < 12 ? ta0 : ta1, pos & 3));
         }
       }
       __syncthreads();
@@ -521,51 +511,9 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     }
     __syncthreads();
     // ---------------------------------- A' + accumulate ----------------------------------------------------------------
-    if constexpr (LOGM == 10) {
-      // N = 2048: the radix-16 inverse of a (polynomial, q) is split over the lane pair: half h inverts the even (h = 0) / odd
-      // (h = 1) frequencies with a radix-8 DIT, the odd half applies conj(W_16^j), the pair swaps its 8 values and half h
-      // forms outputs m = j + 8h, untwists them and accumulates their 8 coefficient pairs.
-      const double2 *row = buf + pA * M;
-      // tensor-memory addresses are warp-uniform (LDTM takes a uniform register): both halves' twiddles are loaded and the
-      // lane's eight are selected afterwards
-      TmemLd ta0, ta1, ta2, ta3;
-      tmem_issue(ta0, taddr + COL_TA);
-      tmem_issue(ta1, taddr + COL_TA + 16);
-      tmem_issue(ta2, taddr + COL_TA + 32);
-      tmem_issue(ta3, taddr + COL_TA + 48);
-      double2 y[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = row[(8 * hA + j) * 64 + ((j & 1) ? qs1 : qs0)];
-      tmem_wait(ta0);
-      tmem_also(ta1); tmem_also(ta2); tmem_also(ta3);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double2 t0 = tmem_c(j < 4 ? ta0 : ta1, j & 3), t1 = tmem_c(j < 4 ? ta2 : ta3, j & 3);
-        y[j] = cmul_conj(y[j], make_double2(hA ? t1.x : t0.x, hA ? t1.y : t0.y));
-      }
-      if constexpr (FOLD) reg_dit_inv_fma<8>(y); else reg_dit_inv<8>(y);
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-        double c, sn;
-        w64_cs(4 * j, c, sn);
-        const double cs = hA ? c : 1.0, ss = hA ? -sn : 0.0;        // conj(W_16^j)
-        y[j] = make_double2(fma(y[j].x, cs, -y[j].y * ss), fma(y[j].x, ss, y[j].y * cs));
-      }
-      const double sg = hA ? -1.0 : 1.0;
-      u64 *ap = acc + pA * N + qA + 512 * hA;                     // coefficient q + 64 m, m = j + 8h
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double rx = __shfl_xor_sync(0xffffffffu, y[j].x, 16), ry = __shfl_xor_sync(0xffffffffu, y[j].y, 16);
-        const double2 o = make_double2(fma(sg, y[j].x, rx), fma(sg, y[j].y, ry));   // h = 0: E + O; h = 1: E - O
-        double c0, s0, c1, s1;                                     // untwist conj(W_64^m), m = j + 8h (WQ = 1)
-        w64_cs(j, c0, s0);
-        w64_cs(j + 8, c1, s1);
-        const double cu = hA ? c1 : c0, su = hA ? -s1 : -s0;
-        const double2 z = make_double2(fma(o.x, cu, -o.y * su), fma(o.x, su, o.y * cu));
-        ap[64 * j] += f64_to_torus_scaled(z.x, Q.out_scale);      // trlwe_from_DFT + trlwe_addto
-        ap[64 * j + M] += f64_to_torus_scaled(z.y, Q.out_scale);
-      }
-    } else {
+    // (N = 2048: splitting the radix-16 inverse over lane pairs so that all 256 threads work here was measured 4 % SLOWER,
+    // profiles/r2k: +54 % instructions in this phase for the selects, shuffles and extra tensor-memory loads)
+    if (SLOTS == 2 || slot < 2) {
       const double2 *row = buf + pA * M;
       double2 x[RA];
 #pragma unroll
@@ -667,11 +615,11 @@ static void launch_q(const K1QArgs &a, int count, cudaStream_t st) {
   count_launch();
 }
 
-// default variant bits (see the kernel): key pipelining + hybrid two-row pass B.  Measured on B200, 4096 ciphertexts
-// (profiles/r2g_k1q_variants.log, r2h_k1q_variants.log): level 1 var 0 / 1 / 3 / 7 = 41.1 / 40.6 / 39.0 / 38.8 ms, level 2 = 124.4 / 120.2 /
-// 119.0-119.5 / 120.8 ms: the folded butterflies (bit 2) remove 7 % of the FP64 instructions and change nothing -- the kernel is bound by
-// the L1 / shared-memory data pipe and by barrier skew, not by the FP64 pipe -- so they stay an option.
-constexpr int K1Q_VAR = 3;
+// default variant bits (see the kernel): key pipelining + hybrid two-row pass B + folded butterflies.  Measured on B200, 4096
+// ciphertexts (profiles/r2g / r2h / r2l_k1q_variants.log): level 1 var 0 / 1 / 3 / 7 = 41.1 / 40.6 / 39.0 / 38.75 ms, level 2 (three
+// key segments) var 3 / 7 = 112.2 / 111.1 ms.  The folded butterflies (bit 2) remove 7 % of the FP64 instructions and gain under 1 %:
+// the kernel is bound by the L1 / shared-memory data pipe and by barrier skew, not by the FP64 pipe.
+constexpr int K1Q_VAR = 7;
 
 // levels per shared-memory batch: 2 when two levels' digits fit the 32-bit packed word, else 1
 static int k1q_lb(int l, int Bg_bit) { return (l >= 2 && 2 * Bg_bit <= 32) ? 2 : 1; }

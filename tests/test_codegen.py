@@ -46,8 +46,8 @@ def test_k1q_kernels_fit_four_warps_per_scheduler():
     """The T = M/4 kernels exist to run 16 warps per SM: 128 registers at most, and only a few spilled words."""
     res = _usage(os.path.join(BUILD, "blind_rotate_k1q.o"))
     # <LOGM, L, LB, PKALL, VAR>
-    level1 = [v for k, v in res.items() if "k1q_kernelILi9ELi3ELi2ELb1ELi3E" in k]
-    level2 = [v for k, v in res.items() if "k1q_kernelILi10ELi4ELi2ELb0ELi3E" in k]
+    level1 = [v for k, v in res.items() if "k1q_kernelILi9ELi3ELi2ELb1ELi7E" in k]
+    level2 = [v for k, v in res.items() if "k1q_kernelILi10ELi4ELi2ELb0ELi7E" in k]
     assert level1 and level2, "benchmark instantiations missing from blind_rotate_k1q.o"
     for name, (reg, stack) in (("level 1", level1[0]), ("level 2", level2[0])):
         assert reg <= 128, f"{name}: {reg} registers"
