@@ -774,10 +774,22 @@ class HostPool {
   int workers() const { return (int)th_.size(); }
   // a group of jobs whose completion can be awaited
   struct Group { std::mutex m; std::condition_variable cv; int pending = 0; };
-  void submit(Group &g, std::function<void()> job) {
+  // urgent jobs (the first GPU wave of a pipelined call) go to the head of the queue: with several device workers
+  // submitting at once, nobody's first wave waits behind another device's bulk
+  void submit(Group &g, std::function<void()> job, bool urgent = false) {
     { std::lock_guard<std::mutex> lk(g.m); ++g.pending; }
-    { std::lock_guard<std::mutex> lk(mu_); q_.push_back(Item{&g, std::move(job)}); }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (urgent) q_.push_front(Item{&g, std::move(job)}); else q_.push_back(Item{&g, std::move(job)});
+    }
     cv_.notify_one();
+  }
+  // at least `n` workers, bounded by the host's cores (multi-GPU mode: every device flattens and scatters its own shard)
+  void grow(int n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw && n > (int)hw - 1) n = (int)hw - 1;
+    while ((int)th_.size() < n) { th_.emplace_back([this] { run(); }); th_.back().detach(); }
   }
   void wait(Group &g) {
     std::unique_lock<std::mutex> lk(g.m);
@@ -1011,6 +1023,7 @@ int mb200_init_multi(int ndev) {
     g_workers.push_back(w);
   }
   g_ndev = ndev;
+  HostPool::get().grow(8 * ndev);                              // every device flattens / scatters its shard at the same time
   return g_ndev;
 }
 int mb200_multi_device_count(void) { return g_ndev; }
@@ -1411,7 +1424,7 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   auto mark = [&](const char *what, int c) {
     if (!trace) return;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    fprintf(stderr, "[mb200 trace] %8.3f ms  %s %d\n", ms, what, c);
+    fprintf(stderr, "[mb200 trace] dev %d %8.3f ms  %s %d\n", mb::current_device(), ms, what, c);
   };
   const int w_in = p.n + 1, w_mid = p.k * p.N + 1, W = (p.k + 1) * p.N;
   const size_t in_b = sizeof(u64) * (size_t)count * w_in, tv_b = sizeof(u64) * (size_t)tv_count * W;
@@ -1419,17 +1432,24 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   u64 *h_tv = (u64 *)t_scratch[S_TV].host(tv_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
   u64 *d_mid = (u64 *)t_scratch[S_MID].dev(sizeof(u64) * (size_t)count * w_mid);
   u64 *h_out = (u64 *)t_scratch[S_OUT].host(in_b), *d_out = (u64 *)t_scratch[S_OUT].dev(in_b);
-  // Two chunks on two streams: the first wave of ciphertexts (resident CTAs of the blind rotation: 4 per SM at N <= 1024,
-  // 2 at N = 2048) is flattened, copied and launched at once; the rest is flattened meanwhile and launched on a second
-  // stream, so that its CTAs fill the SMs as the first launch drains.  (Measured with MB200_TRACE, profiles/r2f: flattening
-  // 4096 inputs takes 0.9 ms on the worker pool; four back-to-back launches on ONE stream cost 2.4 ms in drained tails.)
+  // Two groups on two streams: the first wave of ciphertexts (the resident CTAs of the blind rotation: 4 per SM at
+  // N <= 1024, 2 at N = 2048) is flattened, copied and launched at once; the rest is flattened meanwhile and launched on a
+  // second stream, so that its CTAs fill the SMs as the first launch drains.  (Measured with MB200_TRACE, profiles/r2f:
+  // flattening 4096 inputs takes 0.9 ms on the worker pool; four back-to-back launches on ONE stream cost 2.4 ms in drained
+  // tails.)  The key switch then runs in four slices of the batch, each slice's results copied back on the second stream and
+  // scattered by the host pool while the next slice is switched (its 5.6 MB table stays in L2): only the last quarter's copy
+  // and scatter are exposed.  (Tried and dropped, profiles/r2m: bootstrap -> key switch -> copy per group on prioritised
+  // streams; key-switch CTAs squeezed between the blind-rotation CTAs cost 3 ms of GPU time per 4096 ciphertexts.)
   const int wave = mb::sm_count() * (p.N <= 1024 ? 4 : (p.N <= 2048 ? 2 : 1));
-  int per = wave;
-  if (count < 3 * wave || tv_count != 1) per = count;           // small batches / per-input test vectors: one chunk
-  const int nchunks = per < count ? 2 : 1;
-  cudaStream_t st2 = nchunks > 1 ? mb::second_stream() : st;
+  const bool piped = count >= 3 * wave && tv_count == 1;        // small batches / per-input test vectors: one group
+  struct Grp { int c0, cc; cudaStream_t s; };
+  std::vector<Grp> grp;
+  cudaStream_t st2 = mb::second_stream();
+  if (!piped) grp.push_back(Grp{0, count, st});
+  else { grp.push_back(Grp{0, wave, st}); grp.push_back(Grp{wave, count - wave, st2}); }
+  const int ng = (int)grp.size();
   HostPool &pool = HostPool::get();
-  std::vector<HostPool::Group> gathered(nchunks);
+  std::vector<HostPool::Group> gathered(ng);
   const int sub = 256;                                          // gather / scatter job size (ciphertexts)
   auto gather_job = [=](int b, int e) {
     for (int i = b; i < e; ++i) {
@@ -1437,43 +1457,60 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
       h_in[(size_t)i * w_in + w_in - 1] = in[i]->b;
     }
   };
-  for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, c1 = c == nchunks - 1 ? count : c0 + per;
-    for (int b = c0; b < c1; b += sub) pool.submit(gathered[c], [=] { gather_job(b, b + sub < c1 ? b + sub : c1); });
+  for (int g = 0; g < ng; ++g) {
+    const int c0 = grp[g].c0, c1 = c0 + grp[g].cc;
+    for (int b = c0; b < c1; b += sub) pool.submit(gathered[g], [=] { gather_job(b, b + sub < c1 ? b + sub : c1); }, g == 0 && ng > 1);
   }
   gather_trlwe(h_tv, tv, tv_count, p.k, p.N);
-  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
-  cudaEvent_t tv_ready = nullptr, second_done = nullptr;
-  if (nchunks > 1) {
+  cudaStream_t s0 = grp[0].s;
+  MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, s0));
+  cudaEvent_t tv_ready = nullptr;
+  if (ng > 1) {
     MB_CHECK(cudaEventCreateWithFlags(&tv_ready, cudaEventDisableTiming));
-    MB_CHECK(cudaEventCreateWithFlags(&second_done, cudaEventDisableTiming));
-    MB_CHECK(cudaEventRecord(tv_ready, st));
-    MB_CHECK(cudaStreamWaitEvent(st2, tv_ready, 0));
+    MB_CHECK(cudaEventRecord(tv_ready, s0));
   }
-  for (int c = 0; c < nchunks; ++c) {
-    const int c0 = c * per, cc = (c == nchunks - 1 ? count : c0 + per) - c0;
-    cudaStream_t sc = c == 0 ? st : st2;
-    pool.wait(gathered[c]);
-    mark("gathered chunk", c);
+  // results: (offset, count, event) per piece, in completion order
+  struct Piece { int c0, cc; cudaEvent_t ev; };
+  std::vector<Piece> pieces;
+  auto copy_back = [&](int c0, int cc, cudaStream_t sc) {
+    Piece pc{c0, cc, nullptr};
+    MB_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * w_in, d_out + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyDeviceToHost, sc));
+    MB_CHECK(cudaEventCreateWithFlags(&pc.ev, cudaEventDisableTiming));
+    MB_CHECK(cudaEventRecord(pc.ev, sc));
+    pieces.push_back(pc);
+  };
+  for (int g = 0; g < ng; ++g) {
+    const int c0 = grp[g].c0, cc = grp[g].cc;
+    cudaStream_t sc = grp[g].s;
+    if (g > 0) MB_CHECK(cudaStreamWaitEvent(sc, tv_ready, 0));
+    pool.wait(gathered[g]);
+    mark("gathered group", g);
     MB_CHECK(cudaMemcpyAsync(d_in + (size_t)c0 * w_in, h_in + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyHostToDevice, sc));
     pbs_dev_impl(bsk, d_mid + (size_t)c0 * w_mid, 1, d_tv + (tv_count > 1 ? (size_t)c0 * W : 0), tv_count > 1 ? cc : 1,
                  d_in + (size_t)c0 * w_in, torus_base, cc, sc);
   }
-  if (nchunks > 1) {
+  if (ng > 1) {
+    cudaEvent_t second_done;
+    MB_CHECK(cudaEventCreateWithFlags(&second_done, cudaEventDisableTiming));
     MB_CHECK(cudaEventRecord(second_done, st2));
     MB_CHECK(cudaStreamWaitEvent(st, second_done, 0));
+    MB_CHECK(cudaEventDestroy(second_done));
   }
-  mb::launch_keyswitch(ksk, d_out, d_mid, count, st);
-  mark("all launches queued", nchunks);
-  // results come back in a few chunks so that the host scatter of one overlaps the copy of the next
   const int ochunks = count >= 2048 ? 4 : 1, oper = (count + ochunks - 1) / ochunks;
-  std::vector<cudaEvent_t> done(ochunks);
   for (int c = 0; c < ochunks; ++c) {
     const int c0 = c * oper, cc = (c0 + oper < count ? c0 + oper : count) - c0;
-    MB_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * w_in, d_out + (size_t)c0 * w_in, sizeof(u64) * (size_t)cc * w_in, cudaMemcpyDeviceToHost, st));
-    MB_CHECK(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
-    MB_CHECK(cudaEventRecord(done[c], st));
+    if (cc <= 0) break;
+    mb::launch_keyswitch(ksk, d_out + (size_t)c0 * w_in, d_mid + (size_t)c0 * w_mid, cc, st);
+    if (ochunks > 1) {                                          // the copy leaves on the other stream, behind this slice only
+      cudaEvent_t switched;
+      MB_CHECK(cudaEventCreateWithFlags(&switched, cudaEventDisableTiming));
+      MB_CHECK(cudaEventRecord(switched, st));
+      MB_CHECK(cudaStreamWaitEvent(st2, switched, 0));
+      MB_CHECK(cudaEventDestroy(switched));
+      copy_back(c0, cc, st2);
+    } else copy_back(c0, cc, st);
   }
+  mark("all launches queued", ng);
   HostPool::Group scattered;
   auto scatter_job = [=](int b, int e) {
     for (int i = b; i < e; ++i) {
@@ -1481,14 +1518,14 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
       out[i]->b = h_out[(size_t)i * w_in + w_in - 1];
     }
   };
-  for (int c = 0; c < ochunks; ++c) {
-    const int c0 = c * oper, c1 = c0 + oper < count ? c0 + oper : count;
-    MB_CHECK(cudaEventSynchronize(done[c]));
-    mark("results on the host, chunk", c);
-    MB_CHECK(cudaEventDestroy(done[c]));
+  for (size_t c = 0; c < pieces.size(); ++c) {
+    const int c0 = pieces[c].c0, c1 = c0 + pieces[c].cc;
+    MB_CHECK(cudaEventSynchronize(pieces[c].ev));
+    mark("results on the host, piece", (int)c);
+    MB_CHECK(cudaEventDestroy(pieces[c].ev));
     for (int b = c0; b < c1; b += sub) pool.submit(scattered, [=] { scatter_job(b, b + sub < c1 ? b + sub : c1); });
   }
-  if (tv_ready) { MB_CHECK(cudaEventDestroy(tv_ready)); MB_CHECK(cudaEventDestroy(second_done)); }
+  if (tv_ready) MB_CHECK(cudaEventDestroy(tv_ready));
   pool.wait(scattered);
   mark("scattered", count);
 }

@@ -57,9 +57,9 @@ struct TableKsArgs {
 template <int NV, bool CHUNKED>
 __global__ void __launch_bounds__(KS_MAX_WARPS * 32, 1) keyswitch_warp_kernel(TableKsArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vct = blockIdx.x * A.per_cta + warp;             // (ciphertext, slice, chunk)
-  const int ch = CHUNKED ? vct % A.chunks : 0, cs = CHUNKED ? vct / A.chunks : vct;
-  const int ct = cs / A.slices, sl = cs - ct * A.slices;
+  const int vct = blockIdx.x * A.per_cta + warp;             // (ciphertext, chunk); blockIdx.y = slice of the sweep, so that
+  const int ch = CHUNKED ? vct % A.chunks : 0, ct = CHUNKED ? vct / A.chunks : vct;   // the warps of a CTA read the SAME rows (L1)
+  const int sl = blockIdx.y;
   const bool live = warp < A.per_cta && ct < A.count;
   const int t = A.t, base_bit = A.base_bit, row_stride = A.row_stride;
   const int bm1 = (1 << base_bit) - 1;
@@ -120,24 +120,28 @@ template <int NV, bool CHUNKED>
 static void launch_ks_nv(TableKsArgs A, cudaStream_t st) {
   const int sms = sm_count();
   const int work = A.count * A.chunks;
-  // small batches: split each ciphertext's sweep so that about 8 warps per SM are busy
+  // A warp's sweep is one serial chain (3.4 ms at Level 1 whatever the batch), so a batch below one full wave of
+  // 28 warps per SM splits every ciphertext's sweep over `slices` warps: small batches up to about 8 busy warps per SM
+  // (few ciphertexts share a row through L1, more slices only add atomics), larger ones up to the full wave.
   int slices = 1;
-  if (work < 4 * sms) {
-    slices = (8 * sms + work - 1) / work;
+  if (work < 4 * sms) slices = (8 * sms + work - 1) / work;
+  else if (2 * work <= KS_MAX_WARPS * sms) slices = KS_MAX_WARPS * sms / work;
+  if (slices > 1) {
     const int max_slices = (A.n_entries + 31) / 32;
     if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
   }
   A.i_per = (((A.n_entries + slices - 1) / slices) + 31) & ~31;
   A.slices = (A.n_entries + A.i_per - 1) / A.i_per;
   const int vcount = work * A.slices;
-  // one CTA per SM when the batch allows; as few waves as possible otherwise
-  int waves = (vcount + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
-  int per = (vcount + sms * waves - 1) / (sms * waves);
+  // one CTA per SM when the batch allows; as few waves as possible otherwise.  grid = (CTAs per slice, slices)
+  const int waves = (vcount + sms * KS_MAX_WARPS - 1) / (sms * KS_MAX_WARPS);
+  int gx = sms * waves / A.slices;
+  if (gx < 1) gx = 1;
+  int per = (work + gx - 1) / gx;
   if (per < 1) per = 1;
   if (per > KS_MAX_WARPS) per = KS_MAX_WARPS;
   A.per_cta = per;
-  const int grid = (vcount + per - 1) / per;
+  const dim3 grid((work + per - 1) / per, A.slices);
   static bool configured_dev[MB_MAX_DEV] = {false};        // function attributes are per device
   bool &configured = configured_dev[current_device()];
   if (!configured) {

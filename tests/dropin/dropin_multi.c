@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "mosfhet_b200.h"
 
@@ -88,8 +89,8 @@ int main(int argc, char **argv) {
     if ((int)(dec & 7) != (3 * (i % torus_base) + 1) % 4) wrong++;
   }
   printf("{\"devices\": %d, \"batch\": %d, \"params\": \"n=%d N=%d l=%d Bg_bit=%d t=%d base_bit=%d\", \"rate_1gpu\": %.1f, "
-         "\"rate_multi\": %.1f, \"speedup\": %.3f, \"key_replication_s\": %.3f, \"differ_from_1gpu\": %d, \"wrong\": %d}\n",
-         used, count, n, N, l, Bg_bit, t, base_bit, rate1, rateN, rateN / rate1, repl_s, differ, wrong);
+         "\"rate_multi\": %.1f, \"speedup\": %.3f, \"key_replication_s\": %.3f, \"host_cores\": %ld, \"differ_from_1gpu\": %d, \"wrong\": %d}\n",
+         used, count, n, N, l, Bg_bit, t, base_bit, rate1, rateN, rateN / rate1, repl_s, sysconf(_SC_NPROCESSORS_ONLN), differ, wrong);
   printf((differ || wrong) ? "DROPIN MULTI FAILED\n" : "DROPIN MULTI OK\n");
   return (differ || wrong) ? 1 : 0;
 }
