@@ -785,13 +785,27 @@ class HostPool {
     cv_.notify_one();
   }
   // at least `n` workers, bounded by the host's cores (multi-GPU mode: every device flattens and scatters its own shard)
-  void grow(int n) {
+  // `reserve` cores are left to the caller's other threads (the device workers, which also work the queue while they wait):
+  // oversubscribed cores cost the workers scheduling delays of milliseconds
+  void grow(int n, int reserve) {
     std::lock_guard<std::mutex> lk(mu_);
     const unsigned hw = std::thread::hardware_concurrency();
-    if (hw && n > (int)hw - 1) n = (int)hw - 1;
+    if (hw && n > (int)hw - 1 - reserve) n = (int)hw - 1 - reserve;
     while ((int)th_.size() < n) { th_.emplace_back([this] { run(); }); th_.back().detach(); }
   }
+  // the waiting thread works the queue too (its own jobs or another caller's) until its group is done or nothing is queued
   void wait(Group &g) {
+    for (;;) {
+      { std::lock_guard<std::mutex> lk(g.m); if (g.pending == 0) return; }
+      Item it;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (q_.empty()) break;
+        it = std::move(q_.front());
+        q_.pop_front();
+      }
+      finish(it);
+    }
     std::unique_lock<std::mutex> lk(g.m);
     g.cv.wait(lk, [&] { return g.pending == 0; });
   }
@@ -813,10 +827,13 @@ class HostPool {
         it = std::move(q_.front());
         q_.pop_front();
       }
-      it.job();
-      // notify under the lock: the waiter may destroy the group as soon as it sees pending == 0 and owns the mutex
-      { std::lock_guard<std::mutex> lk(it.g->m); --it.g->pending; it.g->cv.notify_all(); }
+      finish(it);
     }
+  }
+  static void finish(Item &it) {
+    it.job();
+    // notify under the lock: the waiter may destroy the group as soon as it sees pending == 0 and owns the mutex
+    { std::lock_guard<std::mutex> lk(it.g->m); --it.g->pending; it.g->cv.notify_all(); }
   }
   std::mutex mu_;
   std::condition_variable cv_;
@@ -1023,7 +1040,7 @@ int mb200_init_multi(int ndev) {
     g_workers.push_back(w);
   }
   g_ndev = ndev;
-  HostPool::get().grow(8 * ndev);                              // every device flattens / scatters its shard at the same time
+  HostPool::get().grow(8 * ndev, ndev + 1);                           // every device flattens / scatters its shard at the same time
   return g_ndev;
 }
 int mb200_multi_device_count(void) { return g_ndev; }
@@ -1414,10 +1431,6 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   const mb::Params &p = bsk->p;
   MB_REQUIRE(ksk->p.k * ksk->p.N == p.k * p.N && ksk->p.n == p.n, "pbs_ks: key switch (%d -> %d) does not chain with the bootstrap (%d -> %d)",
              ksk->p.k * ksk->p.N, ksk->p.n, p.n, p.k * p.N);
-  for (int i = 0; i < count; ++i) {
-    MB_REQUIRE(in[i]->n == p.n, "TLWE %d has dimension %d, expected %d", i, in[i]->n, p.n);
-    MB_REQUIRE(out[i]->n == p.n, "output TLWE %d has dimension %d, expected %d", i, out[i]->n, p.n);      // tlwe.c:293
-  }
   cudaStream_t st = mb::default_stream();
   static const bool trace = getenv("MB200_TRACE") != nullptr;   // host-side timeline of this call on stderr
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1438,7 +1451,7 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   // flattening 4096 inputs takes 0.9 ms on the worker pool; four back-to-back launches on ONE stream cost 2.4 ms in drained
   // tails.)  The key switch then runs in four slices of the batch, each slice's results copied back on the second stream and
   // scattered by the host pool while the next slice is switched (its 5.6 MB table stays in L2): only the last quarter's copy
-  // and scatter are exposed.  (Tried and dropped, profiles/r2m: bootstrap -> key switch -> copy per group on prioritised
+  // and scatter are exposed (equal quarters: uneven slices fill the key switch's single wave worse, 4.15 against 3.6 ms).  (Tried and dropped, profiles/r2m: bootstrap -> key switch -> copy per group on prioritised
   // streams; key-switch CTAs squeezed between the blind-rotation CTAs cost 3 ms of GPU time per 4096 ciphertexts.)
   const int wave = mb::sm_count() * (p.N <= 1024 ? 4 : (p.N <= 2048 ? 2 : 1));
   const bool piped = count >= 3 * wave && tv_count == 1;        // small batches / per-input test vectors: one group
@@ -1451,8 +1464,12 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
   HostPool &pool = HostPool::get();
   std::vector<HostPool::Group> gathered(ng);
   const int sub = 256;                                          // gather / scatter job size (ciphertexts)
+  // (the dimension checks ride in the flattening jobs: walking thousands of cold handles up front costs the first wave 0.3 ms)
+  const int n_expected = p.n;
   auto gather_job = [=](int b, int e) {
     for (int i = b; i < e; ++i) {
+      MB_REQUIRE(in[i]->n == n_expected, "TLWE %d has dimension %d, expected %d", i, in[i]->n, n_expected);
+      MB_REQUIRE(out[i]->n == n_expected, "output TLWE %d has dimension %d, expected %d", i, out[i]->n, n_expected);   // tlwe.c:293
       memcpy(h_in + (size_t)i * w_in, in[i]->a, sizeof(u64) * (w_in - 1));
       h_in[(size_t)i * w_in + w_in - 1] = in[i]->b;
     }

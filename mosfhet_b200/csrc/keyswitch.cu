@@ -121,10 +121,11 @@ static void launch_ks_nv(TableKsArgs A, cudaStream_t st) {
   const int sms = sm_count();
   const int work = A.count * A.chunks;
   // A warp's sweep is one serial chain (3.4 ms at Level 1 whatever the batch), so a batch below one full wave of
-  // 28 warps per SM splits every ciphertext's sweep over `slices` warps: small batches up to about 8 busy warps per SM
-  // (few ciphertexts share a row through L1, more slices only add atomics), larger ones up to the full wave.
+  // 28 warps per SM splits every ciphertext's sweep over `slices` warps: up to the full wave from two ciphertexts per SM,
+  // about 16 warps per SM below (measured, profiles/r2m_ks_small.log: 256 ciphertexts 0.76 ms at 8 warps per SM, 0.45 at
+  // 16, 0.48 at 28 -- more slices only add atomics there)
   int slices = 1;
-  if (work < 4 * sms) slices = (8 * sms + work - 1) / work;
+  if (work < 2 * sms) slices = (16 * sms + work - 1) / work;
   else if (2 * work <= KS_MAX_WARPS * sms) slices = KS_MAX_WARPS * sms / work;
   if (slices > 1) {
     const int max_slices = (A.n_entries + 31) / 32;
