@@ -561,13 +561,14 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   // widen the window (4.6 GB of DRAM reads per 4096 bootstraps, profiles/r2d).  The steps are then cut into segments whose
   // key rows fit L2, one launch per segment over ALL ciphertexts, the accumulators parked in HBM in between (2 x 134 MB).
   if (pick == K1Q && a.init_rotate && a.size == p.n && a.in_div <= 1 && a.b_index == 0 && !getenv("MB200_NO_SEGMENTS")) {
-    // measured (profiles/r2j_segment_sweep.log, level 2): one launch 119.7 ms, 2 segments 115.9, 3 segments 112.3, 4-8 the same;
-    // the 62 MB level-1 key gains nothing from being cut
-    size_t budget = (size_t)56 << 20;
+    // measured (level 2, profiles/r2j_segment_sweep.log, r2o_level2_dram_budget*.csv): one launch 119.7 ms and 4.6 GB of DRAM
+    // reads; 3 segments (56 MB each) 111.3 ms, 1.18 GB; 4 segments (42 MB) 111.3 ms, 0.61 GB; 6 segments 111.6 ms, 0.87 GB (more
+    // accumulator parking).  The 62 MB level-1 key stays in L2 as it is and gains nothing from being cut.
+    size_t budget = (size_t)42 << 20;
     if (const char *e = getenv("MB200_SEG_BUDGET_MB")) budget = (size_t)atoi(e) << 20;     // experiment knob
     const size_t key_bytes = sizeof(double2) * bsk_elems(p);
     const int wave = sms * (p.N <= 1024 ? 4 : 2);
-    if (key_bytes > budget + budget / 4 && a.count >= 2 * wave) {
+    if (key_bytes > ((size_t)70 << 20) && key_bytes > budget && a.count >= 2 * wave) {
       const int segs = (int)((key_bytes + budget - 1) / budget);
       const size_t W = (size_t)(p.k + 1) * p.N;
       u64 *d_acc = (u64 *)t_scratch[S_SEG].dev(sizeof(u64) * (size_t)a.count * W);
@@ -1288,6 +1289,11 @@ void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int coun
 }
 
 // ---- host-buffer batch ops -------------------------------------------------------------------------
+// A key switch cut into quarter batches fills its single wave by slicing every sweep over four warps: 5 % slower than one
+// launch at Level 1 (3.64 against 3.47 ms per 4096), 12 % at Level 2 (12.1 against 10.8 ms; profiles/r2m_ks_sweep.log,
+// r2o_ks_sweep_level2.log).  It pays when that loss is below the copy + scatter it hides (about 0.5 ms per 4096).
+static bool ks_slicing_pays(const mb::Params &p) { return (long long)p.k * p.N * p.t <= 8192; }
+
 void mb200_pbs_ks_host(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *h_out, const uint64_t *h_tv, int tv_count,
                        const uint64_t *h_in, int torus_base, int count) {
   const mb::Params &p = bsk->p;
@@ -1296,11 +1302,48 @@ void mb200_pbs_ks_host(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *h_out, const 
   const size_t mid_b = sizeof(u64) * (size_t)count * (p.k * p.N + 1), out_b = in_b;
   u64 *d_in = (u64 *)t_scratch[S_IN].dev(in_b), *d_tv = (u64 *)t_scratch[S_TV].dev(tv_b);
   u64 *d_mid = (u64 *)t_scratch[S_MID].dev(mid_b), *d_out = (u64 *)t_scratch[S_OUT].dev(out_b);
-  MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+  MB_REQUIRE(ksk->p.k * ksk->p.N == p.k * p.N && ksk->p.n == p.n, "pbs_ks: key switch (%d -> %d) does not chain with the bootstrap (%d -> %d)",
+             ksk->p.k * ksk->p.N, ksk->p.n, p.n, p.k * p.N);
+  const int wave = mb::sm_count() * (p.N <= 1024 ? 4 : (p.N <= 2048 ? 2 : 1));
+  // (Level 2: the blind rotation runs in key segments over the whole batch and the sliced key switch loses 1.3 ms of its
+  // 10.8 ms, profiles/r2o_ks_sweep_level2.log -- the plain sequence is the faster one there, 0.99 of the device-resident rate)
+  if (count < 3 * wave || tv_count != 1 || !ks_slicing_pays(ksk->p)) {   // small batches: copy, run, copy back
+    MB_CHECK(cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, st));
+    MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
+    mb200_pbs_ks_dev(bsk, ksk, (uint64_t *)d_out, (const uint64_t *)d_tv, tv_count, (const uint64_t *)d_in,
+                     (uint64_t *)d_mid, torus_base, count, st);
+    MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+    MB_CHECK(cudaStreamSynchronize(st));
+    return;
+  }
+  // The same overlap as functional_bootstrap_keyswitch_batch, without the handle trees: the first wave is copied and launched
+  // at once, the rest arrives on a second stream while it runs; the key switch goes in four slices, each slice's results
+  // leaving on the second stream while the next is switched (pinned host buffers make the copies asynchronous).
+  const size_t w_in = (size_t)p.n + 1, w_mid = (size_t)p.k * p.N + 1;
+  cudaStream_t st2 = mb::second_stream();
+  cudaEvent_t ev;
+  MB_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   MB_CHECK(cudaMemcpyAsync(d_tv, h_tv, tv_b, cudaMemcpyHostToDevice, st));
-  mb200_pbs_ks_dev(bsk, ksk, (uint64_t *)d_out, (const uint64_t *)d_tv, tv_count, (const uint64_t *)d_in,
-                   (uint64_t *)d_mid, torus_base, count, st);
-  MB_CHECK(cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  MB_CHECK(cudaEventRecord(ev, st));
+  MB_CHECK(cudaStreamWaitEvent(st2, ev, 0));
+  MB_CHECK(cudaMemcpyAsync(d_in, h_in, sizeof(u64) * wave * w_in, cudaMemcpyHostToDevice, st));
+  pbs_dev_impl(bsk, d_mid, 1, d_tv, 1, d_in, torus_base, wave, st);
+  MB_CHECK(cudaMemcpyAsync(d_in + wave * w_in, h_in + wave * w_in, sizeof(u64) * (count - wave) * w_in, cudaMemcpyHostToDevice, st2));
+  pbs_dev_impl(bsk, d_mid + wave * w_mid, 1, d_tv, 1, d_in + wave * w_in, torus_base, count - wave, st2);
+  MB_CHECK(cudaEventRecord(ev, st2));
+  MB_CHECK(cudaStreamWaitEvent(st, ev, 0));
+  const int slices = count >= 2048 ? 4 : 1, per = (count + slices - 1) / slices;
+  for (int c = 0; c < slices; ++c) {
+    const size_t c0 = (size_t)c * per;
+    const int cc = (int)((c0 + per < (size_t)count ? c0 + per : (size_t)count) - c0);
+    if (cc <= 0) break;
+    mb::launch_keyswitch(ksk, d_out + c0 * w_in, d_mid + c0 * w_mid, cc, st);
+    MB_CHECK(cudaEventRecord(ev, st));
+    MB_CHECK(cudaStreamWaitEvent(st2, ev, 0));
+    MB_CHECK(cudaMemcpyAsync(h_out + c0 * w_in, d_out + c0 * w_in, sizeof(u64) * cc * w_in, cudaMemcpyDeviceToHost, st2));
+  }
+  MB_CHECK(cudaEventDestroy(ev));
+  MB_CHECK(cudaStreamSynchronize(st2));
   MB_CHECK(cudaStreamSynchronize(st));
 }
 void mb200_pbs_host(mb200_bsk_t bsk, uint64_t *h_out, const uint64_t *h_tv, int tv_count, const uint64_t *h_in,
@@ -1514,11 +1557,13 @@ void functional_bootstrap_keyswitch_batch(TLWE *out, TRLWE *tv, int tv_count, TL
     MB_CHECK(cudaEventDestroy(second_done));
   }
   const int ochunks = count >= 2048 ? 4 : 1, oper = (count + ochunks - 1) / ochunks;
+  const bool sliced = ochunks > 1 && ks_slicing_pays(ksk->p);
+  if (!sliced) mb::launch_keyswitch(ksk, d_out, d_mid, count, st);
   for (int c = 0; c < ochunks; ++c) {
     const int c0 = c * oper, cc = (c0 + oper < count ? c0 + oper : count) - c0;
     if (cc <= 0) break;
-    mb::launch_keyswitch(ksk, d_out + (size_t)c0 * w_in, d_mid + (size_t)c0 * w_mid, cc, st);
-    if (ochunks > 1) {                                          // the copy leaves on the other stream, behind this slice only
+    if (sliced) {                                               // the copy leaves on the other stream, behind this slice only
+      mb::launch_keyswitch(ksk, d_out + (size_t)c0 * w_in, d_mid + (size_t)c0 * w_mid, cc, st);
       cudaEvent_t switched;
       MB_CHECK(cudaEventCreateWithFlags(&switched, cudaEventDisableTiming));
       MB_CHECK(cudaEventRecord(switched, st));

@@ -22,6 +22,11 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active"]
 k = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
 print("kernel:", vals[k] if k is not None else "?", file=out)
+if len(rows) > 3:                                  # several launches captured: one line each, details below are the first one's
+    cols = [hdr.index(h) for h in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum") if h in hdr]
+    for i, r in enumerate(rows[2:]):
+        if len(r) > max(cols):
+            print(f"launch {i}: " + ", ".join(f"{hdr[c]} = {r[c]} {units[c]}" for c in cols), file=out)
 for h, u, v in zip(hdr, units, vals):
     if h in keep:
         print(f"{h:85s} {u:16s} {v}", file=out)
