@@ -258,7 +258,9 @@ def test_keyswitch_bit_exact(golden):
     Pm = gparams(g)
     ksk = api.KeySwitchKey.from_host(Pm, g["ksk"])
     rng = np.random.default_rng(5)
-    for count in (1, 3, 7, 300, 1301):
+    # ... and every slicing regime of the launcher: column chunks (< 10), 16 warps per SM (< 2 per SM), sweep sliced to fill
+    # one wave (up to 2072), one warp per ciphertext, more than one wave
+    for count in (1, 3, 7, 150, 300, 592, 1301, 2072, 2073, 4200):
         ins = rng.integers(0, 2 ** 64, size=(count, Pm.k * Pm.N + 1), dtype=np.uint64)
         ins[0] = g["fb_out"][0]
         got = api.ks_host(ksk, ins)
@@ -411,6 +413,30 @@ def test_full_size_round_trip(P, count):
     out2 = api.pbs_ks_host(bsk, ksk, tv, out, torus_base)
     dec2 = ((syn.tlwe_phase(out2, lwe_key) + (np.uint64(1) << np.uint64(60))) >> np.uint64(61)).astype(np.int64)
     assert np.array_equal(dec2 % (2 * torus_base), (((msgs * 3 + 1) % torus_base) * 3 + 1) % torus_base)
+    bsk.free()
+    ksk.free()
+
+
+@pytest.mark.parametrize("count", [1900, 2100])
+def test_pipelined_host_paths_equal_the_plain_sequence(count):
+    """From three GPU waves up, mb200_pbs_ks_host and functional_bootstrap_keyswitch_batch overlap copies, two bootstrap
+    launches on two streams and (from 2048 ciphertexts) a key switch in four sliced quarters.  Same kernels on the same
+    words: the results must equal bootstrap-then-key-switch of the whole batch bit for bit (flat buffers here; the handle
+    arrays on reference-made keys in tests/test_fullsize_parity.py)."""
+    P = LEVEL1
+    lwe_key = syn.binary_key(P.n, 301)
+    rlwe_key = syn.binary_key(P.k * P.N, 302)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=31)
+    ksk = api.KeySwitchKey.synthesize(P, rlwe_key, lwe_key, seed=32)
+    msgs = (np.arange(count) * 5 + 2) % 4
+    cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, P.lwe_sigma, seed=33)
+    lut = syn.encode((np.arange(4) * 3 + 1) % 4, 4)
+    tv = syn.test_vector(lut, P.N, P.k)
+    plain = api.ks_host(ksk, api.pbs_host(bsk, tv, cts, 4))
+    piped = api.pbs_ks_host(bsk, ksk, tv, cts, 4)
+    assert np.array_equal(piped, plain)
+    dec = ((syn.tlwe_phase(piped, lwe_key) + (np.uint64(1) << np.uint64(60))) >> np.uint64(61)).astype(np.int64)
+    assert np.array_equal(dec % 8, (msgs * 3 + 1) % 4)
     bsk.free()
     ksk.free()
 
