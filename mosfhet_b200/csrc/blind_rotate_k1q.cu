@@ -511,8 +511,11 @@ __global__ void __launch_bounds__((1 << LOGM) / 4, 512 / ((1 << LOGM) / 4)) blin
     }
     __syncthreads();
     // ---------------------------------- A' + accumulate ----------------------------------------------------------------
-    // (N = 2048: splitting the radix-16 inverse over lane pairs so that all 256 threads work here was measured 4 % SLOWER,
-    // profiles/r2k: +54 % instructions in this phase for the selects, shuffles and extra tensor-memory loads)
+    // (N = 2048: only half of the 256 threads have a row here.  Two ways of employing the other half were measured SLOWER,
+    // because both add work to pipes that the SM's other CTA would otherwise use: the radix-16 inverse split over lane pairs
+    // (+54 % instructions in this phase for selects, shuffles and extra tensor-memory loads: 117.2 vs 112.3 ms, profiles/r2k)
+    // and the outputs split by parity over the two slots of a polynomial (both load and untwiddle all 16 positions, then one
+    // radix-8 inverse each: +18 % instructions in this phase, 114.8 vs 112.2 ms, profiles/r2q))
     if (SLOTS == 2 || slot < 2) {
       const double2 *row = buf + pA * M;
       double2 x[RA];
