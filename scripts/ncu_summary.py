@@ -52,6 +52,13 @@ def op(r):
     t = r[ix["Source"]].split()
     if not t: return ""
     return (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+# a report with several launches repeats the source page once per launch: keep the first copy
+if "Address" in ix:
+    first = data[0][ix["Address"]] if data and len(data[0]) > ix["Address"] else None
+    for i in range(1, len(data)):
+        if len(data[i]) > ix["Address"] and data[i][ix["Address"]] == first:
+            data = data[:i]
+            break
 segs, start = [], 0
 for i, r in enumerate(data):
     if op(r) == "BAR":
