@@ -282,7 +282,8 @@ __device__ __forceinline__ void tmem_ld4(double2 (&v)[4], unsigned taddr) {
 // Key rows are read with the plain read-only load.  The streaming form (ld.global.nc.L1::no_allocate), used while the
 // twiddles still competed for the 28 KB of L1, also leaves the lines first in line for eviction from L2: a single
 // bootstrap then re-reads the whole key from HBM every time once something else has displaced it (2.6 -> 3.4 ms,
-// scripts/latency_after_load.py), and the full batch is 2.3 % slower (profiles/r1p_k1_tmem.log).
+// scripts/latency_after_load.py), and the full batch is 2.3 % slower (profiles/r1p_k1_tmem.log).  Round 2, T = M/4 kernel:
+// no_allocate 0.8 % slower, no_allocate + an L2 evict_last policy the same as the plain load (profiles/r2r_key_load_policy.log).
 __device__ __forceinline__ double2 ldg_key(const double2 *p) { return __ldg(p); }
 
 
