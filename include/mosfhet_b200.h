@@ -329,7 +329,10 @@ void mb200_vertical_packing_batch_dev(mb200_bsk_t bits, uint64_t *d_luts, uint64
 void mb200_torus_to_dft_dev(double *d_out /* [count][N] Re|Im */, const uint64_t *d_in, int N, int count, void *stream);
 void mb200_dft_to_torus_dev(uint64_t *d_out, const double *d_in, int N, int count, void *stream);
 
-/* Host-buffer batch ops: H2D of inputs, kernels, D2H of results, synchronous on return. */
+/* Host-buffer batch ops: H2D of inputs, kernels, D2H of results, synchronous on return.  From three GPU waves of ciphertexts
+ * up, mb200_pbs_ks_host overlaps the copies with the kernels on two streams (first wave launched at once, key switch in four
+ * slices whose results leave while the next is switched) -- effective when the host buffers are pinned (cudaHostAlloc /
+ * cudaHostRegister); with pageable memory the copies are staged by the driver and the call is merely correct. */
 void mb200_pbs_ks_host(mb200_bsk_t bsk, mb200_ksk_t ksk, uint64_t *h_out /* [count][n+1] */,
                        const uint64_t *h_tv, int tv_count, const uint64_t *h_in /* [count][n+1] */,
                        int torus_base, int count);
