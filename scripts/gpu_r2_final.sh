@@ -12,10 +12,14 @@ timeout 900 python bench.py --workload level2 --steps 3 --no-extras 2>gpurun_out
 for WL in level1 level2; do
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_${WL}_launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --workload $WL > gpurun_out/${T}_${WL}_launches_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:blind_rotate_k1q -s 3 -c 3 -f -o gpurun_out/${T}_${WL}_k1q \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:blind_rotate_k1q -s 4 -c 4 -f -o gpurun_out/${T}_${WL}_k1q \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras --workload $WL > gpurun_out/${T}_${WL}_k1q.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:keyswitch -s 1 -c 1 -f -o gpurun_out/${T}_${WL}_ks \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras --workload $WL > gpurun_out/${T}_${WL}_ks.log 2>&1
+  # summarise on the box and drop the reports: gpurun brings back at most 64 MiB
+  python scripts/ncu_summary.py gpurun_out/${T}_${WL}_k1q.ncu-rep gpurun_out/${T}_${WL}_k1q_ncu_summary.txt
+  python scripts/ncu_summary.py gpurun_out/${T}_${WL}_ks.ncu-rep gpurun_out/${T}_${WL}_ks_ncu_summary.txt
+  rm -f gpurun_out/${T}_${WL}_k1q.ncu-rep gpurun_out/${T}_${WL}_ks.ncu-rep
 done
 python - <<'PY'
 import json
