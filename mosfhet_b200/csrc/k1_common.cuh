@@ -1,5 +1,6 @@
 // k1_common.cuh -- register-resident FFT building blocks shared by the k = 1 blind-rotation kernels.
 #pragma once
+#include <mutex>
 #include "common.cuh"
 #include "device_math.cuh"
 #include "w64_constants.cuh"
@@ -12,6 +13,8 @@ static __constant__ double CW64C[64], CW64S[64];   // one copy per translation u
 static __constant__ double CW64T[9];               // tan(2 pi m / 64), m = 0..8 (folded-twiddle butterflies)
 static void upload_w64() {
   static bool done_dev[MB_MAX_DEV] = {false};          // __constant__ memory is per device
+  static std::mutex mu;                                // first calls may come from several host threads at once
+  std::lock_guard<std::mutex> lk(mu);
   bool &done = done_dev[current_device()];
   if (done) return;
   MB_CHECK(cudaMemcpyToSymbol(CW64C, W64C_HOST, sizeof(double) * 64));

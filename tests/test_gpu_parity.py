@@ -417,6 +417,33 @@ def test_full_size_round_trip(P, count):
     ksk.free()
 
 
+def test_entry_points_from_concurrent_host_threads():
+    """entry points may be called from several host threads (streams, staging buffers and the last-kernel
+    name are per thread; the key caches are locked).  Four threads run bootstrap + key switch on different inputs at once
+    over the same resident keys (pipelined and plain paths, full-batch and small-batch kernels); every result must equal
+    the serial one."""
+    from concurrent.futures import ThreadPoolExecutor
+    P = Params(48, 1024, 1, 3, 6, 7, 2)
+    lwe_key, rlwe_key = syn.binary_key(P.n, 401), syn.binary_key(P.k * P.N, 402)
+    bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=41)
+    ksk = api.KeySwitchKey.synthesize(P, rlwe_key, lwe_key, seed=42)
+    lut = syn.encode((np.arange(4) * 3 + 1) % 4, 4)
+    tv = syn.test_vector(lut, P.N, P.k)
+    counts = (700, 2100, 37, 1300)                       # pipelined and plain paths, k1q and the small-batch kernel
+    ins = [syn.tlwe_encrypt(syn.encode((np.arange(c) * 3 + w) % 4, 4), lwe_key, 2.0 ** -30, seed=50 + w) for w, c in enumerate(counts)]
+    serial = [api.pbs_ks_host(bsk, ksk, tv, x, 4).copy() for x in ins]
+    for _ in range(3):
+        with ThreadPoolExecutor(len(ins)) as ex:
+            got = list(ex.map(lambda x: api.pbs_ks_host(bsk, ksk, tv, x, 4).copy(), ins))
+        for a, b in zip(got, serial):
+            assert np.array_equal(a, b)
+    for w, c in enumerate(counts):
+        dec = ((syn.tlwe_phase(serial[w], lwe_key) + (np.uint64(1) << np.uint64(60))) >> np.uint64(61)).astype(np.int64)
+        assert np.array_equal(dec % 8, (((np.arange(c) * 3 + w) % 4) * 3 + 1) % 4)
+    bsk.free()
+    ksk.free()
+
+
 @pytest.mark.parametrize("count", [1900, 2100])
 def test_pipelined_host_paths_equal_the_plain_sequence(count):
     """From three GPU waves up, mb200_pbs_ks_host and functional_bootstrap_keyswitch_batch overlap copies, two bootstrap
