@@ -536,7 +536,7 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   // policy 0: fastest available for the batch size; 1: generic kernel; 2: T = M/8 kernel (k1); 3: T = M/4 latency kernel
   // (k1h); 4: 2-CTA cluster kernel (k1c); 5: T = M/4 throughput kernel (k1q).
   //   full batches   k1q where it has the shape (N = 1024 / 2048; four warps per scheduler), else k1
-  //   small batches  k1h (N <= 1024, batch <= 2 x SMs: half the serial work per thread, profiles/r1j_latency.log) or
+  //   small batches  k1h (N <= 1024, batch <= SMs: half the serial work per thread, profiles/r1j_latency.log, r2t_latency.log) or
   //                  k1c (N > 1024, 2 x batch <= SMs: two SMs per bootstrap, profiles/r1o_latency.log)
   const mb::Params &p = a.bsk->p;
   const int sms = mb::sm_count();
@@ -545,7 +545,8 @@ void run_blind_rotate(const mb::BlindRotateLaunch &a, cudaStream_t st) {
   if (!a.direct) {
     if (g_policy == 0) {
       const bool want_c = env_flag("MB200_K1C", 2 * a.count <= sms && p.N > 1024);
-      const bool want_h = env_flag("MB200_K1H", a.count <= 2 * sms && p.N <= 1024);
+      // (profiles/r2t_latency.log, N = 1024: 148 ciphertexts k1h 2.58 / k1q 2.64 ms, 296 ciphertexts 4.01 / 3.45 ms)
+      const bool want_h = env_flag("MB200_K1H", a.count <= sms && p.N <= 1024);
       // measured (profiles/r2d_k1q_timing.log, 4096 ciphertexts): N = 1024 k1q 40.6 ms vs k1 42.9 ms; N = 2048 120.3 vs 126.4 ms
       const bool want_q = env_flag("MB200_K1Q", true);
       if (want_c && mb::k1c_supported(p)) pick = K1C;

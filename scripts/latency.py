@@ -1,4 +1,4 @@
-"""Small-batch latency of the blind-rotation kernels (k1, k1h, and the 2-CTA cluster kernel k1c)."""
+"""Small-batch latency of the blind-rotation kernels (k1, k1q, k1h, and the 2-CTA cluster kernel k1c)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,14 +10,14 @@ for wl in ("level1", "level2"):
     lwe_key, rlwe_key = syn.binary_key(P.n, 1), syn.binary_key(P.N, 2)
     bsk = api.BootstrapKey.synthesize(P, lwe_key, rlwe_key, seed=3)
     st = torch.cuda.Stream()
-    for B in (1, 16, 74, 148, 296, 444):
+    for B in [int(v) for v in os.environ.get("BATCHES", "1,16,74,148,296,444,592,888,1184").split(",")]:
         msgs = np.arange(B) % 4
         cts = syn.tlwe_encrypt(syn.encode(msgs, 4), lwe_key, P.lwe_sigma, seed=4)
         lut = syn.encode((3 * np.arange(4) + 1) % 4, 4)
         d_in = torch.from_numpy(cts.view(np.int64)).cuda()
         d_tv = torch.from_numpy(syn.test_vector(lut, P.N, 1).view(np.int64)).cuda()
         d_out = torch.empty((B, P.N + 1), dtype=torch.int64, device="cuda")
-        for tag, pol in (("k1", 2), ("k1h", 3), ("k1c", 4), ("auto", 0)):
+        for tag, pol in (("k1", 2), ("k1q", 5), ("k1h", 3), ("k1c", 4), ("auto", 0)):
             api.set_kernel_policy(pol)
             ts = []
             for it in range(4):
